@@ -1,0 +1,468 @@
+// Host side of libso100_b200.so: model narrowing/validation, device allocation, kernel
+// launches behind the C ABI of include/so100_b200.h.  No CPU fallback exists: every entry
+// point either launches the sm_100a kernels or fails with an error code.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/so100_b200.h"
+#include "../../include/so100_model.h"
+
+namespace so100 { constexpr int SO100_NDIAG_K = SO100_NDIAG; }
+#include "so100_kernels.cuh"
+
+using namespace so100;
+
+static_assert(NC == SO100_MAX_CONTACTS, "contact capacity mismatch");
+
+#ifndef SO100_LPE
+#define SO100_LPE 32          // lanes per env (tile width)
+#endif
+constexpr unsigned LPE = SO100_LPE;
+constexpr int BLOCK = 128;
+constexpr int EPB = BLOCK / LPE;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_OK(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail(SO100_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct so100_ctx {
+  int n = 0, device = 0, task = 0;
+  uint64_t seed = 0;
+  int64_t env_offset = 0;
+  float* state = nullptr;
+  DevGeom* geom = nullptr;
+  DevPair* pair = nullptr;
+  float4* vert = nullptr;
+  unsigned long long* diag = nullptr;
+  // staging for the host-buffer entry point
+  float *h_action = nullptr, *h_obs = nullptr, *h_ag = nullptr, *h_dg = nullptr, *h_rew = nullptr, *h_fin = nullptr;
+  uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_succ = nullptr;
+  DevTables tables() const { return DevTables{geom, pair, vert}; }
+};
+
+// ------------------------------------------------------------------ small host math (double)
+namespace {
+struct D3 { double x, y, z; };
+struct DQ { double w, x, y, z; };
+DQ qmul_h(DQ a, DQ b) {
+  return {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+          a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w};
+}
+void q2mat_h(DQ q, double* m) {
+  double w = q.w, x = q.x, y = q.y, z = q.z;
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+D3 rot_h(const double* m, D3 v) {
+  return {m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z};
+}
+double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// frame of body b relative to `root` (an ancestor reached through joint-less bodies): pos + quat
+bool rel_frame(const so100_model& m, int b, int root, D3& pos, DQ& q) {
+  pos = {0, 0, 0}; q = {1, 0, 0, 0};
+  while (b != root) {
+    if (b <= 0 || m.body_jtype[b] >= 0) return false;
+    double R[9];
+    DQ qb = {m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]};
+    q2mat_h(qb, R);
+    D3 p = rot_h(R, pos);
+    pos = {m.body_pos[b][0] + p.x, m.body_pos[b][1] + p.y, m.body_pos[b][2] + p.z};
+    q = qmul_h(qb, q);
+    b = m.body_parent[b];
+  }
+  return true;
+}
+}  // namespace
+
+// Narrow the packed fp64 model to the kernel's specialised float32 tables.
+static int build_dev_model(const so100_model& m, DevModel& dm, std::vector<DevGeom>& geoms, std::vector<DevPair>& pairs,
+                           std::vector<float4>& verts) {
+  memset(&dm, 0, sizeof(dm));
+  if (m.nv != NV || m.nq != NQ || m.nu != NL) return fail(SO100_ERR_MODEL, "kernel is specialised for nq=13 nv=12 nu=6");
+  if (m.ngeom != NGEOM || m.npair > NPAIR_MAX || m.npair > 255) return fail(SO100_ERR_MODEL, "geom/pair count does not fit");
+  // chain: hinge bodies in dof order, each the child of the previous one; one free body with dofs 6..11
+  int link_body[NL], cube_body = -1, link_of_body[SO100_MAXBODY];
+  for (int b = 0; b < SO100_MAXBODY; b++) link_of_body[b] = -2;
+  for (int l = 0; l < NL; l++) link_body[l] = -1;
+  for (int b = 1; b < m.nbody; b++) {
+    if (m.body_jtype[b] == SO100_JNT_HINGE) {
+      int d = m.body_dofadr[b];
+      if (d < 0 || d >= NL || m.body_qposadr[b] != d) return fail(SO100_ERR_MODEL, "hinge dofs must be 0..5");
+      link_body[d] = b; link_of_body[b] = d;
+    } else if (m.body_jtype[b] == SO100_JNT_FREE) {
+      if (m.body_dofadr[b] != NL || m.body_qposadr[b] != NL || m.body_parent[b] != 0) return fail(SO100_ERR_MODEL, "free body must own dofs 6..11");
+      cube_body = b; link_of_body[b] = NL;
+    }
+  }
+  if (cube_body < 0) return fail(SO100_ERR_MODEL, "no free body");
+  for (int b = 0; b < m.nbody; b++)
+    if (m.body_weldid[b] == 0) link_of_body[b] = -1;   // static
+  D3 rp; DQ rq;
+  for (int l = 0; l < NL; l++) {
+    int b = link_body[l];
+    if (b < 0) return fail(SO100_ERR_MODEL, "missing hinge link");
+    int parent = m.body_parent[b];
+    if (l == 0) {
+      if (m.body_weldid[parent] != 0) return fail(SO100_ERR_MODEL, "first link must hang off a static body");
+      if (!rel_frame(m, parent, 0, rp, rq)) return fail(SO100_ERR_MODEL, "base frame");
+      dm.base_pos[0] = (float)rp.x; dm.base_pos[1] = (float)rp.y; dm.base_pos[2] = (float)rp.z;
+      dm.base_quat[0] = (float)rq.w; dm.base_quat[1] = (float)rq.x; dm.base_quat[2] = (float)rq.y; dm.base_quat[3] = (float)rq.z;
+    } else if (parent != link_body[l - 1]) {
+      return fail(SO100_ERR_MODEL, "links must form a serial chain");
+    }
+    for (int k = 0; k < 3; k++) {
+      dm.link_pos[l][k] = (float)m.body_pos[b][k];
+      dm.link_axis[l][k] = (float)m.body_jaxis[b][k];
+      dm.link_ipos[l][k] = (float)m.body_ipos[b][k];
+    }
+    for (int k = 0; k < 4; k++) dm.link_quat[l][k] = (float)m.body_quat[b][k];
+    dm.link_mass[l] = (float)m.body_mass[b];
+    // body-frame inertia tensor Ri diag Ri^T
+    double Ri[9], I[9];
+    q2mat_h({m.body_iquat[b][0], m.body_iquat[b][1], m.body_iquat[b][2], m.body_iquat[b][3]}, Ri);
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += Ri[r * 3 + k] * m.body_inertia[b][k] * Ri[c * 3 + k];
+        I[r * 3 + c] = s;
+      }
+    dm.link_Ib[l][0] = (float)I[0]; dm.link_Ib[l][1] = (float)I[1]; dm.link_Ib[l][2] = (float)I[2];
+    dm.link_Ib[l][3] = (float)I[4]; dm.link_Ib[l][4] = (float)I[5]; dm.link_Ib[l][5] = (float)I[8];
+    dm.armature[l] = (float)m.dof_armature[l];
+    dm.lim_lo[l] = m.dof_limited[l] ? (float)m.dof_range[l][0] : -1e30f;
+    dm.lim_hi[l] = m.dof_limited[l] ? (float)m.dof_range[l][1] : 1e30f;
+    dm.lim_invw[l] = (float)m.dof_invweight0[l];
+    if (m.act_dof[l] != l) return fail(SO100_ERR_MODEL, "actuator a must drive dof a");
+    dm.kp[l] = (float)m.act_kp[l]; dm.kv[l] = (float)m.act_kv[l];
+    dm.ctrl_lo[l] = (float)m.act_ctrlrange[l][0]; dm.ctrl_hi[l] = (float)m.act_ctrlrange[l][1];
+    dm.frc_lo[l] = (float)m.act_forcerange[l][0]; dm.frc_hi[l] = (float)m.act_forcerange[l][1];
+    dm.start_pose[l] = (float)m.start_pose[l];
+    dm.act_lo[l] = (float)m.act_lo[l]; dm.act_hi[l] = (float)m.act_hi[l];
+    dm.act_range[l] = (float)(m.act_hi[l] - m.act_lo[l]);
+  }
+  {
+    int b = cube_body;
+    for (int k = 0; k < 3; k++)
+      if (m.body_ipos[b][k] != 0) return fail(SO100_ERR_MODEL, "free body needs its CoM at the origin");
+    if (fabs(m.body_iquat[b][0]) != 1.0) return fail(SO100_ERR_MODEL, "free body needs a principal-axes frame");
+    dm.cube_mass = (float)m.body_mass[b];
+    for (int k = 0; k < 3; k++) dm.cube_I[k] = (float)m.body_inertia[b][k];
+    for (int d = NL; d < NV; d++)
+      if (m.dof_armature[d] != 0) return fail(SO100_ERR_MODEL, "armature on the free joint");
+  }
+  dm.timestep = (float)m.timestep;
+  dm.gx = (float)m.gravity[0]; dm.gy = (float)m.gravity[1]; dm.gz = (float)m.gravity[2];
+  dm.impratio = (float)m.impratio;
+  dm.inv_scale = (float)(1.0 / (m.meaninertia * NV));
+  dm.nsub = m.nsubstep; dm.npair = m.npair; dm.ngeom = m.ngeom;
+  dm.max_episode_steps = m.max_episode_steps; dm.goal_max_steps = 300; dm.curriculum_steps = m.goal_curriculum_steps;
+  // frictionloss / limit rows: default solref (0.02,1), solimp (0.9,0.95,0.001,0.5,2)
+  const double tc = std::max(0.02, 2 * m.timestep), dmax = 0.95, d0 = 0.9;
+  for (int d = 0; d < NV; d++) {
+    double R = std::max(1e-15, (1 - d0) / d0 * m.dof_invweight0[d]);
+    dm.fr_R[d] = (float)R; dm.fr_D[d] = (float)(1.0 / R); dm.fr_floss[d] = (float)m.dof_frictionloss[d];
+  }
+  dm.fr_B = (float)(2.0 / (dmax * tc));
+  dm.lim_B = dm.fr_B;
+  dm.lim_K = (float)(1.0 / (dmax * dmax * tc * tc));
+  const float dsi[5] = {0.9f, 0.95f, 0.001f, 0.5f, 2.0f};
+  memcpy(dm.lim_solimp, dsi, sizeof(dsi));
+
+  // static body world frames
+  auto world_frame = [&](int b, D3& p, DQ& q) { return rel_frame(m, b, 0, p, q); };
+  // geoms
+  geoms.assign(NGEOM, DevGeom{});
+  verts.clear();
+  for (int g = 0; g < NGEOM; g++) {
+    DevGeom& G = geoms[g];
+    int b = m.geom_body[g];
+    G.link = link_of_body[b];
+    if (G.link == -2) return fail(SO100_ERR_MODEL, "collidable geom on a welded child body");
+    G.mjid = m.geom_mjid[g];
+    G.rbound = (float)m.geom_rbound[g];
+    double Rg[9];
+    q2mat_h({m.geom_quat[g][0], m.geom_quat[g][1], m.geom_quat[g][2], m.geom_quat[g][3]}, Rg);
+    bool ident = fabs(Rg[0] - 1) < 1e-12 && fabs(Rg[4] - 1) < 1e-12 && fabs(Rg[8] - 1) < 1e-12;
+    if (!ident) return fail(SO100_ERR_MODEL, "geom frames must be aligned with their body");
+    for (int k = 0; k < 3; k++) { G.center[k] = (float)m.geom_center[g][k]; G.half[k] = (float)m.geom_half[g][k]; }
+    G.boxlike = m.geom_type[g] == SO100_GEOM_BOX;
+    G.vadr = (int)verts.size(); G.vnum = m.geom_vnum[g];
+    if (m.geom_type[g] == SO100_GEOM_MESH) {
+      int hits = 0;
+      for (int v = 0; v < G.vnum; v++) {
+        const double* p = m.vert[m.geom_vadr[g] + v];
+        verts.push_back(make_float4((float)p[0], (float)p[1], (float)p[2], 0.0f));
+        bool corner = true;
+        for (int k = 0; k < 3; k++) corner = corner && fabs(fabs(p[k] - m.geom_center[g][k]) - m.geom_half[g][k]) < 1e-9;
+        hits += corner;
+      }
+      if (G.vnum == 8 && hits == 8) G.boxlike = 1;   // exact cuboid hull (the table): same support map as a box
+    }
+    if (G.link < 0) {
+      if (!world_frame(b, rp, rq)) return fail(SO100_ERR_MODEL, "static geom frame");
+      double Rw[9];
+      q2mat_h(rq, Rw);
+      D3 c = rot_h(Rw, {m.geom_center[g][0], m.geom_center[g][1], m.geom_center[g][2]});
+      G.center[0] = (float)(rp.x + c.x); G.center[1] = (float)(rp.y + c.y); G.center[2] = (float)(rp.z + c.z);
+      for (int k = 0; k < 9; k++) G.wmat[k] = (float)Rw[k];
+    }
+  }
+  // pairs
+  pairs.assign(m.npair, DevPair{});
+  for (int p = 0; p < m.npair; p++) {
+    DevPair& P = pairs[p];
+    P.g1 = m.pair_g1[p]; P.g2 = m.pair_g2[p]; P.dim = m.pair_condim[p];
+    const bool box1 = m.geom_type[P.g1] == SO100_GEOM_BOX, box2 = m.geom_type[P.g2] == SO100_GEOM_BOX;
+    if (geoms[P.g1].boxlike && geoms[P.g2].boxlike) P.mode = (box1 && box2) ? MODE_BOX_MULTI : MODE_BOX_SINGLE;
+    else P.mode = MODE_HULL;
+    P.f0 = (float)m.pair_friction[p][0]; P.f1 = (float)m.pair_friction[p][1];
+    double si[5];
+    for (int k = 0; k < 5; k++) si[k] = m.pair_solimp[p][k];
+    si[0] = clampd(si[0], 1e-4, 0.9999); si[1] = clampd(si[1], 1e-4, 0.9999); si[2] = std::max(0.0, si[2]);
+    si[3] = clampd(si[3], 1e-4, 0.9999); si[4] = std::max(1.0, si[4]);
+    for (int k = 0; k < 5; k++) P.solimp[k] = (float)si[k];
+    double tcp = m.pair_solref[p][0], dr = m.pair_solref[p][1];
+    if (tcp <= 0) return fail(SO100_ERR_MODEL, "direct solref (negative) is not supported");
+    tcp = std::max(tcp, 2 * m.timestep);
+    P.K = (float)(1.0 / std::max(1e-15, si[1] * si[1] * tcp * tcp * dr * dr));
+    P.B = (float)(2.0 / std::max(1e-15, si[1] * tcp));
+    int b1 = m.geom_body[P.g1], b2 = m.geom_body[P.g2];
+    P.dtran = (float)(m.body_invweight0[b1][0] + m.body_invweight0[b2][0]);
+    P.drot = (float)(m.body_invweight0[b1][1] + m.body_invweight0[b2][1]);
+  }
+  // sites
+  auto site_in_link = [&](int s, int& link, D3& p) {
+    int b = m.site_body[s];
+    D3 sp = {m.site_pos[s][0], m.site_pos[s][1], m.site_pos[s][2]};
+    int root = b;
+    while (root > 0 && m.body_jtype[root] < 0) root = m.body_parent[root];
+    D3 bp; DQ bq;
+    if (!rel_frame(m, b, root, bp, bq)) return false;
+    double R[9];
+    q2mat_h(bq, R);
+    D3 r = rot_h(R, sp);
+    p = {bp.x + r.x, bp.y + r.y, bp.z + r.z};
+    link = root == 0 ? -1 : link_of_body[root];
+    return true;
+  };
+  int lk; D3 sp;
+  if (!site_in_link(m.site_ee, lk, sp) || lk != 4) return fail(SO100_ERR_MODEL, "ee_site must ride on link 4 (Fixed_Jaw)");
+  dm.ee_off[0] = (float)sp.x; dm.ee_off[1] = (float)sp.y; dm.ee_off[2] = (float)sp.z;
+  if (!site_in_link(m.site_cube, lk, sp) || lk != NL) return fail(SO100_ERR_MODEL, "cube_site must ride on the free body");
+  dm.cube_site_off[0] = (float)sp.x; dm.cube_site_off[1] = (float)sp.y; dm.cube_site_off[2] = (float)sp.z;
+  if (!site_in_link(m.site_bin, lk, sp) || lk != -1) return fail(SO100_ERR_MODEL, "bin_center must be static");
+  const double bc[3] = {sp.x, sp.y, sp.z};
+  for (int k = 0; k < 3; k++) dm.bin_center[k] = (float)bc[k];
+  // single_arm.py:64-75 in float64
+  dm.bin_min[0] = bc[0] - m.bin_hw; dm.bin_min[1] = bc[1] - m.bin_hw; dm.bin_min[2] = bc[2] + 0.0;
+  dm.bin_max[0] = bc[0] + m.bin_hw; dm.bin_max[1] = bc[1] + m.bin_hw; dm.bin_max[2] = bc[2] + m.bin_h;
+  for (int k = 0; k < 3; k++) {
+    dm.box_lo[k] = (float)m.box_lo[k];
+    dm.box_range[k] = (float)m.box_hi[k] - (float)m.box_lo[k];
+    dm.bin_goal_lo[k] = (float)m.bin_goal_lo[k]; dm.bin_goal_hi[k] = (float)m.bin_goal_hi[k];
+  }
+  dm.cube_half = (float)m.cube_half; dm.goal_threshold = (float)m.goal_threshold;
+  dm.lift_xy = (float)m.lift_goal_xy; dm.lift_zlo = (float)m.lift_goal_zlo; dm.lift_zhi = (float)m.lift_goal_zhi;
+  dm.cg_cube = m.cg_cube; dm.cg_table = m.cg_table; dm.pad_mask = m.pad_mask;
+  return SO100_OK;
+}
+
+// ------------------------------------------------------------------ launches
+static size_t smem_bytes() { return (size_t)EPB * sizeof(EnvS); }
+static int grid_for(int n) { return (n + EPB - 1) / EPB; }
+
+static int configure_kernels() {
+  static bool done = false;
+  if (done) return SO100_OK;
+  const int bytes = (int)smem_bytes();
+  CUDA_OK(cudaFuncSetAttribute(step_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(reset_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(substeps_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(forward_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done = true;
+  return SO100_OK;
+}
+
+extern "C" {
+
+const char* so100_last_error(void) { return g_err.c_str(); }
+
+int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device, int task, uint64_t seed,
+                 int64_t env_offset, so100_handle* out) {
+  if (!model_blob || !out || num_envs <= 0) return fail(SO100_ERR_ARG, "so100_create: bad argument");
+  if (nbytes != sizeof(so100_model)) return fail(SO100_ERR_ARG, "so100_create: model blob has the wrong size");
+  if (task != SO100_TASK_CUBE_TO_BIN && task != SO100_TASK_GOAL) return fail(SO100_ERR_ARG, "so100_create: unknown task");
+  so100_model m;
+  memcpy(&m, model_blob, sizeof(m));
+  if (m.magic != SO100_MODEL_MAGIC || m.version != SO100_MODEL_VERSION) return fail(SO100_ERR_ARG, "so100_create: model magic/version mismatch");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0)
+    return fail(SO100_ERR_CUDA, "so100_create: no CUDA device available (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(SO100_ERR_ARG, "so100_create: bad device index");
+  CUDA_OK(cudaSetDevice(device));
+  DevModel dm;
+  std::vector<DevGeom> geoms;
+  std::vector<DevPair> pairs;
+  std::vector<float4> verts;
+  int rc = build_dev_model(m, dm, geoms, pairs, verts);
+  if (rc) return rc;
+  rc = configure_kernels();
+  if (rc) return rc;
+  so100_ctx* h = new so100_ctx();
+  h->n = num_envs; h->device = device; h->task = task; h->seed = seed; h->env_offset = env_offset;
+  CUDA_OK(cudaMemcpyToSymbol(c_m, &dm, sizeof(dm)));
+  CUDA_OK(cudaMalloc(&h->state, (size_t)num_envs * STATE_WORDS * sizeof(float)));
+  CUDA_OK(cudaMalloc(&h->geom, geoms.size() * sizeof(DevGeom)));
+  CUDA_OK(cudaMalloc(&h->pair, pairs.size() * sizeof(DevPair)));
+  CUDA_OK(cudaMalloc(&h->vert, std::max<size_t>(verts.size(), 1) * sizeof(float4)));
+  CUDA_OK(cudaMalloc(&h->diag, SO100_NDIAG * sizeof(unsigned long long)));
+  CUDA_OK(cudaMemcpy(h->geom, geoms.data(), geoms.size() * sizeof(DevGeom), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(h->pair, pairs.data(), pairs.size() * sizeof(DevPair), cudaMemcpyHostToDevice));
+  if (!verts.empty()) CUDA_OK(cudaMemcpy(h->vert, verts.data(), verts.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  const int total = num_envs * STATE_WORDS;
+  init_state_kernel<<<(total + 255) / 256, 256>>>(h->state, num_envs);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  *out = h;
+  return SO100_OK;
+}
+
+int so100_destroy(so100_handle h) {
+  if (!h) return SO100_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->state); cudaFree(h->geom); cudaFree(h->pair); cudaFree(h->vert); cudaFree(h->diag);
+  cudaFree(h->h_action); cudaFree(h->h_obs); cudaFree(h->h_ag); cudaFree(h->h_dg); cudaFree(h->h_rew); cudaFree(h->h_fin);
+  cudaFree(h->h_term); cudaFree(h->h_trunc); cudaFree(h->h_succ);
+  delete h;
+  return SO100_OK;
+}
+
+int so100_num_envs(so100_handle h) { return h ? h->n : SO100_ERR_ARG; }
+
+int so100_reset(so100_handle h, const uint8_t* mask, const float* box_pose, float* obs, float* achieved, float* desired,
+                void* stream) {
+  if (!h) return fail(SO100_ERR_ARG, "so100_reset: null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  reset_kernel<LPE><<<grid_for(h->n), BLOCK, smem_bytes(), st>>>(h->state, mask, box_pose, obs, achieved, desired, h->n, h->task,
+                                                                (uint32_t)h->seed, (uint32_t)(h->seed >> 32), h->env_offset,
+                                                                h->tables());
+  CUDA_OK(cudaGetLastError());
+  return SO100_OK;
+}
+
+int so100_step(so100_handle h, const float* action, int autoreset, float* obs, float* achieved, float* desired, float* reward,
+               uint8_t* terminated, uint8_t* truncated, uint8_t* success, float* final_obs, void* stream) {
+  if (!h || !action) return fail(SO100_ERR_ARG, "so100_step: null handle or action");
+  StepArgs A;
+  A.state = h->state; A.action = action; A.obs = obs; A.achieved = achieved; A.desired = desired; A.reward = reward;
+  A.final_obs = final_obs; A.terminated = terminated; A.truncated = truncated; A.success = success;
+  A.n = h->n; A.autoreset = autoreset; A.task = h->task;
+  A.seed_lo = (uint32_t)h->seed; A.seed_hi = (uint32_t)(h->seed >> 32); A.env_offset = h->env_offset;
+  step_kernel<LPE><<<grid_for(h->n), BLOCK, smem_bytes(), (cudaStream_t)stream>>>(A, h->tables());
+  CUDA_OK(cudaGetLastError());
+  return SO100_OK;
+}
+
+int so100_step_host(so100_handle h, const float* action, int autoreset, float* obs, float* achieved, float* desired,
+                    float* reward, uint8_t* terminated, uint8_t* truncated, uint8_t* success, float* final_obs, void* stream) {
+  if (!h || !action) return fail(SO100_ERR_ARG, "so100_step_host: null handle or action");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = h->n;
+  if (!h->h_action) {
+    CUDA_OK(cudaMalloc(&h->h_action, n * 6 * sizeof(float)));
+    CUDA_OK(cudaMalloc(&h->h_obs, n * 15 * sizeof(float)));
+    CUDA_OK(cudaMalloc(&h->h_fin, n * 15 * sizeof(float)));
+    CUDA_OK(cudaMalloc(&h->h_ag, n * 3 * sizeof(float)));
+    CUDA_OK(cudaMalloc(&h->h_dg, n * 3 * sizeof(float)));
+    CUDA_OK(cudaMalloc(&h->h_rew, n * sizeof(float)));
+    CUDA_OK(cudaMalloc(&h->h_term, n));
+    CUDA_OK(cudaMalloc(&h->h_trunc, n));
+    CUDA_OK(cudaMalloc(&h->h_succ, n));
+  }
+  CUDA_OK(cudaMemcpyAsync(h->h_action, action, n * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = so100_step(h, h->h_action, autoreset, h->h_obs, achieved ? h->h_ag : nullptr, desired ? h->h_dg : nullptr,
+                      reward ? h->h_rew : nullptr, terminated ? h->h_term : nullptr, truncated ? h->h_trunc : nullptr,
+                      success ? h->h_succ : nullptr, final_obs ? h->h_fin : nullptr, stream);
+  if (rc) return rc;
+  if (obs) CUDA_OK(cudaMemcpyAsync(obs, h->h_obs, n * 15 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (final_obs) CUDA_OK(cudaMemcpyAsync(final_obs, h->h_fin, n * 15 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (achieved) CUDA_OK(cudaMemcpyAsync(achieved, h->h_ag, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (desired) CUDA_OK(cudaMemcpyAsync(desired, h->h_dg, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (reward) CUDA_OK(cudaMemcpyAsync(reward, h->h_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (terminated) CUDA_OK(cudaMemcpyAsync(terminated, h->h_term, n, cudaMemcpyDeviceToHost, st));
+  if (truncated) CUDA_OK(cudaMemcpyAsync(truncated, h->h_trunc, n, cudaMemcpyDeviceToHost, st));
+  if (success) CUDA_OK(cudaMemcpyAsync(success, h->h_succ, n, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return SO100_OK;
+}
+
+int so100_compute_reward(const float* achieved, const float* desired, int64_t n, float threshold, float* reward, void* stream) {
+  if (!achieved || !desired || !reward || n < 0) return fail(SO100_ERR_ARG, "so100_compute_reward: bad argument");
+  if (n == 0) return SO100_OK;
+  compute_reward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(achieved, desired, n, threshold, reward);
+  CUDA_OK(cudaGetLastError());
+  return SO100_OK;
+}
+
+static int state_io(so100_handle h, int dir, float* qpos, float* qvel, float* ctrl, float* warm, float* goal, int32_t* sc,
+                    int32_t* ts, uint32_t* ep, void* stream) {
+  if (!h) return fail(SO100_ERR_ARG, "state io: null handle");
+  const int total = h->n * STATE_WORDS;
+  state_io_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, h->n, dir, qpos, qvel, ctrl, warm, goal, sc, ts, ep);
+  CUDA_OK(cudaGetLastError());
+  return SO100_OK;
+}
+int so100_get_state(so100_handle h, float* qpos, float* qvel, float* ctrl, float* warm, void* stream) {
+  return state_io(h, 0, qpos, qvel, ctrl, warm, nullptr, nullptr, nullptr, nullptr, stream);
+}
+int so100_set_state(so100_handle h, const float* qpos, const float* qvel, const float* ctrl, const float* warm, void* stream) {
+  return state_io(h, 1, (float*)qpos, (float*)qvel, (float*)ctrl, (float*)warm, nullptr, nullptr, nullptr, nullptr, stream);
+}
+int so100_get_aux(so100_handle h, float* goal, int32_t* step_count, int32_t* total_steps, uint32_t* episode, void* stream) {
+  return state_io(h, 0, nullptr, nullptr, nullptr, nullptr, goal, step_count, total_steps, episode, stream);
+}
+int so100_set_aux(so100_handle h, const float* goal, const int32_t* step_count, const int32_t* total_steps,
+                  const uint32_t* episode, void* stream) {
+  return state_io(h, 1, nullptr, nullptr, nullptr, nullptr, (float*)goal, (int32_t*)step_count, (int32_t*)total_steps,
+                  (uint32_t*)episode, stream);
+}
+
+int so100_substeps(so100_handle h, int nsub, void* stream) {
+  if (!h || nsub < 0) return fail(SO100_ERR_ARG, "so100_substeps: bad argument");
+  substeps_kernel<LPE><<<grid_for(h->n), BLOCK, smem_bytes(), (cudaStream_t)stream>>>(h->state, h->n, nsub, h->tables());
+  CUDA_OK(cudaGetLastError());
+  return SO100_OK;
+}
+
+int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom, float* con_data, float* sites, void* stream) {
+  if (!h) return fail(SO100_ERR_ARG, "so100_forward: null handle");
+  forward_kernel<LPE><<<grid_for(h->n), BLOCK, smem_bytes(), (cudaStream_t)stream>>>(h->state, h->n, qacc, ncon, con_geom, con_data,
+                                                                                     sites, h->tables());
+  CUDA_OK(cudaGetLastError());
+  return SO100_OK;
+}
+
+int so100_diagnostics(so100_handle h, int64_t* out8, void* stream) {
+  if (!h || !out8) return fail(SO100_ERR_ARG, "so100_diagnostics: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_OK(cudaMemsetAsync(h->diag, 0, SO100_NDIAG * sizeof(unsigned long long), st));
+  diag_reduce_kernel<<<148, 256, 0, st>>>(h->state, h->n, h->diag);
+  CUDA_OK(cudaGetLastError());
+  unsigned long long tmp[SO100_NDIAG];
+  CUDA_OK(cudaMemcpyAsync(tmp, h->diag, sizeof(tmp), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  for (int k = 0; k < SO100_NDIAG; k++) out8[k] = (int64_t)tmp[k];
+  return SO100_OK;
+}
+
+}  // extern "C"

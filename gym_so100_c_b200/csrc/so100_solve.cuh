@@ -1,0 +1,496 @@
+// Constraint rows + primal Newton solver with elliptic cones + semi-implicit Euler
+// (SURVEY.md Appendix A steps 7-9), one tile per env.  Row ownership:
+//   lane d < 12      dof d: its frictionloss row and (d < 6) its joint-limit row, kept in registers
+//   lane c (strided) contact c: impedance, cone state, per-iteration jar / jv in registers
+//   lane e (strided) packed Hessian entry e of the 12x12 lower triangle
+// The dense contact Jacobian J (<= 4 rows x 12 per contact) lives in shared memory.
+#pragma once
+#include "so100_step.cuh"
+
+namespace so100 {
+
+constexpr int S_DIAG = 49;   // per-env diagnostic counters inside the state record (uint32 words 49..56)
+constexpr int NEWTON_MAXIT = 50;   // MuJoCo: 100; warm-started solves need 1-3
+constexpr int LS_MAXIT = 10;
+
+__device__ __forceinline__ float impedance(const float* si, float dist) {
+  if (si[0] == si[1] || si[2] <= 1e-15f) return 0.5f * (si[0] + si[1]);
+  float x = fabsf(dist) / si[2];
+  if (x >= 1.0f) return si[1];
+  if (x <= 0.0f) return si[0];
+  float y, p = si[4], mid = si[3];
+  if (p == 1.0f) y = x;
+  else if (x <= mid) y = __powf(x, p) / __powf(mid, p - 1.0f);
+  else y = 1.0f - __powf(1.0f - x, p) / __powf(1.0f - mid, p - 1.0f);
+  return si[0] + y * (si[1] - si[0]);
+}
+
+// mju_makeFrame: tangents of a unit normal
+__device__ __forceinline__ void make_frame(V3 n, V3& t1, V3& t2) {
+  V3 y = (n.y < 0.5f && n.y > -0.5f) ? mk(0, 1, 0) : mk(0, 0, 1);
+  y = y - n * dot(n, y);
+  t1 = normalized(y);
+  t2 = cross(n, t1);
+}
+
+__device__ __forceinline__ void untri(int e, int& i, int& j) {
+  i = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+  if (tri(i + 1, 0) <= e) i++;
+  if (tri(i, 0) > e) i--;
+  j = e - tri(i, 0);
+}
+
+// ------------------------------------------------------------------ contact rows
+template <unsigned LPE> __device__ void make_contact_rows(const Tile<LPE>& t, EnvS* S, const DevTables& T) {
+  const int lane = t.thread_rank();
+  const int ncon = min(S->ncon, NC);
+  const float rs_imp = rsqrtf(fmaxf(c_m.impratio, 1e-15f));
+  for (int c = lane; c < ncon; c += LPE) {
+    const DevPair& P = T.pair[S->cpair[c]];
+    float dist = S->cdist[c];
+    float imp = impedance(P.solimp, dist);
+    float R0 = fmaxf((1.0f - imp) / imp * P.dtran, 1e-15f);
+    float R1 = R0 / fmaxf(c_m.impratio, 1e-15f);
+    S->cD[c][0] = 1.0f / R0;
+    S->cD[c][1] = 1.0f / R1;
+    S->cD[c][2] = 1.0f / R1;
+    S->cD[c][3] = (P.f1 * P.f1) / (R1 * P.f0 * P.f0);
+    S->cmu[c] = P.f0 * rs_imp;                 // friction[0] * sqrt(R1 / R0)
+    S->caref[c][0] = -P.K * imp * dist;
+    S->caref[c][1] = S->caref[c][2] = S->caref[c][3] = 0.0f;
+  }
+  for (int it = lane; it < ncon * NV; it += LPE) {
+    const int c = it / NV, d = it - c * NV;
+    const DevPair& P = T.pair[S->cpair[c]];
+    const int l1 = T.geom[P.g1].link, l2 = T.geom[P.g2].link;
+    V3 n = ld3(S->cnrm[c]), t1, t2, pos = ld3(S->cpos[c]);
+    make_frame(n, t1, t2);
+    V3 jp = mk(0, 0, 0), jr = mk(0, 0, 0);
+    if (d < NL) {
+      float s = ((l2 >= d && l2 < NL) ? 1.0f : 0.0f) - ((l1 >= d && l1 < NL) ? 1.0f : 0.0f);
+      if (s != 0.0f) {
+        V3 ax = ld3(S->axis[d]);
+        jr = ax * s;
+        jp = cross(ax, pos - ld3(S->lpos[d])) * s;
+      }
+    } else {
+      float s = (l2 == NL ? 1.0f : 0.0f) - (l1 == NL ? 1.0f : 0.0f);
+      if (s != 0.0f) {
+        const int k = d - NL;
+        if (k < 3) {
+          jp = mk(k == 0 ? s : 0.0f, k == 1 ? s : 0.0f, k == 2 ? s : 0.0f);
+        } else {
+          V3 col = mcol(S->lmat[NL], k - 3);
+          jr = col * s;
+          jp = cross(col, pos - ld3(S->lpos[NL])) * s;
+        }
+      }
+    }
+    S->w.J[c * 4 + 0][d] = dot(n, jp);
+    S->w.J[c * 4 + 1][d] = dot(t1, jp);
+    S->w.J[c * 4 + 2][d] = dot(t2, jp);
+    S->w.J[c * 4 + 3][d] = P.dim > 3 ? dot(n, jr) : 0.0f;
+  }
+  t.sync();
+  for (int it = lane; it < ncon * 4; it += LPE) {
+    const int c = it >> 2, k = it & 3;
+    const DevPair& P = T.pair[S->cpair[c]];
+    float v = 0;
+#pragma unroll
+    for (int d = 0; d < NV; d++) v = fmaf(S->w.J[it][d], S->st[S_QVEL + d], v);
+    S->caref[c][k] -= P.B * v;
+  }
+  t.sync();
+}
+
+// elliptic cone: cost, force and (optionally) the 4x4 Hessian block, packed lower triangle
+template <bool HESS>
+__device__ __forceinline__ float cone_eval(const float* x, const float* D, float mu, float f0, float f1, int dim,
+                                           float* force, int& zone, float* Hc) {
+  const float fr[3] = {f0, f0, f1};
+  float U[4];
+  U[0] = x[0] * mu;
+  float TT = 0;
+#pragma unroll
+  for (int j = 1; j < 4; j++) { U[j] = (j < dim) ? x[j] * fr[j - 1] : 0.0f; TT = fmaf(U[j], U[j], TT); }
+  const float Tn = sqrtf(TT), N = U[0];
+  if (N >= mu * Tn || (Tn <= 0.0f && N >= 0.0f)) {
+    zone = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) force[j] = 0.0f;
+    return 0.0f;
+  }
+  if (mu * N + Tn <= 0.0f || (Tn <= 0.0f && N < 0.0f)) {
+    zone = 1;
+    float cost = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float dj = (j < dim) ? D[j] : 0.0f;
+      cost = fmaf(0.5f * dj * x[j], x[j], cost);
+      force[j] = -dj * x[j];
+    }
+    if (HESS) {
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++) Hc[tri(a, b)] = (a == b && a < dim) ? D[a] : 0.0f;
+    }
+    return cost;
+  }
+  zone = 2;
+  const float Dm = D[0] / fmaxf(mu * mu * (1.0f + mu * mu), 1e-15f);
+  const float NmT = N - mu * Tn, invT = 1.0f / Tn;
+  force[0] = -Dm * NmT * mu;
+#pragma unroll
+  for (int j = 1; j < 4; j++) force[j] = (j < dim) ? -force[0] * invT * U[j] * fr[j - 1] : 0.0f;
+  if (HESS) {
+    float g[4], wv[4];
+    g[0] = mu; wv[0] = 0;
+#pragma unroll
+    for (int j = 1; j < 4; j++) { wv[j] = (j < dim) ? fr[j - 1] * U[j] : 0.0f; g[j] = -mu * wv[j] * invT; }
+    const float k1 = -NmT * mu * invT, k2 = NmT * mu * invT * invT * invT;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b <= a; b++) {
+        float h = g[a] * g[b];
+        if (a > 0 && b > 0) {
+          h += k2 * wv[a] * wv[b];
+          if (a == b && a < dim) h += k1 * fr[a - 1] * fr[a - 1];
+        }
+        Hc[tri(a, b)] = Dm * h;
+      }
+  }
+  return 0.5f * Dm * NmT * NmT;
+}
+
+// first / second directional derivative of the cone cost along x + alpha v
+__device__ __forceinline__ void cone_ls(const double* x0, const float* v, float alpha, const float* D, float mu,
+                                        float f0, float f1, int dim, float& d1, float& d2) {
+  const float fr[3] = {f0, f0, f1};
+  float x[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) x[j] = (float)fma((double)alpha, (double)v[j], x0[j]);
+  float N = x[0] * mu, Np = v[0] * mu, TT = 0, UV = 0, VV = 0;
+#pragma unroll
+  for (int j = 1; j < 4; j++) {
+    float f = (j < dim) ? fr[j - 1] : 0.0f;
+    float U = x[j] * f, V = v[j] * f;
+    TT = fmaf(U, U, TT); UV = fmaf(U, V, UV); VV = fmaf(V, V, VV);
+  }
+  const float Tn = sqrtf(TT);
+  if (N >= mu * Tn || (Tn <= 0.0f && N >= 0.0f)) return;
+  if (mu * N + Tn <= 0.0f || (Tn <= 0.0f && N < 0.0f)) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float dj = (j < dim) ? D[j] : 0.0f;
+      d1 = fmaf(dj * x[j], v[j], d1);
+      d2 = fmaf(dj * v[j], v[j], d2);
+    }
+    return;
+  }
+  const float Dm = D[0] / fmaxf(mu * mu * (1.0f + mu * mu), 1e-15f);
+  const float Tp = UV / Tn, Tpp = (VV - Tp * Tp) / Tn, NmT = N - mu * Tn, dp = Np - mu * Tp;
+  d1 = fmaf(Dm * NmT, dp, d1);
+  d2 += Dm * (dp * dp - NmT * mu * Tpp);
+}
+
+// ------------------------------------------------------------------ Newton solver
+template <unsigned LPE> struct SolveRegs {
+  static constexpr int CPL = (NC + LPE - 1) / LPE;   // contacts per lane
+  // dof rows
+  float qfs, fr_aref, fr_R, fr_D, fr_fl;
+  float lim_sgn, lim_D, lim_aref;
+  // contact rows
+  double jar[CPL][4];    // J a - aref cancels to ~1e-4 of its terms under stiff contacts: kept in fp64
+  float jv[CPL][4];
+  int dim[CPL];
+  float f0[CPL], f1[CPL];
+};
+
+// cost at S->a (and forces / cone Hessians when HESS); returns the tile-wide total.
+// Per-lane outputs: Ma (dof lanes), dof_force (friction + limit force on dof d).
+template <unsigned LPE, bool HESS>
+__device__ float eval_cost(const Tile<LPE>& t, EnvS* S, SolveRegs<LPE>& r, int ncon, float& Ma, float& dof_force) {
+  const int lane = t.thread_rank();
+  float cost = 0;
+  Ma = 0; dof_force = 0;
+  if (lane < NV) {
+    const float ad = S->a[lane];
+    Ma = mul_M(S, S->a, lane);
+    cost = 0.5f * ad * Ma - ad * r.qfs;
+    // frictionloss row (Huber)
+    float x = ad - r.fr_aref, rf = r.fr_R * r.fr_fl, hd = 0;
+    if (x <= -rf) { cost += r.fr_fl * (-0.5f * rf - x); dof_force = r.fr_fl; }
+    else if (x >= rf) { cost += r.fr_fl * (-0.5f * rf + x); dof_force = -r.fr_fl; }
+    else { cost += 0.5f * r.fr_D * x * x; dof_force = -r.fr_D * x; hd = r.fr_D; }
+    if (r.lim_sgn != 0.0f) {
+      float xl = r.lim_sgn * ad - r.lim_aref;
+      if (xl < 0) { cost += 0.5f * r.lim_D * xl * xl; dof_force += -r.lim_sgn * r.lim_D * xl; hd += r.lim_D; }
+    }
+    if (HESS) S->hdiag[lane] = hd;
+  }
+#pragma unroll
+  for (int s = 0; s < SolveRegs<LPE>::CPL; s++) {
+    const int c = lane + s * LPE;
+    if (c < ncon) {
+      float x[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        double v = -(double)S->caref[c][k];
+#pragma unroll
+        for (int d = 0; d < NV; d++) v = fma((double)S->w.J[c * 4 + k][d], S->ad[d], v);
+        x[k] = (float)v; r.jar[s][k] = v;
+      }
+      float force[4], Hc[10];
+      int zone;
+      cost += cone_eval<HESS>(x, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], force, zone, Hc);
+      if (HESS) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) S->cfrc[c][k] = force[k];
+        S->czone[c] = (unsigned char)zone;
+        if (zone != 0) {
+#pragma unroll
+          for (int k = 0; k < 10; k++) S->cH[c][k] = Hc[k];
+        }
+      }
+    }
+  }
+  return tsum(t, cost);
+}
+
+template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const DevTables& T, float qas_d, uint32_t* diag) {
+  const int lane = t.thread_rank();
+  const int ncon = min(S->ncon, NC);
+  SolveRegs<LPE> r;
+  // ---- dof rows
+  r.qfs = 0; r.fr_aref = 0; r.fr_R = 1; r.fr_D = 0; r.fr_fl = 0; r.lim_sgn = 0; r.lim_D = 0; r.lim_aref = 0;
+  if (lane < NV) {
+    r.qfs = S->qfs[lane];
+    r.fr_R = c_m.fr_R[lane]; r.fr_D = c_m.fr_D[lane]; r.fr_fl = c_m.fr_floss[lane];
+    const float qd = S->st[S_QVEL + lane];
+    r.fr_aref = -c_m.fr_B * qd;
+    if (lane < NL) {
+      const float q = S->st[S_QPOS + lane];
+      float dist = 0;
+      if (q < c_m.lim_lo[lane]) { r.lim_sgn = 1.0f; dist = q - c_m.lim_lo[lane]; }
+      else if (q > c_m.lim_hi[lane]) { r.lim_sgn = -1.0f; dist = c_m.lim_hi[lane] - q; }
+      if (r.lim_sgn != 0.0f) {
+        float imp = impedance(c_m.lim_solimp, dist);
+        float R = fmaxf((1.0f - imp) / imp * c_m.lim_invw[lane], 1e-15f);
+        r.lim_D = 1.0f / R;
+        r.lim_aref = -c_m.lim_B * (r.lim_sgn * qd) - c_m.lim_K * imp * dist;
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < SolveRegs<LPE>::CPL; s++) {
+    const int c = lane + s * LPE;
+    r.dim[s] = 3; r.f0[s] = 1; r.f1[s] = 1;
+    if (c < ncon) {
+      const DevPair& P = T.pair[S->cpair[c]];
+      r.dim[s] = P.dim; r.f0[s] = P.f0; r.f1[s] = P.f1;
+    }
+  }
+  // ---- warm start: previous qacc unless the unconstrained acceleration is cheaper
+  float Ma, dof_force;
+  if (lane < NV) { S->a[lane] = S->st[S_WARM + lane]; S->ad[lane] = (double)S->st[S_WARM + lane]; }
+  t.sync();
+  const float cw = eval_cost<LPE, false>(t, S, r, ncon, Ma, dof_force);
+  t.sync();
+  if (lane < NV) { S->a[lane] = qas_d; S->ad[lane] = (double)qas_d; }
+  t.sync();
+  const float cs = eval_cost<LPE, false>(t, S, r, ncon, Ma, dof_force);
+  t.sync();
+  if (cw < cs) {
+    if (lane < NV) { S->a[lane] = S->st[S_WARM + lane]; S->ad[lane] = (double)S->st[S_WARM + lane]; }
+    t.sync();
+  }
+  int it = 0;
+  bool converged = false, small_step = false;
+  for (; it < NEWTON_MAXIT; it++) {
+    const float cost = eval_cost<LPE, true>(t, S, r, ncon, Ma, dof_force);
+    t.sync();
+    // ---- gradient: M a - qfrc_smooth - J^T f
+    float g = 0, jtf = 0;
+    if (lane < NV) {
+      jtf = dof_force;
+      for (int c = 0; c < ncon; c++) {
+        if (S->czone[c] == 0) continue;
+#pragma unroll
+        for (int k = 0; k < 4; k++) jtf = fmaf(S->w.J[c * 4 + k][lane], S->cfrc[c][k], jtf);
+      }
+      g = Ma - r.qfs - jtf;
+      S->vec[lane] = g;
+    }
+    // float32 stopping rule: MuJoCo's 1e-8 is below the round-off of the cancelling terms, so the
+    // tolerance is 2e-6 relative to their magnitude (|qfrc_smooth| + |J^T f|), scaled like MuJoCo's.
+    const float gnorm = sqrtf(tsum(t, g * g));
+    const float gscale = sqrtf(tsum(t, r.qfs * r.qfs + jtf * jtf));
+    if (gnorm * c_m.inv_scale < 2e-6f * (1.0f + gscale)) { converged = true; break; }
+    // ---- Hessian (packed lower triangle)
+    for (int e = lane; e < 78; e += LPE) {
+      int i, j;
+      untri(e, i, j);
+      float h = 0;
+      if (i < NL) h = S->Marm[e];
+      else if (i == j) h = (i < 9 ? c_m.cube_mass : c_m.cube_I[i - 9]);
+      if (i == j) h += S->hdiag[i];
+      for (int c = 0; c < ncon; c++) {
+        const int zone = S->czone[c];
+        if (zone == 0) continue;
+        const float* Hc = S->cH[c];
+        if (zone == 1) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) h = fmaf(Hc[tri(k, k)] * S->w.J[c * 4 + k][i], S->w.J[c * 4 + k][j], h);
+        } else {
+          float ji[4], jj[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) { ji[k] = S->w.J[c * 4 + k][i]; jj[k] = S->w.J[c * 4 + k][j]; }
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            float tb = 0;
+#pragma unroll
+            for (int a2 = 0; a2 < 4; a2++) tb = fmaf(ji[a2], Hc[a2 >= b ? tri(a2, b) : tri(b, a2)], tb);
+            h = fmaf(tb, jj[b], h);
+          }
+        }
+      }
+      S->u.sol.H[e] = h;
+    }
+    t.sync();
+    // ---- Cholesky in place; diagonal stores 1/L_kk
+    for (int k = 0; k < NV; k++) {
+      const float dk = rsqrtf(fmaxf(S->u.sol.H[tri(k, k)], 1e-20f));
+      t.sync();
+      for (int i = k + lane; i < NV; i += LPE) {
+        if (i == k) S->u.sol.H[tri(k, k)] = dk;
+        else S->u.sol.H[tri(i, k)] *= dk;
+      }
+      t.sync();
+      for (int e = lane; e < 78; e += LPE) {
+        int i, j;
+        untri(e, i, j);
+        if (j > k) S->u.sol.H[e] = fmaf(-S->u.sol.H[tri(i, k)], S->u.sol.H[tri(j, k)], S->u.sol.H[e]);
+      }
+      t.sync();
+    }
+    // ---- p = -H^-1 g  (column-oriented substitutions, lane d holds component d)
+    float x = -g;
+    for (int k = 0; k < NV; k++) {
+      float xk = t.shfl(x, k) * S->u.sol.H[tri(k, k)];
+      if (lane == k) x = xk;
+      else if (lane > k && lane < NV) x = fmaf(-S->u.sol.H[tri(lane, k)], xk, x);
+    }
+    for (int k = NV - 1; k >= 0; k--) {
+      float xk = t.shfl(x, k) * S->u.sol.H[tri(k, k)];
+      if (lane == k) x = xk;
+      else if (lane < k) x = fmaf(-S->u.sol.H[tri(k, lane)], xk, x);
+    }
+    const float pd = (lane < NV) ? x : 0.0f;
+    if (lane < NV) S->vec[lane] = pd;
+    t.sync();
+    // ---- line-search set-up
+    float Mp = 0;
+    if (lane < NV) Mp = mul_M(S, S->vec, lane);
+    const float pMp = tsum(t, pd * Mp);
+    const float pg = tsum(t, pd * (Ma - r.qfs));
+#pragma unroll
+    for (int s = 0; s < SolveRegs<LPE>::CPL; s++) {
+      const int c = lane + s * LPE;
+      if (c < ncon) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          float v = 0;
+#pragma unroll
+          for (int d = 0; d < NV; d++) v = fmaf(S->w.J[c * 4 + k][d], S->vec[d], v);
+          r.jv[s][k] = v;
+        }
+      }
+    }
+    const float xf0 = S->a[lane < NV ? lane : 0] - r.fr_aref, xl0 = r.lim_sgn * S->a[lane < NV ? lane : 0] - r.lim_aref;
+    auto ls_eval = [&](float alpha, float& D1, float& D2) {
+      float d1 = 0, d2 = 0;
+      if (lane < NV) {
+        const float x = fmaf(alpha, pd, xf0), rf = r.fr_R * r.fr_fl;
+        if (x <= -rf) d1 = -r.fr_fl * pd;
+        else if (x >= rf) d1 = r.fr_fl * pd;
+        else { d1 = r.fr_D * x * pd; d2 = r.fr_D * pd * pd; }
+        if (r.lim_sgn != 0.0f) {
+          const float v = r.lim_sgn * pd, xl = fmaf(alpha, v, xl0);
+          if (xl < 0) { d1 = fmaf(r.lim_D * xl, v, d1); d2 = fmaf(r.lim_D * v, v, d2); }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < SolveRegs<LPE>::CPL; s++) {
+        const int c = lane + s * LPE;
+        if (c < ncon) cone_ls(r.jar[s], r.jv[s], alpha, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], d1, d2);
+      }
+      D1 = tsum(t, d1) + pg + alpha * pMp;
+      D2 = tsum(t, d2) + pMp;
+    };
+    // ---- exact line search: safeguarded 1-D Newton on phi'
+    float alpha = 0, d1, d2, lo = 0, hi = -1;
+    ls_eval(0.0f, d1, d2);
+    const float d10 = fabsf(d1);
+    if (!(d1 < 0)) { converged = true; break; }   // no descent left at float32 resolution
+    for (int ls = 0; ls < LS_MAXIT; ls++) {
+      float na = alpha - d1 / d2;
+      if (hi >= 0 && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
+      alpha = na;
+      ls_eval(alpha, d1, d2);
+      if (fabsf(d1) <= 1e-4f * d10) break;
+      if (d1 < 0) lo = alpha; else hi = alpha;
+    }
+    if (lane < NV) {
+      const double na = fma((double)alpha, (double)pd, S->ad[lane]);
+      S->ad[lane] = na; S->a[lane] = (float)na;
+    }
+    t.sync();
+    // predicted decrease 1/2 alpha |phi'(0)| below float32 resolution of the cost: stop (MuJoCo's
+    // "improvement < tolerance" test, made relative because the arithmetic is float32)
+    if (0.5f * alpha * d10 < 1e-9f * (1.0f + fabsf(cost))) { small_step = true; it++; break; }
+  }
+  if (converged == false) {
+    // forces at the last iterate (loop ran out): refresh so cfrc matches S->a
+    eval_cost<LPE, true>(t, S, r, ncon, Ma, dof_force);
+    t.sync();
+  }
+  if (lane == 0 && diag) {
+    diag[1] += (converged || small_step) ? 0u : 1u;
+    diag[5] += (uint32_t)it;
+    diag[6] += 1u;
+    diag[7] += (uint32_t)ncon;
+  }
+}
+
+// ------------------------------------------------------------------ semi-implicit Euler
+template <unsigned LPE> __device__ void integrate(const Tile<LPE>& t, EnvS* S) {
+  const int lane = t.thread_rank();
+  const float h = c_m.timestep;
+  if (lane < NV) {
+    const float a = S->a[lane];
+    S->st[S_QVEL + lane] = fmaf(h, a, S->st[S_QVEL + lane]);
+    S->st[S_WARM + lane] = a;
+  }
+  t.sync();
+  if (lane < 9) {
+    S->st[S_QPOS + lane] = fmaf(h, S->st[S_QVEL + lane], S->st[S_QPOS + lane]);
+  } else if (lane == 9) {
+    V3 w = ld3(&S->st[S_QVEL + 9]);
+    Q4 q = {S->st[S_QPOS + 9], S->st[S_QPOS + 10], S->st[S_QPOS + 11], S->st[S_QPOS + 12]};
+    q = qnormalize(q);
+    const float wn = sqrtf(dot(w, w)), ang = wn * h;
+    if (ang > 0) {
+      float sn, cs;
+      sincosf(0.5f * ang, &sn, &cs);
+      const float k = sn / wn;
+      Q4 dq = {cs, w.x * k, w.y * k, w.z * k};
+      q = qnormalize(qmul(q, dq));
+    }
+    S->st[S_QPOS + 9] = q.w; S->st[S_QPOS + 10] = q.x; S->st[S_QPOS + 11] = q.y; S->st[S_QPOS + 12] = q.z;
+  }
+  t.sync();
+}
+
+}  // namespace so100

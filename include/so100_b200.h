@@ -1,0 +1,116 @@
+/* C ABI of libso100_b200.so -- the B200-native batched replacement for the hot path of
+ * gym_so100's bin-a-cube env:  reset()/step() of SO100Env (task "so100_cube_to_bin") and
+ * SO100GoalEnv, i.e. everything the reference executes between receiving an action and
+ * returning (obs, reward, terminated, truncated, info), for N independent envs at once.
+ *
+ * Plain pointers and sizes only; no torch / CUDA types in the signatures.  Unless a parameter
+ * says "host", pointers are DEVICE pointers on the device given to so100_create and calls are
+ * enqueued on `stream` (a cudaStream_t passed as void*, NULL = legacy default stream) without
+ * any host synchronisation.  Every function returns 0 on success or a negative so100_status;
+ * so100_last_error() describes the last failure on the calling thread.  A handle is not
+ * re-entrant; use one handle (and one process) per GPU.
+ *
+ * Batched layouts (row-major, one row per env):
+ *   action  float32 [N,6]   normalised joint targets in [-1,1]          (env.py:75-77)
+ *   obs     float32 [N,15]  box(3) bin(3) ee(3) qpos(6), "so100_state"  (env.py:137-145)
+ *   achieved/desired float32 [N,3]  GoalEnv goals                        (env.py:360-370)
+ *   reward  float32 [N];  terminated/truncated/success uint8 [N]
+ *   qpos float32 [N,13], qvel [N,12], ctrl [N,6], warm [N,12]  (MuJoCo qpos/qvel/ctrl/qacc_warmstart)
+ */
+#ifndef SO100_B200_H_
+#define SO100_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct so100_ctx* so100_handle;
+
+enum so100_status {
+  SO100_OK = 0,
+  SO100_ERR_ARG = -1,      /* bad argument / model blob */
+  SO100_ERR_CUDA = -2,     /* CUDA runtime error */
+  SO100_ERR_MODEL = -3,    /* model does not fit the compiled kernel specialisation */
+  SO100_ERR_NOMEM = -4
+};
+
+enum so100_task {
+  SO100_TASK_CUBE_TO_BIN = 0,  /* SO100Env(task="so100_cube_to_bin"): staged reward, TimeLimit 700 */
+  SO100_TASK_GOAL = 1          /* SO100GoalEnv: sparse HER reward, truncation at 300 steps       */
+};
+
+#define SO100_MAX_CONTACTS 24   /* per-env contact capacity; overflow is counted in diagnostics */
+#define SO100_NDIAG 8
+
+/* Replaces: SO100Env.__init__/_make_env_task -> mujoco.Physics.from_xml_path + control.Environment
+ * (gym_so100/env.py:29-77, 92-128).  `model_blob` (host) is the packed so100_model
+ * (include/so100_model.h) produced by gym_so100_c_b200.model.pack(); `env_offset` is the global
+ * index of this handle's env 0 (multi-GPU sharding: RNG streams depend on the global index only). */
+int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device, int task,
+                 uint64_t seed, int64_t env_offset, so100_handle* out);
+int so100_destroy(so100_handle h);
+int so100_num_envs(so100_handle h);
+
+/* Replaces: SO100Env.reset / SO100GoalEnv.reset (env.py:148-170, 302-320) incl.
+ * sample_so100_box_pose (utils.py:18-29) and initialize_episode (single_arm.py:299-309).
+ * mask: uint8 [N] or NULL (= all envs).  box_pose: float32 [N,7] (xyz + wxyz) or NULL; NULL draws
+ * the pose on the device (Philox keyed by seed / global env index / episode).  Outputs may be NULL. */
+int so100_reset(so100_handle h, const uint8_t* mask, const float* box_pose, float* obs,
+                float* achieved, float* desired, void* stream);
+
+/* Replaces: SO100Env.step / SO100GoalEnv.step (env.py:172-182, 372-406): before_step
+ * (single_arm.py:33-38), physics.step(10) + trailing mj_step1, get_reward (single_arm.py:322-380),
+ * get_observation / _format_raw_obs.  autoreset != 0 gives SB3-VecEnv semantics (the reference's
+ * consumers, scripts/train_sac.py:294-301): envs that finish are reset in the same call, `obs`
+ * holds the first observation of the new episode and `final_obs` (nullable) the terminal one.
+ * All output pointers except `obs` may be NULL. */
+int so100_step(so100_handle h, const float* action, int autoreset, float* obs, float* achieved,
+               float* desired, float* reward, uint8_t* terminated, uint8_t* truncated,
+               uint8_t* success, float* final_obs, void* stream);
+
+/* Same as so100_step with HOST buffers (pageable or pinned): copies the actions in, steps, copies
+ * the results out and synchronises `stream` before returning -- what a CPU-side caller of the
+ * reference's env.step sees. */
+int so100_step_host(so100_handle h, const float* action, int autoreset, float* obs, float* achieved,
+                    float* desired, float* reward, uint8_t* terminated, uint8_t* truncated,
+                    uint8_t* success, float* final_obs, void* stream);
+
+/* Replaces: SO100GoalEnv.compute_reward on batches (env.py:341-353), used by HER relabelling. */
+int so100_compute_reward(const float* achieved, const float* desired, int64_t n, float threshold,
+                         float* reward, void* stream);
+
+/* MuJoCo data.qpos/qvel/ctrl/qacc_warmstart access (physics.data.*, single_arm.py:46,54,304-307);
+ * also the injection point of the parity tests.  Any pointer may be NULL. */
+int so100_get_state(so100_handle h, float* qpos, float* qvel, float* ctrl, float* warm, void* stream);
+int so100_set_state(so100_handle h, const float* qpos, const float* qvel, const float* ctrl,
+                    const float* warm, void* stream);
+/* goal float32 [N,3]; step_count int32 [N]; total_steps int32 [N]; episode uint32 [N] */
+int so100_get_aux(so100_handle h, float* goal, int32_t* step_count, int32_t* total_steps,
+                  uint32_t* episode, void* stream);
+int so100_set_aux(so100_handle h, const float* goal, const int32_t* step_count,
+                  const int32_t* total_steps, const uint32_t* episode, void* stream);
+
+/* Parity / debug: advance the physics only (`nsub` x mj_step with the stored ctrl). */
+int so100_substeps(so100_handle h, int nsub, void* stream);
+/* Parity / debug: mj_forward on the stored state.  qacc float32 [N,12]; ncon int32 [N];
+ * con_geom int32 [N,SO100_MAX_CONTACTS,2] (MuJoCo geom ids, geom1 first);
+ * con_data float32 [N,SO100_MAX_CONTACTS,11] = dist, pos[3], normal[3], force[4];
+ * sites float32 [N,3,3] = cube_site, bin_center, ee_site.  Any pointer may be NULL. */
+int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom, float* con_data,
+                  float* sites, void* stream);
+
+/* Host counters accumulated on the device since create (synchronises the stream):
+ * [0] contact-capacity overflows, [1] solver runs that hit the iteration cap, [2] non-finite
+ * states forced to reset, [3] episodes finished, [4] successes, [5] total Newton iterations,
+ * [6] total solver runs, [7] total contacts seen. */
+int so100_diagnostics(so100_handle h, int64_t* out8, void* stream);
+
+const char* so100_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SO100_B200_H_ */

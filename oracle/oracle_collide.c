@@ -310,22 +310,25 @@ static int box_box(const double* cA, const double* RA, const double* hA,
     if (sep > 0) return 0;
     if (sep > best_face) { best_face = sep; face_code = k; }
   }
-  double best_edge = -1e300, edge_axis[3] = {0, 0, 0}; int ei = -1, ej = -1;
+  double best_edge = -1e300, best_sel = -1e300, edge_axis[3] = {0, 0, 0}; int ei = -1, ej = -1;
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) {
       double L[3];
       cross3(L, A[i], B[j]);
       double len = norm3(L);
-      if (len < 1e-6) continue;
+      if (len * len < 1e-6) continue;   /* (near-)parallel edges: covered by the face axes */
       scl3(L, L, 1.0 / len);
       double rA = 0, rB = 0;
       for (int k = 0; k < 3; k++) { rA += hA[k] * fabs(dot3(A[k], L)); rB += hB[k] * fabs(dot3(B[k], L)); }
+      /* edge axes are penalised by 2e-6 m / sin(angle): float32 round-off on nearly parallel edges must
+         never beat a face axis in the CUDA path, and the oracle follows the same rule */
       double sep = fabs(dot3(t, L)) - (rA + rB);
       if (sep > 0) return 0;
-      if (sep > best_edge) { best_edge = sep; copy3(edge_axis, L); ei = i; ej = j; }
+      double sel = sep - 2e-6 / len;
+      if (sel > best_sel) { best_sel = sel; best_edge = sep; copy3(edge_axis, L); ei = i; ej = j; }
     }
   /* an edge axis must beat the best face axis by 5% (faces preferred: stable manifolds) */
-  if (ei >= 0 && best_edge * 1.05 > best_face) {
+  if (ei >= 0 && best_sel * 1.05 > best_face) {
     double n[3];
     copy3(n, edge_axis);
     if (dot3(n, t) < 0) scl3(n, n, -1);
@@ -425,6 +428,31 @@ static void add_contact(const so100_model* m, oenv* e, int pair, const double* p
   memset(c->force, 0, sizeof(c->force));
 }
 
+/* box geom, or mesh whose hull vertices are exactly the 8 corners of its bounding box */
+static int is_cuboid(const so100_model* m, int g) {
+  if (m->geom_type[g] == SO100_GEOM_BOX) return 1;
+  if (m->geom_vnum[g] != 8) return 0;
+  for (int v = 0; v < 8; v++)
+    for (int k = 0; k < 3; k++)
+      if (fabs(fabs(m->vert[m->geom_vadr[g] + v][k] - m->geom_center[g][k]) - m->geom_half[g][k]) > 1e-9) return 0;
+  return 1;
+}
+
+/* entry used by the tests to cross-check the two narrow phases on box pairs */
+int so100o_test_box_pair(const double* cA, const double* RA, const double* hA, const double* cB, const double* RB,
+                         const double* hB, double* sat_out /* n[3], depth */, double* epa_out /* n[3], depth */) {
+  double cpos[8][3], cdist[8], normal[3];
+  int nc = box_box(cA, RA, hA, cB, RB, hB, cpos, cdist, normal);
+  double dmin = 0;
+  for (int k = 0; k < nc; k++) if (cdist[k] < dmin) dmin = cdist[k];
+  copy3(sat_out, normal); sat_out[3] = -dmin;
+  shape A = {SO100_GEOM_BOX, cA, RA, hA, 0, 0}, B = {SO100_GEOM_BOX, cB, RB, hB, 0, 0};
+  double n2[3] = {0, 0, 0}, depth = 0, pa[3], pb[3];
+  int hit = gjk_epa(&A, &B, cA, cB, n2, &depth, pa, pb);
+  copy3(epa_out, n2); epa_out[3] = hit ? depth : 0;
+  return nc * 16 + hit;
+}
+
 void o_collide(const so100_model* m, oenv* e) {
   e->ncon = 0;
   for (int p = 0; p < m->npair; p++) {
@@ -438,10 +466,24 @@ void o_collide(const so100_model* m, oenv* e) {
     const double* R1 = m->geom_type[g1] == SO100_GEOM_BOX ? e->gmat[g1] : e->xmat[m->geom_body[g1]];
     const double* R2 = m->geom_type[g2] == SO100_GEOM_BOX ? e->gmat[g2] : e->xmat[m->geom_body[g2]];
     if (obb_separated(e->gcen[g1], R1, m->geom_half[g1], e->gcen[g2], R2, m->geom_half[g2])) continue;
-    if (m->geom_type[g1] == SO100_GEOM_BOX && m->geom_type[g2] == SO100_GEOM_BOX) {
+    if (is_cuboid(m, g1) && is_cuboid(m, g2)) {
+      /* Two boxes.  A mesh whose hull is an exact cuboid (the table) has the support map of a box, so
+         the separating-axis result equals the GJK/EPA one (tests/test_oracle_collision.py checks this);
+         pairs that involve such a mesh keep mjc_Convex's one-contact-per-pair rule: deepest feature,
+         centroid of the deepest points (within 1e-6 m) when it is not a single vertex. */
       double cpos[8][3], cdist[8], normal[3];
-      int nc = box_box(e->gpos[g1], e->gmat[g1], m->geom_size[g1], e->gpos[g2], e->gmat[g2], m->geom_size[g2],
-                       cpos, cdist, normal);
+      int nc = box_box(e->gcen[g1], R1, m->geom_half[g1], e->gcen[g2], R2, m->geom_half[g2], cpos, cdist, normal);
+      int single = m->geom_type[g1] != SO100_GEOM_BOX || m->geom_type[g2] != SO100_GEOM_BOX;
+      if (single && nc > 1) {
+        double dmin = cdist[0], acc[3] = {0, 0, 0};
+        int cnt = 0;
+        for (int k = 1; k < nc; k++) if (cdist[k] < dmin) dmin = cdist[k];
+        for (int k = 0; k < nc; k++)
+          if (cdist[k] <= dmin + 1e-6) { add3(acc, acc, cpos[k]); cnt++; }
+        scl3(cpos[0], acc, 1.0 / cnt);
+        cdist[0] = dmin;
+        nc = 1;
+      }
       for (int k = 0; k < nc; k++) add_contact(m, e, p, cpos[k], normal, cdist[k]);
     } else {
       shape A, B;

@@ -176,7 +176,8 @@ void o_solve(const so100_model* m, oenv* e) {
     gn = sqrt(gn);
     e->solver_grad = gn * scale;
     e->solver_iter = it;
-    if (gn * scale < 1e-13) break;
+    /* 1e-11 is ~100x above the fp64 round-off floor of this gradient and 1000x tighter than MuJoCo's 1e-8 */
+    if (gn * scale < 1e-11) break;
     /* Hessian */
     memcpy(H, e->M, sizeof(H));
     for (int r = 0; r < nefc; r++) {

@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def model_blob():
+    from gym_so100_c_b200 import model
+    return model.pack(model.load_model())
+
+
+@pytest.fixture(scope="session")
+def model_rec():
+    from gym_so100_c_b200 import model
+    return model.load_model()
