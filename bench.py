@@ -1,0 +1,254 @@
+#!/usr/bin/env python
+"""bin-a-cube env-steps/s on B200 (BASELINE.json metric), plus the CPU arm.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (fp64 restatement, all host cores)
+
+One "step" = one env.step over the whole batch: action un-normalise, 10 physics substeps,
+trailing forward, reward/flags/obs, same-call auto-reset.  Workload = BASELINE
+config 3: full bin-a-cube with gripper/cube/table/bin contacts, 16384 envs per GPU, random actions
+U(-1,1) (the reference's action_space.sample(), scripts/example.py:20), weak scaling over GPUs.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 16384
+ALG_BYTES_PER_ENV_STEP = 432          # 188 B read + 244 B written per env-step
+FLOP_PER_ENV_STEP = 1.0e6             # SURVEY.md Appendix C convention F_contact (fp32 FLOPs, FMA = 2)
+FP32_PEAK_NOMINAL_TFLOPS = 74.4       # 148 SM x 128 lanes x 2 x 1.965 GHz
+METRIC = "env-steps/sec (bin-a-cube)"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:  # noqa: BLE001
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm(n_envs: int, steps: int, warmup: int, seed: int = 1234):
+    """The CPU implementation of the same step: the fp64 C restatement (oracle/) on all host cores.
+    kind = "port": MuJoCo itself is not installable here, so this is NOT MuJoCo."""
+    from gym_so100_c_b200 import model
+    from oracle.so100_oracle import Oracle, build
+    build()
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    orc = Oracle(model.pack(model.load_model()), n_envs, task=0, seed=seed)
+    orc.reset()
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(-1, 1, size=(steps + warmup, n_envs, 6)).astype(np.float32)
+    for s in range(warmup):
+        orc.step(acts[s], autoreset=True)
+    t0 = time.perf_counter()
+    for s in range(warmup, warmup + steps):
+        orc.step(acts[s], autoreset=True)
+    dt = time.perf_counter() - t0
+    orc.close()
+    return n_envs * steps / dt, dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n = 4 * cores
+    value, dt, cores = cpu_arm(n, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE config 3: full bin-a-cube with contacts, random actions U(-1,1), auto-reset",
+                   "envs_per_step": n, "note": "bounded sample of the 16384-env batch: 4 envs per host core per step"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} envs x {args.steps} steps, fp64 C restatement of the step (oracle/), OpenMP over envs; "
+                                   "MuJoCo/dm_control are not installable in this image"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_gpu(args):
+    import torch
+    from gym_so100_c_b200 import parallel
+    from gym_so100_c_b200.engine import BatchedSim
+
+    rank, world, local = parallel.init_from_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n = args.envs_per_gpu
+    lo, hi = parallel.shard_range(n * world, rank, world)
+    sim = BatchedSim(hi - lo, device=dev, task=0, seed=0x50100, env_offset=lo)
+    sim.reset()
+    K, W = args.steps, args.warmup
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    acts = torch.rand((K + W, hi - lo, 6), device=dev, generator=gen) * 2 - 1       # inputs resident in HBM
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
+    for s in range(W):
+        sim.step(acts[s], autoreset=True)
+    torch.cuda.synchronize()
+    parallel.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_wall = time.perf_counter()
+    for s in range(K):
+        flush.fill_(float(s))                       # evict L2 between timed iterations (not timed)
+        ev[s][0].record()
+        sim.step(acts[W + s], autoreset=True)       # ONE kernel launch of this repo
+        ev[s][1].record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = parallel.max_over_ranks(float(sum(ms)), device=dev)
+    kernel_ms = float(np.mean(ms))
+    diag = parallel.all_reduce_stats(sim.diagnostics(), device=dev)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host actions -> device -> host results)
+    Ke = max(3, min(K, 50))
+    h_act = torch.empty((hi - lo, 6), dtype=torch.float32).pin_memory()
+    h_src = acts[W:W + Ke].cpu()
+    sim.step_host(h_src[0].numpy(), autoreset=True)
+    torch.cuda.synchronize()
+    parallel.barrier()
+    t0 = time.perf_counter()
+    for s in range(Ke):
+        h_act.copy_(h_src[s])
+        out = sim.step_host(h_act.numpy(), autoreset=True)      # H2D + kernel + D2H + stream sync inside
+        _ = float(out["reward"][0])
+    e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, device=dev)
+    nl = hi - lo
+    h2d = nl * 6 * 4
+    d2h = nl * (15 * 4 + 15 * 4 + 3 * 4 + 3 * 4 + 4 + 3)
+
+    if rank == 0:
+        hbm_peak, peak_src = measured_peaks()
+        n_total = n * world
+        value = n_total * K / (total_ms * 1e-3)
+        achieved = ALG_BYTES_PER_ENV_STEP * nl / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
+                tj = json.load(f)
+            if int(tj.get("envs", -1)) == nl:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+        fp32_tflops = FLOP_PER_ENV_STEP * nl / (kernel_ms * 1e-3) / 1e12
+        cores = os.cpu_count() or 1
+        cpu_n = 4 * cores
+        # reported baseline, rank 0 at N=1 only (multi-GPU lines carry null)
+        cpu_value, cpu_dt, cores = cpu_arm(cpu_n, steps=3, warmup=1) if world == 1 else (None, None, cores)
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 3: full bin-a-cube (gripper/cube/table/bin contacts), random actions "
+                                   "U(-1,1), same-step auto-reset",
+                       "envs_per_gpu": n, "envs_total": n_total, "substeps_per_step": 10, "l2": "flushed between timed steps "
+                       "(256 MiB write, untimed)", "parallelism": f"env-shard x{world}, no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "note": "HBM is not the binding roof for this path (SURVEY 8d): the step is FP32-issue bound",
+                         "fp32_convention": {"flop_per_env_step": FLOP_PER_ENV_STEP, "achieved_tflops": fp32_tflops,
+                                             "peak_tflops_nominal": FP32_PEAK_NOMINAL_TFLOPS,
+                                             "frac": fp32_tflops / FP32_PEAK_NOMINAL_TFLOPS}},
+            "cpu_baseline": {"value": cpu_value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": f"{cpu_n} envs x 3 steps of the same workload, fp64 C restatement (oracle/), OpenMP over envs"},
+            "e2e": {"value": n_total * Ke / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "steps": Ke},
+            "gpu_launches": K,
+            "clocks": clocks,
+            "physics_substeps_per_s": value * 10,
+            "wall_s_timed_region": t_wall,
+            "diagnostics": diag,
+        }
+        print(json.dumps(line))
+    sim.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -214,6 +214,7 @@ static int build_dev_model(const so100_model& m, DevModel& dm, std::vector<DevGe
       D3 c = rot_h(Rw, {m.geom_center[g][0], m.geom_center[g][1], m.geom_center[g][2]});
       G.center[0] = (float)(rp.x + c.x); G.center[1] = (float)(rp.y + c.y); G.center[2] = (float)(rp.z + c.z);
       for (int k = 0; k < 9; k++) G.wmat[k] = (float)Rw[k];
+      G.org[0] = (float)rp.x; G.org[1] = (float)rp.y; G.org[2] = (float)rp.z;
     }
   }
   // pairs

@@ -38,6 +38,7 @@ struct DevGeom {
   float half[3];   // OBB half sizes
   float rbound;
   float wmat[9];   // static geoms: world axes (row-major); dynamic: unused
+  float org[3];    // static geoms: world origin of the body frame the hull vertices live in
 };
 
 struct DevPair {

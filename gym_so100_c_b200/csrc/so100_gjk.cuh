@@ -1,0 +1,360 @@
+// GJK + EPA for the pairs that involve a general convex hull (arm links, jaw hulls, base),
+// one tile per env: the support map over the hull vertices is lane-parallel (float4 loads +
+// shuffle arg-max), the simplex / polytope logic is tile-uniform, the EPA polytope lives in
+// the shared-memory region that later holds the contact Jacobian.  One contact per pair
+// (MuJoCo mjc_Convex with multiccd off): normal and depth are the minimum-translation
+// solution, the point is the midpoint of the EPA witness points.
+#pragma once
+#include "so100_step.cuh"
+
+namespace so100 {
+
+struct Shape {
+  int boxlike;
+  V3 base;            // boxlike: world centre; hull: world origin of the vertex frame
+  const float* mat;   // row-major axes (shared-memory link frame or static table)
+  float h[3];
+  int vadr, vnum;
+};
+
+template <unsigned LPE>
+__device__ __forceinline__ void load_shape(const EnvS* S, const DevGeom& G, int gi, Shape& s) {
+  s.boxlike = G.boxlike;
+  s.mat = G.link >= 0 ? S->lmat[G.link] : G.wmat;
+  s.h[0] = G.half[0]; s.h[1] = G.half[1]; s.h[2] = G.half[2];
+  s.vadr = G.vadr; s.vnum = G.vnum;
+  if (G.boxlike) s.base = ld3(S->gcen[gi]);
+  else s.base = G.link >= 0 ? ld3(S->lpos[G.link]) : ld3(G.org);
+}
+
+// support point in world direction d; identical on every lane of the tile
+template <unsigned LPE>
+__device__ __forceinline__ V3 support(const Tile<LPE>& t, const Shape& s, V3 d, const float4* __restrict__ vert) {
+  const V3 dl = mulmtv(s.mat, d);
+  V3 pl;
+  if (s.boxlike) {
+    pl = mk(dl.x >= 0 ? s.h[0] : -s.h[0], dl.y >= 0 ? s.h[1] : -s.h[1], dl.z >= 0 ? s.h[2] : -s.h[2]);
+  } else {
+    float best = -3.0e38f;
+    int bi = 0x7fffffff;
+    for (int v = t.thread_rank(); v < s.vnum; v += LPE) {
+      const float4 p = __ldg(&vert[s.vadr + v]);
+      const float val = fmaf(p.x, dl.x, fmaf(p.y, dl.y, p.z * dl.z));
+      if (val > best) { best = val; bi = v; }
+    }
+#pragma unroll
+    for (int off = LPE / 2; off > 0; off >>= 1) {
+      const float ov = t.shfl_xor(best, off);
+      const int oi = t.shfl_xor(bi, off);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    const float4 p = __ldg(&vert[s.vadr + bi]);
+    pl = mk(p.x, p.y, p.z);
+  }
+  return s.base + mulmv(s.mat, pl);
+}
+
+struct MV { V3 w, a; };   // Minkowski-difference vertex w = a - b (b is recovered as a - w)
+
+template <unsigned LPE>
+__device__ __forceinline__ MV msupport(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 d, const float4* vert) {
+  MV m;
+  m.a = support(t, A, d, vert);
+  const V3 b = support(t, B, -d, vert);
+  m.w = m.a - b;
+  return m;
+}
+
+// triangle case of the simplex update: A = s[2] is the newest point
+__device__ inline void simplex_triangle(MV* s, int& n, V3& dir) {
+  const MV A = s[2], B = s[1], C = s[0];
+  const V3 ao = -A.w, ab = B.w - A.w, ac = C.w - A.w, abc = cross(ab, ac);
+  bool edge_ab = false;
+  if (dot(cross(abc, ac), ao) > 0) {
+    if (dot(ac, ao) > 0) { s[0] = C; s[1] = A; n = 2; dir = cross(cross(ac, ao), ac); return; }
+    edge_ab = true;
+  } else if (dot(cross(ab, abc), ao) > 0) {
+    edge_ab = true;
+  }
+  if (edge_ab) {
+    if (dot(ab, ao) > 0) { s[0] = B; s[1] = A; n = 2; dir = cross(cross(ab, ao), ab); }
+    else { s[0] = A; n = 1; dir = ao; }
+    return;
+  }
+  if (dot(abc, ao) > 0) dir = abc;
+  else { s[0] = B; s[1] = C; s[2] = A; dir = -abc; }
+}
+
+// simplex update; returns true when the tetrahedron encloses the origin
+__device__ inline bool do_simplex(MV* s, int& n, V3& dir) {
+  if (n == 2) {
+    const V3 ao = -s[1].w, ab = s[0].w - s[1].w;
+    if (dot(ab, ao) > 0) dir = cross(cross(ab, ao), ab);
+    else { s[0] = s[1]; n = 1; dir = ao; }
+    return false;
+  }
+  if (n == 3) { simplex_triangle(s, n, dir); return false; }
+  const MV A = s[3], B = s[2], C = s[1], D = s[0];
+  const V3 ao = -A.w, ab = B.w - A.w, ac = C.w - A.w, ad = D.w - A.w;
+  V3 abc = cross(ab, ac), acd = cross(ac, ad), adb = cross(ad, ab);
+  if (dot(abc, ad) > 0) abc = -abc;
+  if (dot(acd, ab) > 0) acd = -acd;
+  if (dot(adb, ac) > 0) adb = -adb;
+  if (dot(abc, ao) > 0) { s[0] = C; s[1] = B; s[2] = A; }
+  else if (dot(acd, ao) > 0) { s[0] = D; s[1] = C; s[2] = A; }
+  else if (dot(adb, ao) > 0) { s[0] = B; s[1] = D; s[2] = A; }
+  else return true;
+  n = 3;
+  simplex_triangle(s, n, dir);
+  return false;
+}
+
+// closest point of triangle (a,b,c) to the origin: barycentric weights, returns squared distance
+__device__ inline float tri_closest(V3 a, V3 b, V3 c, float* lam) {
+  const V3 ab = b - a, ac = c - a;
+  const float d1 = -dot(ab, a), d2 = -dot(ac, a);
+  if (d1 <= 0 && d2 <= 0) { lam[0] = 1; lam[1] = 0; lam[2] = 0; return dot(a, a); }
+  const float d3 = -dot(ab, b), d4 = -dot(ac, b);
+  if (d3 >= 0 && d4 <= d3) { lam[0] = 0; lam[1] = 1; lam[2] = 0; return dot(b, b); }
+  const float vc = d1 * d4 - d3 * d2;
+  if (vc <= 0 && d1 >= 0 && d3 <= 0) {
+    const float v = d1 / (d1 - d3);
+    lam[0] = 1 - v; lam[1] = v; lam[2] = 0;
+  } else {
+    const float d5 = -dot(ab, c), d6 = -dot(ac, c);
+    if (d6 >= 0 && d5 <= d6) { lam[0] = 0; lam[1] = 0; lam[2] = 1; return dot(c, c); }
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) {
+      const float w = d2 / (d2 - d6);
+      lam[0] = 1 - w; lam[1] = 0; lam[2] = w;
+    } else {
+      const float va = d3 * d6 - d5 * d4;
+      if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+        const float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        lam[0] = 0; lam[1] = 1 - w; lam[2] = w;
+      } else {
+        const float den = 1.0f / (va + vb + vc);
+        lam[1] = vb * den; lam[2] = vc * den; lam[0] = 1 - lam[1] - lam[2];
+      }
+    }
+  }
+  const V3 p = a * lam[0] + b * lam[1] + c * lam[2];
+  return dot(p, p);
+}
+
+// EPA polytope in shared memory (aliases the contact-Jacobian region; see EnvS::w)
+constexpr int EPA_MAXV = 32;
+constexpr int EPA_MAXF = 64;
+struct EpaScratch {
+  float vw[EPA_MAXV][3], va[EPA_MAXV][3];
+  float fn[EPA_MAXF][3], fdp[EPA_MAXF], fdt[EPA_MAXF];
+  unsigned char fv[EPA_MAXF][4];        // vertex ids, [3] = alive flag
+  unsigned char vis[EPA_MAXF];
+  unsigned char owner[EPA_MAXV][EPA_MAXV];  // face owning the directed edge a -> b
+  unsigned char hedge[EPA_MAXF][2];
+  unsigned char freed[EPA_MAXF];
+};
+
+__device__ __forceinline__ void epa_make_face(EpaScratch* E, int slot, int i, int j, int k) {
+  const V3 a = ld3(E->vw[i]), b = ld3(E->vw[j]), c = ld3(E->vw[k]);
+  V3 n = cross(b - a, c - a);
+  const float len2 = dot(n, n);
+  float lam[3];
+  E->fv[slot][0] = (unsigned char)i; E->fv[slot][1] = (unsigned char)j; E->fv[slot][2] = (unsigned char)k;
+  E->owner[i][j] = (unsigned char)slot; E->owner[j][k] = (unsigned char)slot; E->owner[k][i] = (unsigned char)slot;
+  if (len2 < 1e-30f) { E->fv[slot][3] = 0; E->fdt[slot] = 3.0e38f; E->fdp[slot] = 0; st3(E->fn[slot], mk(0, 0, 1)); return; }
+  n = n * rsqrtf(len2);
+  st3(E->fn[slot], n);
+  E->fdp[slot] = dot(n, a);
+  E->fdt[slot] = sqrtf(tri_closest(a, b, c, lam));
+  E->fv[slot][3] = 1;
+}
+
+// Penetration of A into B.  On a hit: normal (A -> B), depth > 0, contact point (midpoint of the
+// witness points).  All lanes return the same values.
+template <unsigned LPE>
+__device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 ca, V3 cb, const float4* vert,
+                        EpaScratch* E, V3& normal, float& depth, V3& pos) {
+  const int lane = t.thread_rank();
+  MV s[4];
+  int n = 1;
+  V3 dir = cb - ca;
+  if (dot(dir, dir) < 1e-20f) dir = mk(1, 0, 0);
+  s[0] = msupport(t, A, B, dir, vert);
+  dir = -s[0].w;
+  bool hit = false;
+  for (int it = 0; it < 48; it++) {
+    if (dot(dir, dir) < 1e-24f) return false;
+    const MV w = msupport(t, A, B, dir, vert);
+    if (dot(w.w, dir) <= 0) return false;
+    s[n++] = w;
+    if (do_simplex(s, n, dir)) { hit = true; break; }
+  }
+  if (!hit) return false;
+  // ---- EPA
+  t.sync();
+  if (lane < 4) { st3(E->vw[lane], s[lane].w); st3(E->va[lane], s[lane].a); }
+  t.sync();
+  if (lane < 4) {
+    const int tf[4][3] = {{0, 1, 2}, {0, 3, 1}, {0, 2, 3}, {1, 3, 2}};
+    int a = tf[lane][0], b = tf[lane][1], c = tf[lane][2];
+    const int opp = 6 - a - b - c;
+    const V3 va = ld3(E->vw[a]);
+    const V3 nn = cross(ld3(E->vw[b]) - va, ld3(E->vw[c]) - va);
+    if (dot(nn, ld3(E->vw[opp]) - va) > 0) { const int tmp = b; b = c; c = tmp; }
+    epa_make_face(E, lane, a, b, c);
+  }
+  t.sync();
+  int nface = 4, nv = 4, best = 0;
+  bool degenerate = false;
+  for (int k = 0; k < 4; k++) degenerate |= (E->fv[k][3] == 0);
+  if (degenerate) return false;   // flat tetrahedron: touching
+  for (int it = 0; it < EPA_MAXV - 4; it++) {
+    // closest face (ties -> lowest slot)
+    float bd = 3.0e38f; int bf = 0x7fffffff;
+    for (int f = lane; f < nface; f += LPE)
+      if (E->fv[f][3] && E->fdt[f] < bd) { bd = E->fdt[f]; bf = f; }
+#pragma unroll
+    for (int off = LPE / 2; off > 0; off >>= 1) {
+      const float ov = t.shfl_xor(bd, off);
+      const int of = t.shfl_xor(bf, off);
+      if (ov < bd || (ov == bd && of < bf)) { bd = ov; bf = of; }
+    }
+    if (bf == 0x7fffffff) break;
+    best = bf;
+    const V3 nb = ld3(E->fn[best]);
+    const MV w = msupport(t, A, B, nb, vert);
+    if (dot(w.w, nb) - E->fdp[best] < 1e-6f || nface + 2 > EPA_MAXF) break;
+    // visibility
+    int myvis = 0;
+    for (int f = lane; f < nface; f += LPE) {
+      const unsigned char v = (E->fv[f][3] && dot(ld3(E->fn[f]), w.w - ld3(E->vw[E->fv[f][0]])) > 0.0f) ? 1 : 0;
+      E->vis[f] = v;
+      myvis += v;
+    }
+    t.sync();
+    if (!E->vis[best]) break;      // round-off: the expanding face does not see the new point
+    // freed slots (compaction of visible faces) and horizon edges
+    int nfree = 0, nh = 0;
+    for (int base = 0; base < nface; base += LPE) {
+      const int f = base + lane;
+      const bool v = f < nface && E->vis[f];
+      const unsigned m = t.ballot(v);
+      if (v) E->freed[nfree + __popc(m & ((1u << lane) - 1u))] = (unsigned char)f;
+      nfree += __popc(m);
+    }
+    for (int base = 0; base < nface * 3; base += LPE) {
+      const int idx = base + lane, f = idx / 3, e = idx - f * 3;
+      bool h = false;
+      int ea = 0, eb = 0;
+      if (f < nface && E->vis[f]) {
+        ea = E->fv[f][e]; eb = E->fv[f][e == 2 ? 0 : e + 1];
+        h = !E->vis[E->owner[eb][ea]];
+      }
+      const unsigned m = t.ballot(h);
+      if (h) {
+        const int k = nh + __popc(m & ((1u << lane) - 1u));
+        if (k < EPA_MAXF) { E->hedge[k][0] = (unsigned char)ea; E->hedge[k][1] = (unsigned char)eb; }
+      }
+      nh += __popc(m);
+    }
+    t.sync();
+    if (nh < 3 || nh > EPA_MAXF || nface + (nh - nfree) > EPA_MAXF) break;
+    if (lane == 0) { st3(E->vw[nv], w.w); st3(E->va[nv], w.a); }
+    for (int f = lane; f < nface; f += LPE) if (E->vis[f]) E->fv[f][3] = 0;
+    t.sync();
+    for (int k = lane; k < nh; k += LPE) {
+      const int slot = k < nfree ? E->freed[k] : nface + (k - nfree);
+      epa_make_face(E, slot, E->hedge[k][0], E->hedge[k][1], nv);
+    }
+    nface += max(nh - nfree, 0);
+    nv++;
+    t.sync();
+  }
+  const V3 a0 = ld3(E->vw[E->fv[best][0]]), a1 = ld3(E->vw[E->fv[best][1]]), a2 = ld3(E->vw[E->fv[best][2]]);
+  float lam[3];
+  tri_closest(a0, a1, a2, lam);
+  const V3 pa = ld3(E->va[E->fv[best][0]]) * lam[0] + ld3(E->va[E->fv[best][1]]) * lam[1] + ld3(E->va[E->fv[best][2]]) * lam[2];
+  const V3 pw = a0 * lam[0] + a1 * lam[1] + a2 * lam[2];
+  normal = ld3(E->fn[best]);
+  depth = E->fdp[best];
+  pos = pa - pw * 0.5f;
+  t.sync();
+  return depth > 0;
+}
+
+// 15-axis oriented-box overlap test (cull only)
+__device__ inline bool obb_overlap(const Obb& A, const Obb& B) {
+  float R[3][3], aR[3][3], tA[3];
+  const V3 t = B.c - A.c;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    tA[i] = dot(t, A.ax[i]);
+#pragma unroll
+    for (int j = 0; j < 3; j++) { R[i][j] = dot(A.ax[i], B.ax[j]); aR[i][j] = fabsf(R[i][j]) + 1e-6f; }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    if (fabsf(tA[i]) > A.h[i] + B.h[0] * aR[i][0] + B.h[1] * aR[i][1] + B.h[2] * aR[i][2]) return false;
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+    if (fabsf(tA[0] * R[0][j] + tA[1] * R[1][j] + tA[2] * R[2][j]) > B.h[j] + A.h[0] * aR[0][j] + A.h[1] * aR[1][j] + A.h[2] * aR[2][j]) return false;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const float ra = A.h[i1] * aR[i2][j] + A.h[i2] * aR[i1][j];
+      const float rb = B.h[j1] * aR[i][j2] + B.h[j2] * aR[i][j1];
+      if (fabsf(tA[i2] * R[i1][j] - tA[i1] * R[i2][j]) > ra + rb) return false;
+    }
+  }
+  return true;
+}
+
+static_assert(sizeof(EpaScratch) <= sizeof(float) * 900, "EPA scratch does not fit its shared-memory slot");
+
+// hull pairs that survived the sphere tests: oriented-box cull (one lane per pair), then GJK/EPA
+// with the whole tile per pair, in pair order (deterministic contact order)
+template <unsigned LPE> __device__ void hull_stage(const Tile<LPE>& t, EnvS* S, const DevTables& T, int nhull) {
+  const int lane = t.thread_rank();
+  int nsurv = 0;
+  for (int base = 0; base < nhull; base += LPE) {
+    const int k = base + lane;
+    bool pass = false;
+    int p = 0;
+    if (k < nhull) {
+      p = S->w.col.qhull[k];
+      const DevPair& P = T.pair[p];
+      Obb A, B;
+      load_obb(S, T.geom[P.g1], P.g1, A);
+      load_obb(S, T.geom[P.g2], P.g2, B);
+      pass = obb_overlap(A, B);
+    }
+    const unsigned m = t.ballot(pass);
+    if (pass) S->w.col.q1[nsurv + __popc(m & ((1u << lane) - 1u))] = (unsigned char)p;
+    nsurv += __popc(m);
+  }
+  t.sync();
+  EpaScratch* E = reinterpret_cast<EpaScratch*>(S->w.col.epa);
+  for (int k = 0; k < nsurv; k++) {
+    const int p = S->w.col.q1[k];
+    const DevPair& P = T.pair[p];
+    Shape A, B;
+    load_shape<LPE>(S, T.geom[P.g1], P.g1, A);
+    load_shape<LPE>(S, T.geom[P.g2], P.g2, B);
+    V3 n, pos;
+    float depth;
+    if (gjk_epa(t, A, B, ld3(S->gcen[P.g1]), ld3(S->gcen[P.g2]), T.vert, E, n, depth, pos)) {
+      if (lane == 0) {
+        const int c = S->ncon;
+        if (c < NC) { st3(S->cpos[c], pos); st3(S->cnrm[c], n); S->cdist[c] = -depth; S->cpair[c] = (unsigned char)p; }
+        S->ncon = min(c + 1, NC + 1);
+      }
+    }
+    t.sync();
+  }
+}
+
+}  // namespace so100

@@ -2,6 +2,7 @@
 // state pack/unpack.  Env e is handled by tile (e % EPB) of block (e / EPB).
 #pragma once
 #include "so100_solve.cuh"
+#include "so100_gjk.cuh"
 
 namespace so100 {
 

@@ -49,7 +49,7 @@ struct __align__(16) EnvS {
   } u;
   union {
     float J[NC * 4][JS];
-    struct { unsigned char q1[NPAIR_MAX], qbox[NPAIR_MAX], qhull[NPAIR_MAX]; } col;
+    struct { unsigned char q1[NPAIR_MAX], qbox[NPAIR_MAX], qhull[NPAIR_MAX]; float epa[900]; } col;
   } w;
 };
 
@@ -420,6 +420,8 @@ __device__ int box_box(const Obb& A, const Obb& B, float (*cp)[3], float* cd, V3
   return nc;
 }
 
+template <unsigned LPE> __device__ void hull_stage(const Tile<LPE>& t, EnvS* S, const DevTables& T, int nhull);
+
 template <unsigned LPE> __device__ void collide(const Tile<LPE>& t, EnvS* S, const DevTables& T) {
   const int lane = t.thread_rank();
   // world OBB centres
@@ -501,8 +503,8 @@ template <unsigned LPE> __device__ void collide(const Tile<LPE>& t, EnvS* S, con
     if (lane == 0) S->ncon = min(S->ncon + total, NC + 1);   // NC+1 marks overflow
     t.sync();
   }
-  S->nhull = nhull;   // every lane writes the same value
-  t.sync();
+  // stage 2b: pairs that involve a general hull (so100_gjk.cuh)
+  hull_stage(t, S, T, nhull);
 }
 
 }  // namespace so100

@@ -1,0 +1,252 @@
+"""Gymnasium-VectorEnv surface of the reference envs, batched on one GPU.
+
+Mirrors (names, argument meaning, returned tuple shapes, error behaviour):
+  * ``gym_so100.env.SO100Env(task="so100_cube_to_bin", obs_type="so100_state")``
+    (gym_so100/env.py:26-185; registered as gym_so100/SO100CubeToBin-v0 with
+    max_episode_steps=700, gym_so100/__init__.py:24-32)            -> :class:`SO100VecEnv`
+  * ``gym_so100.env.SO100GoalEnv`` (gym_so100/env.py:188-409)      -> :class:`SO100GoalVecEnv`
+  * the SB3 ``VecEnv`` protocol the reference's training scripts consume
+    (scripts/train_sac.py:294-301, scripts/train_sac_her.py:220-254) -> :class:`SB3VecEnvAdapter`
+
+All returned arrays are device-resident ``torch`` tensors owned by the env and overwritten by
+the next call (the reference returns fresh numpy copies; copy if you keep them).  Declared
+deviations: no renderer, so ``obs_type`` must be ``"so100_state"`` and the
+GoalEnv ``"observation"`` entry is the 15-float state vector instead of flattened pixels.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ext
+from .engine import BatchedSim
+from .model import BOX_RANGE_HI, BOX_RANGE_LO
+from .spaces import Box, Dict as DictSpace, batch_box
+
+METADATA = {"render_modes": ["rgb_array"], "render_fps": 50}   # env.py:27
+
+
+def sample_so100_box_pose(seed=None) -> np.ndarray:
+    """gym_so100/utils.py:18-29 restated: MT19937 ``RandomState(seed)``, three uniform draws, identity quat."""
+    rng = np.random.RandomState(seed)
+    ranges = np.vstack([[BOX_RANGE_LO[0], BOX_RANGE_HI[0]], [BOX_RANGE_LO[1], BOX_RANGE_HI[1]], [BOX_RANGE_LO[2], BOX_RANGE_HI[2]]])
+    pos = rng.uniform(ranges[:, 0], ranges[:, 1])
+    return np.concatenate([pos, np.array([1, 0, 0, 0])])
+
+
+class _VecBase:
+    metadata = METADATA
+    _task = ext.TASK_CUBE_TO_BIN
+
+    def __init__(self, num_envs: int, device="cuda:0", seed: int = 0, env_offset: int = 0,
+                 autoreset: bool = True, render_mode: Optional[str] = None):
+        if num_envs <= 0:
+            raise ValueError("num_envs must be positive")
+        self.num_envs = int(num_envs)
+        self.render_mode = render_mode
+        self.autoreset = bool(autoreset)
+        self.sim = BatchedSim(self.num_envs, device=device, task=self._task, seed=seed, env_offset=env_offset)
+        self.device = self.sim.device
+        self.single_action_space = Box(low=-1, high=1, shape=(6,), dtype=np.float32)        # env.py:75-77
+        self.action_space = batch_box(self.single_action_space, self.num_envs)
+        self.closed = False
+
+    # -- reference API that has no batched meaning
+    def render(self):
+        raise NotImplementedError("rendering is out of scope for the batched engine (state observations only)")
+
+    def close(self):
+        if not self.closed:
+            self.sim.close()
+            self.closed = True
+
+    def _box_poses(self, seed) -> Optional[torch.Tensor]:
+        """VectorEnv seeding: env i is reset with ``sample_so100_box_pose(seed + i)`` exactly like the
+        reference's per-env ``reset(seed=...)``; ``None`` draws on the device (Philox)."""
+        if seed is None:
+            return None
+        seeds = [int(seed) + i for i in range(self.num_envs)] if np.isscalar(seed) else [int(s) for s in seed]
+        if len(seeds) != self.num_envs:
+            raise ValueError("need one seed per env")
+        poses = np.stack([sample_so100_box_pose(s) for s in seeds]).astype(np.float32)
+        return torch.from_numpy(poses)
+
+    def _mask(self, options) -> Optional[torch.Tensor]:
+        if options and options.get("reset_mask") is not None:
+            return torch.as_tensor(options["reset_mask"]).to(torch.uint8)
+        return None
+
+    def diagnostics(self) -> Dict[str, int]:
+        return self.sim.diagnostics()
+
+    def get_state(self):
+        return self.sim.get_state()
+
+    def set_state(self, qpos=None, qvel=None, ctrl=None, warm=None):
+        self.sim.set_state(qpos, qvel, ctrl, warm)
+
+
+class SO100VecEnv(_VecBase):
+    """N copies of ``SO100Env(task="so100_cube_to_bin", obs_type="so100_state")`` under a 700-step TimeLimit."""
+
+    _task = ext.TASK_CUBE_TO_BIN
+
+    def __init__(self, num_envs: int, task: str = "so100_cube_to_bin", obs_type: str = "so100_state", **kw):
+        if task != "so100_cube_to_bin":
+            raise NotImplementedError(task)           # env.py:117-118
+        if obs_type != "so100_state":
+            raise NotImplementedError(f"obs_type {obs_type!r}: the batched engine has no renderer (so100_state only)")
+        super().__init__(num_envs, **kw)
+        self.task = task
+        self.obs_type = obs_type
+        self.max_episode_steps = 700                  # __init__.py:27
+        self.single_observation_space = Box(low=-100.0, high=100.0, shape=(15,), dtype=np.float32)   # env.py:67-73
+        self.observation_space = batch_box(self.single_observation_space, self.num_envs)
+
+    def reset(self, seed=None, options: Optional[dict] = None):
+        obs, _, _ = self.sim.reset(mask=self._mask(options), box_pose=self._box_poses(seed))
+        infos = {"is_success": torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)}   # env.py:169
+        return obs, infos
+
+    def step(self, actions):
+        if getattr(actions, "ndim", 2) != 2:
+            raise AssertionError("actions must be [num_envs, 6]")   # env.py:173 asserts ndim == 1 per env
+        obs, reward, term, trunc, succ = self.sim.step(actions, autoreset=self.autoreset)
+        term_b, trunc_b = term.bool(), trunc.bool()
+        infos: Dict[str, Any] = {"is_success": succ.bool()}          # env.py:175-177
+        if self.autoreset:
+            infos["final_obs"] = self.sim.final_obs
+            infos["_final_obs"] = term_b | trunc_b
+        infos["TimeLimit.truncated"] = trunc_b & ~term_b
+        return obs, reward, term_b, trunc_b, infos
+
+
+class SO100GoalVecEnv(_VecBase):
+    """N copies of ``SO100GoalEnv``: dict observations, sparse 0/-1 reward, 300-step truncation."""
+
+    _task = ext.TASK_GOAL
+
+    def __init__(self, num_envs: int, **kw):
+        super().__init__(num_envs, **kw)
+        self.max_episode_steps = 300                  # env.py:200
+        self.distance_threshold = 0.01                # env.py:252
+        inf = np.inf
+        self.single_observation_space = DictSpace({
+            "observation": Box(low=-inf, high=inf, shape=(15,), dtype=np.float32),
+            "achieved_goal": Box(low=-inf, high=inf, shape=(3,), dtype=np.float32),   # env.py:228-235
+            "desired_goal": Box(low=-inf, high=inf, shape=(3,), dtype=np.float32),
+        })
+        self.observation_space = DictSpace({k: batch_box(s, self.num_envs) for k, s in self.single_observation_space.items()})
+
+    def _obs(self):
+        return {"observation": self.sim.obs, "achieved_goal": self.sim.achieved, "desired_goal": self.sim.desired}
+
+    def reset(self, seed=None, options: Optional[dict] = None):
+        self.sim.reset(mask=self._mask(options), box_pose=self._box_poses(seed))
+        infos = {"is_success": torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)}   # env.py:318
+        return self._obs(), infos
+
+    def step(self, actions):
+        if getattr(actions, "ndim", 2) != 2:
+            raise AssertionError("actions must be [num_envs, 6]")
+        _, reward, term, trunc, succ = self.sim.step(actions, autoreset=self.autoreset)
+        term_b, trunc_b = term.bool(), trunc.bool()
+        infos: Dict[str, Any] = {"is_success": succ.bool(), "TimeLimit.truncated": trunc_b}   # env.py:392-403
+        if self.autoreset:
+            infos["final_obs"] = self.sim.final_obs
+            infos["_final_obs"] = term_b | trunc_b
+        return self._obs(), reward, term_b, trunc_b, infos
+
+    def compute_reward(self, achieved_goal, desired_goal, info=None):
+        """env.py:341-353.  Batched inputs ([..., 3]) -> float32 rewards; single inputs -> Python float."""
+        ag = torch.as_tensor(achieved_goal)
+        dg = torch.as_tensor(desired_goal)
+        r = self.sim.compute_reward(ag, dg, self.distance_threshold)
+        if ag.ndim > 1:
+            return r.reshape(ag.shape[:-1])
+        return float(r[0].item())
+
+
+class SB3VecEnvAdapter:
+    """Duck-typed stable_baselines3 ``VecEnv`` over a batched env: numpy in/out, same-step auto-reset,
+    ``infos[i]["terminal_observation"]`` and ``env_method("compute_reward", ...)`` for ``HerReplayBuffer``
+    (scripts/train_sac_her.py:240-244).  Every call synchronises and copies to the host."""
+
+    def __init__(self, venv: _VecBase):
+        if not venv.autoreset:
+            raise ValueError("SB3 semantics need autoreset=True")
+        self.venv = venv
+        self.num_envs = venv.num_envs
+        self.observation_space = venv.single_observation_space
+        self.action_space = venv.single_action_space
+        self._actions = None
+
+    @staticmethod
+    def _np(x):
+        if isinstance(x, dict):
+            return {k: v.cpu().numpy().copy() for k, v in x.items()}
+        return x.cpu().numpy().copy()
+
+    def reset(self):
+        obs, _ = self.venv.reset()
+        return self._np(obs)
+
+    def seed(self, seed=None):
+        self._seed = seed
+        return [seed] * self.num_envs
+
+    def step_async(self, actions):
+        self._actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
+
+    def step_wait(self):
+        obs, rew, term, trunc, infos = self.venv.step(self._actions)
+        done = (term | trunc).cpu().numpy()
+        succ = infos["is_success"].cpu().numpy()
+        tl = infos["TimeLimit.truncated"].cpu().numpy()
+        final = infos["final_obs"].cpu().numpy()
+        out = []
+        for i in range(self.num_envs):
+            d = {"is_success": bool(succ[i]), "TimeLimit.truncated": bool(tl[i])}
+            if done[i]:
+                if isinstance(obs, dict):
+                    d["terminal_observation"] = {"observation": final[i].copy(), "achieved_goal": final[i, :3].copy(),
+                                                 "desired_goal": None}
+                else:
+                    d["terminal_observation"] = final[i].copy()
+            out.append(d)
+        return self._np(obs), rew.cpu().numpy().copy(), done, out
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def env_method(self, method_name: str, *args, indices: Optional[Sequence[int]] = None, **kwargs):
+        n = self.num_envs if indices is None else len(list(indices))
+        res = getattr(self.venv, method_name)(*args, **kwargs)
+        if torch.is_tensor(res):
+            res = res.cpu().numpy()
+        return [res] * n
+
+    def get_attr(self, name: str, indices=None):
+        n = self.num_envs if indices is None else len(list(indices))
+        return [getattr(self.venv, name)] * n
+
+    def set_attr(self, name: str, value, indices=None):
+        setattr(self.venv, name, value)
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False] * self.num_envs
+
+    def close(self):
+        self.venv.close()
+
+
+def make(env_id: str, num_envs: int, **kw):
+    """Batched counterpart of ``gym.make`` for the registered ids (gym_so100/__init__.py:4-32)."""
+    if env_id in ("gym_so100/SO100CubeToBin-v0", "SO100CubeToBin-v0"):
+        return SO100VecEnv(num_envs, task="so100_cube_to_bin", **kw)
+    if env_id in ("gym_so100/SO100Goal-v0", "SO100GoalEnv"):
+        return SO100GoalVecEnv(num_envs, **kw)
+    raise NotImplementedError(f"{env_id}: only the bin-a-cube envs are built (TouchCube variants: SURVEY 8f 'next')")

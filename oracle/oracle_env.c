@@ -319,6 +319,25 @@ int so100o_get_efc(const so100o* h, int i, int maxr, double* J, double* aref, do
   }
   return e->nefc;
 }
+/* reward truth-table hook for the golden vectors: synthetic contact list (MuJoCo geom ids, geom1 first)
+   and cube_site position on env 0, everything else as left by the last position stage */
+float so100o_test_reward(so100o* h, int ncon, const int32_t* geom_mjid_pairs, const double* cube_site) {
+  oenv* e = &h->env[0];
+  const so100_model* m = &h->m;
+  e->ncon = 0;
+  for (int c = 0; c < ncon && c < MAXCON; c++) {
+    int g[2] = {-1, -1};
+    for (int s = 0; s < 2; s++)
+      for (int k = 0; k < m->ngeom; k++)
+        if (m->geom_mjid[k] == geom_mjid_pairs[2 * c + s]) g[s] = k;
+    if (g[0] < 0 || g[1] < 0) return -1000.0f;
+    e->con[e->ncon].g1 = g[0]; e->con[e->ncon].g2 = g[1];
+    e->ncon++;
+  }
+  memcpy(e->site[m->site_cube], cube_site, 3 * sizeof(double));
+  return cube_to_bin_reward(h, e);
+}
+
 /* batched HER reward, env.py:346-349 */
 int so100o_compute_reward(const float* ag, const float* dg, int n, float thr, float* out) {
   for (int i = 0; i < n; i++) out[i] = goal_distance(ag + 3 * i, dg + 3 * i) < thr ? 0.0f : -1.0f;

@@ -144,6 +144,28 @@ class Oracle:
         return dict(J=J[:n], aref=aref[:n], R=R[:n], force=f[:n], jar=jar[:n])
 
 
+def test_reward(oracle: Oracle, contacts, cube_site) -> float:
+    """single_arm.py:322-380 on a synthetic contact list [(geom1_mjid, geom2_mjid), ...] and cube_site position."""
+    l = lib()
+    l.so100o_test_reward.restype = C.c_float
+    pairs = np.ascontiguousarray(np.asarray(contacts, dtype=np.int32).reshape(-1, 2))
+    site = np.ascontiguousarray(cube_site, dtype=np.float64)
+    return float(l.so100o_test_reward(C.c_void_p(oracle.h), len(pairs), _p(pairs), _p(site)))
+
+
+def test_box_pair(cA, RA, hA, cB, RB, hB):
+    """(SAT normal, SAT depth, EPA normal, EPA depth, n_sat_points, epa_hit) for two boxes (row-major R)."""
+    l = lib()
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (cA, RA, hA, cB, RB, hB)]
+    sat = np.zeros(4); epa = np.zeros(4)
+    rc = l.so100o_test_box_pair(*[_p(x) for x in a], _p(sat), _p(epa))
+    return sat[:3], sat[3], epa[:3], epa[3], rc // 16, rc % 16
+
+
+test_reward.__test__ = False
+test_box_pair.__test__ = False
+
+
 def compute_reward(ag, dg, thr=0.01):
     ag = np.ascontiguousarray(ag, dtype=np.float32).reshape(-1, 3)
     dg = np.ascontiguousarray(dg, dtype=np.float32).reshape(-1, 3)

@@ -104,10 +104,79 @@ def limits(n, seed=3):
     return _f32(qpos), _f32(qvel), _f32(ctrl)
 
 
+def _site_pose(qarm):
+    """ee_site position and Fixed_Jaw frame for one arm configuration (numpy FK of the loader)."""
+    from gym_so100_c_b200 import model
+    from gym_so100_c_b200.mjcf import quat_to_mat
+    m = model.load_model()
+    q = m["qpos0"].copy()
+    q[:6] = qarm
+    xpos, xquat = model.fk(m, q)
+    return xpos[8], quat_to_mat(xquat[8]), xquat[8]
+
+
+def _sample_filtered(n, seed, kind):
+    """Rejection-sample states whose ORACLE contact list contains general-hull pairs (GJK/EPA path):
+    kind = "arm": random arm configurations that touch the table / base / themselves;
+    kind = "grasp": cube dropped into the gripper gap (jaw hulls + pads against the cube)."""
+    from gym_so100_c_b200 import model
+    from oracle.so100_oracle import Oracle
+    m = model.load_model()
+    blob = model.pack(m)
+    hull_ids = {int(m["geom_mjid"][g]) for g in range(int(m["ngeom"])) if int(m["geom_type"][g]) == 7 and int(m["geom_vnum"][g]) != 8}
+    rng = np.random.default_rng(seed)
+    lo = np.array([-1.92, -3.32, -0.174, -1.66, -2.79, -0.174]) + 0.02
+    hi = np.array([1.92, 0.174, 3.14, 1.66, 2.79, 1.75]) - 0.02
+    keep_q, keep_v, keep_c = [], [], []
+    batch = 128
+    orc = Oracle(blob, batch)
+    while len(keep_q) < n:
+        qpos = np.zeros((batch, 13)); qvel = np.zeros((batch, 12)); ctrl = np.zeros((batch, 6))
+        if kind == "arm":
+            qpos[:, :6] = rng.uniform(lo, hi, size=(batch, 6))
+            qpos[:, 6:9] = [0.3, 0.3, 0.3]      # cube parked far away
+            qpos[:, 9] = 1
+            qpos[:, 9:13] = _rand_quat(rng, batch, np.pi)
+        else:
+            qpos[:, :6] = START + rng.uniform(-0.3, 0.3, size=(batch, 6))
+            qpos[:, 5] = rng.uniform(0.1, 1.2, batch)
+            for i in range(batch):
+                p8, R8, _ = _site_pose(qpos[i, :6])
+                local = np.array([rng.uniform(-0.03, 0.03), rng.uniform(-0.1, -0.03), rng.uniform(-0.015, 0.015)])
+                qpos[i, 6:9] = p8 + R8 @ local
+            qpos[:, 9:13] = _rand_quat(rng, batch, np.pi)
+        qvel[:, :6] = rng.uniform(-0.3, 0.3, size=(batch, 6))
+        qvel[:, 6:12] = rng.uniform(-0.2, 0.2, size=(batch, 6))
+        ctrl[:] = qpos[:, :6] + rng.uniform(-0.05, 0.05, size=(batch, 6))
+        qpos, qvel, ctrl = _f32(qpos), _f32(qvel), _f32(ctrl)
+        orc.set_state(qpos, qvel, ctrl, np.zeros((batch, 12)))
+        orc.forward()
+        for i in range(batch):
+            cs = orc.contacts(i)
+            if not cs or len(cs) > 16:
+                continue
+            has_hull = any(c["geom1"] in hull_ids or c["geom2"] in hull_ids for c in cs)
+            depth = max(-c["dist"] for c in cs)
+            if has_hull and 2e-5 < depth < 6e-3 and len(keep_q) < n:
+                keep_q.append(qpos[i]); keep_v.append(qvel[i]); keep_c.append(ctrl[i])
+    orc.close()
+    return np.stack(keep_q), np.stack(keep_v), np.stack(keep_c)
+
+
+def arm_hull_contacts(n, seed=5):
+    return _sample_filtered(n, seed, "arm")
+
+
+def grasp_hull_contacts(n, seed=6):
+    return _sample_filtered(n, seed, "grasp")
+
+
 ALL = {
     "free_space": free_space,
     "cube_on_table": cube_on_table,
     "cube_flat": lambda n, seed=4: cube_on_table(n, seed, flat=True),
     "cube_in_bin": cube_in_bin,
     "limits": limits,
+    "arm_hull_contacts": arm_hull_contacts,
+    "grasp_hull_contacts": grasp_hull_contacts,
 }

@@ -1,0 +1,125 @@
+"""CPU-side checks: the C-ABI library loads and exports exactly what include/so100_b200.h declares,
+fails loudly without a GPU (no fallback), and the host-side logic (spaces, seeding, sharding, the
+2-rank gloo statistics all-reduce) behaves."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "so100_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(so100_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gym_so100_c_b200 import build, ext
+    build.build()                        # nvcc cross-compiles sm_100a without a GPU
+    lib = C.CDLL(build.LIB)
+    declared = _declared_symbols()
+    assert set(declared) == set(ext.SYMBOLS), (declared, ext.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_library_contains_sm100a_code_only():
+    from gym_so100_c_b200 import build
+    out = subprocess.run(["cuobjdump", "-lelf", build.LIB], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_model_header_matches_dtype(model_blob):
+    from gym_so100_c_b200 import model
+    header = open(os.path.join(ROOT, "include", "so100_model.h")).read()
+    assert header == model.c_header()
+    assert f"#define SO100_MODEL_BYTES {len(model_blob)}" in header
+    m = model.unpack(model_blob)
+    assert int(m["magic"]) == model.MAGIC
+    with pytest.raises(ValueError):
+        model.unpack(model_blob[:-8])
+
+
+def test_create_fails_loudly_without_gpu(model_blob):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gym_so100_c_b200 import ext
+    lib = ext.load()
+    h = C.c_void_p()
+    rc = lib.so100_create(model_blob, len(model_blob), 4, 0, 0, C.c_uint64(0), C.c_int64(0), C.byref(h))
+    assert rc == -2 and b"no CPU path" in lib.so100_last_error()
+    rc = lib.so100_create(model_blob[:100], 100, 4, 0, 0, C.c_uint64(0), C.c_int64(0), C.byref(h))
+    assert rc == -1
+    from gym_so100_c_b200.vec_env import SO100VecEnv
+    with pytest.raises(ext.So100Error):
+        SO100VecEnv(4)
+    with pytest.raises(NotImplementedError):
+        SO100VecEnv(4, task="so100_touch_cube")
+    with pytest.raises(NotImplementedError):
+        SO100VecEnv(4, obs_type="so100_pixels_agent_pos")
+
+
+def test_spaces_shim():
+    from gym_so100_c_b200.spaces import Box, Dict, batch_box
+    a = Box(low=-1, high=1, shape=(6,), dtype=np.float32)
+    assert a.shape == (6,) and a.contains(a.sample()) and not a.contains(np.full(6, 2, np.float32))
+    b = batch_box(a, 5)
+    assert b.shape == (5, 6)
+    d = Dict({"x": a})
+    assert d.contains({"x": a.sample()})
+
+
+def test_shard_ranges_partition():
+    from gym_so100_c_b200.parallel import shard_range
+    for n in (1, 7, 16384, 1048576, 1000003):
+        for world in (1, 2, 4, 8):
+            r = [shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from gym_so100_c_b200 import parallel
+rank, world, local = parallel.init_from_env(backend="gloo")
+lo, hi = parallel.shard_range(1001, rank, world)
+stats = {k: (rank + 1) * (i + 1) for i, k in enumerate(parallel.STAT_KEYS)}
+stats["episodes"] = hi - lo
+tot = parallel.all_reduce_stats(stats)
+mx = parallel.max_over_ranks(10.0 + rank)
+parallel.barrier()
+assert tot["episodes"] == 1001, tot
+assert tot["contact_overflow"] == sum(range(1, world + 1)), tot
+assert mx == 10.0 + world - 1, mx
+if rank == 0:
+    print("GLOO_OK", world, tot["episodes"])
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_statistics(tmp_path):
+    """world_size-2 gloo run of the N>1 host path: shard ranges + episode-statistics all-reduce + max-over-ranks."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GLOO_OK 2 1001" in out.stdout
