@@ -111,14 +111,14 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n = 4 * cores
+    n = 128 * cores
     value, dt, cores = cpu_arm(n, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "BASELINE config 3: full bin-a-cube with contacts, random actions U(-1,1), auto-reset",
-                   "envs_per_step": n, "note": "bounded sample of the 16384-env batch: 4 envs per host core per step"},
+                   "envs_per_step": n, "note": "bounded sample of the 16384-env batch: 128 envs per host core per step"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{n} envs x {args.steps} steps, fp64 C restatement of the step (oracle/), OpenMP over envs; "
                                    "MuJoCo/dm_control are not installable in this image"},
@@ -202,9 +202,9 @@ def run_gpu(args):
             pass
         fp32_tflops = FLOP_PER_ENV_STEP * nl / (kernel_ms * 1e-3) / 1e12
         cores = os.cpu_count() or 1
-        cpu_n = 4 * cores
+        cpu_n, cpu_steps = 128 * cores, 50
         # reported baseline, rank 0 at N=1 only (multi-GPU lines carry null)
-        cpu_value, cpu_dt, cores = cpu_arm(cpu_n, steps=3, warmup=1) if world == 1 else (None, None, cores)
+        cpu_value, cpu_dt, cores = cpu_arm(cpu_n, steps=cpu_steps, warmup=2) if world == 1 else (None, None, cores)
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -220,7 +220,7 @@ def run_gpu(args):
                                              "peak_tflops_nominal": FP32_PEAK_NOMINAL_TFLOPS,
                                              "frac": fp32_tflops / FP32_PEAK_NOMINAL_TFLOPS}},
             "cpu_baseline": {"value": cpu_value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                             "sample": f"{cpu_n} envs x 3 steps of the same workload, fp64 C restatement (oracle/), OpenMP over envs"},
+                             "sample": f"{cpu_n} envs x {cpu_steps} steps of the same workload, fp64 C restatement (oracle/), OpenMP over envs"},
             "e2e": {"value": n_total * Ke / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "steps": Ke},
             "gpu_launches": K,

@@ -11,7 +11,7 @@ from parity_util import contact_errors, gpu_contacts, inject, make_pair, match_c
 pytestmark = pytest.mark.gpu
 
 N = 64
-CONTACT_FREE = ("free_space", "limits")
+CONTACT_FREE = ("free_space",)
 
 
 @pytest.mark.parametrize("name", list(scenarios.ALL))
