@@ -29,11 +29,17 @@ def needs_build() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, lanes_per_env: int | None = None) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, lanes_per_env: int | None = None, profile: bool = False,
+          out: str | None = None) -> str:
+    """`profile=True` builds the development variant with per-stage clock64 counters (libso100_b200_prof.so);
+    point SO100_LIB at it to load it instead of the product library."""
+    target = out or (os.path.join(HERE, "libso100_b200_prof.so") if profile else LIB)
+    if not force and not profile and out is None and not needs_build():
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB]
+           "-Xcompiler", "-fPIC", "-shared", "-o", target]
+    if profile:
+        cmd.append("-DSO100_PROFILE")
     if lanes_per_env:
         cmd.append(f"-DSO100_LPE={int(lanes_per_env)}")
     if verbose:
@@ -43,7 +49,7 @@ def build(force: bool = False, verbose: bool = False, lanes_per_env: int | None 
     env.pop("CC", None)
     env.pop("CXX", None)
     subprocess.check_call(cmd, env=env)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -12,6 +12,7 @@
 
 namespace so100 { constexpr int SO100_NDIAG_K = SO100_NDIAG; }
 #include "so100_kernels.cuh"
+#include "so100_phases.cuh"
 
 using namespace so100;
 
@@ -33,7 +34,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 struct so100_ctx {
-  int n = 0, device = 0, task = 0;
+  int n = 0, device = 0, task = 0, nsub = 10;
   uint64_t seed = 0;
   int64_t env_offset = 0;
   float* state = nullptr;
@@ -41,6 +42,8 @@ struct so100_ctx {
   DevPair* pair = nullptr;
   float4* vert = nullptr;
   unsigned long long* diag = nullptr;
+  float* work = nullptr;      // [N, WORK_WORDS] phase-pipeline workspace (L2-resident)
+  bool fused = false;         // SO100_FUSED=1: single fused step kernel (kept for A/B measurements)
   // staging for the host-buffer entry point
   float *h_action = nullptr, *h_obs = nullptr, *h_ag = nullptr, *h_dg = nullptr, *h_rew = nullptr, *h_fin = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_succ = nullptr;
@@ -285,10 +288,14 @@ static int configure_kernels() {
   static bool done = false;
   if (done) return SO100_OK;
   const int bytes = (int)smem_bytes();
-  CUDA_OK(cudaFuncSetAttribute(step_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(step_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SO100_BLOCK / LPE) * sizeof(EnvS))));
   CUDA_OK(cudaFuncSetAttribute(reset_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(substeps_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(forward_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(phase_kin_dyn<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(phase_collide<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(phase_solve<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(phase_task<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   done = true;
   return SO100_OK;
 }
@@ -321,12 +328,19 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   if (rc) return rc;
   so100_ctx* h = new so100_ctx();
   h->n = num_envs; h->device = device; h->task = task; h->seed = seed; h->env_offset = env_offset;
+  h->nsub = m.nsubstep;
   CUDA_OK(cudaMemcpyToSymbol(c_m, &dm, sizeof(dm)));
   CUDA_OK(cudaMalloc(&h->state, (size_t)num_envs * STATE_WORDS * sizeof(float)));
   CUDA_OK(cudaMalloc(&h->geom, geoms.size() * sizeof(DevGeom)));
   CUDA_OK(cudaMalloc(&h->pair, pairs.size() * sizeof(DevPair)));
   CUDA_OK(cudaMalloc(&h->vert, std::max<size_t>(verts.size(), 1) * sizeof(float4)));
   CUDA_OK(cudaMalloc(&h->diag, SO100_NDIAG * sizeof(unsigned long long)));
+  CUDA_OK(cudaMalloc(&h->work, (size_t)num_envs * WORK_WORDS * sizeof(float)));
+  CUDA_OK(cudaMemset(h->work, 0, (size_t)num_envs * WORK_WORDS * sizeof(float)));
+  {
+    const char* f = getenv("SO100_FUSED");
+    h->fused = f && f[0] == '1';
+  }
   CUDA_OK(cudaMemcpy(h->geom, geoms.data(), geoms.size() * sizeof(DevGeom), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(h->pair, pairs.data(), pairs.size() * sizeof(DevPair), cudaMemcpyHostToDevice));
   if (!verts.empty()) CUDA_OK(cudaMemcpy(h->vert, verts.data(), verts.size() * sizeof(float4), cudaMemcpyHostToDevice));
@@ -341,7 +355,7 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
 int so100_destroy(so100_handle h) {
   if (!h) return SO100_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->state); cudaFree(h->geom); cudaFree(h->pair); cudaFree(h->vert); cudaFree(h->diag);
+  cudaFree(h->state); cudaFree(h->geom); cudaFree(h->pair); cudaFree(h->vert); cudaFree(h->diag); cudaFree(h->work);
   cudaFree(h->h_action); cudaFree(h->h_obs); cudaFree(h->h_ag); cudaFree(h->h_dg); cudaFree(h->h_rew); cudaFree(h->h_fin);
   cudaFree(h->h_term); cudaFree(h->h_trunc); cudaFree(h->h_succ);
   delete h;
@@ -369,7 +383,24 @@ int so100_step(so100_handle h, const float* action, int autoreset, float* obs, f
   A.final_obs = final_obs; A.terminated = terminated; A.truncated = truncated; A.success = success;
   A.n = h->n; A.autoreset = autoreset; A.task = h->task;
   A.seed_lo = (uint32_t)h->seed; A.seed_hi = (uint32_t)(h->seed >> 32); A.env_offset = h->env_offset;
-  step_kernel<LPE><<<grid_for(h->n), BLOCK, smem_bytes(), (cudaStream_t)stream>>>(A, h->tables());
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->fused) {
+    constexpr int epb_step = SO100_BLOCK / LPE;
+    step_kernel<LPE><<<(h->n + epb_step - 1) / epb_step, SO100_BLOCK, (size_t)epb_step * sizeof(EnvS), st>>>(A, h->tables());
+  } else {
+    // phase pipeline (so100_phases.cuh): 3 small kernels per substep + trailing forward + task layer
+    const int grid = grid_for(h->n);
+    const size_t smem = smem_bytes();
+    const DevTables T = h->tables();
+    for (int s = 0; s < h->nsub; s++) {
+      phase_kin_dyn<LPE><<<grid, BLOCK, smem, st>>>(h->state, h->work, s == 0 ? action : nullptr, h->n, 1);
+      phase_collide<LPE><<<grid, BLOCK, smem, st>>>(h->work, h->n, T);
+      phase_solve<LPE><<<grid, BLOCK, smem, st>>>(h->state, h->work, h->n, T);
+    }
+    phase_kin_dyn<LPE><<<grid, BLOCK, smem, st>>>(h->state, h->work, h->nsub == 0 ? action : nullptr, h->n, 0);
+    phase_collide<LPE><<<grid, BLOCK, smem, st>>>(h->work, h->n, T);
+    phase_task<LPE><<<grid, BLOCK, smem, st>>>(A, h->work, T);
+  }
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
@@ -452,6 +483,17 @@ int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom,
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
+
+#ifdef SO100_PROFILE
+// development builds only: read and clear the per-stage SM-cycle counters
+int so100_profile(unsigned long long* out8) {
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpyFromSymbol(out8, g_prof, 8 * sizeof(unsigned long long)));
+  unsigned long long zero[8] = {0};
+  CUDA_OK(cudaMemcpyToSymbol(g_prof, zero, sizeof(zero)));
+  return SO100_OK;
+}
+#endif
 
 int so100_diagnostics(so100_handle h, int64_t* out8, void* stream) {
   if (!h || !out8) return fail(SO100_ERR_ARG, "so100_diagnostics: bad argument");

@@ -28,16 +28,33 @@ template <unsigned LPE> __device__ __forceinline__ void store_state(const Tile<L
 }
 
 // one full MuJoCo substep (mj_step) on the state in S->st
+#ifdef SO100_PHASE_SYNC
+#define PHASE_SYNC() __syncthreads()
+#else
+#define PHASE_SYNC() do { } while (0)
+#endif
 template <unsigned LPE> __device__ void substep(const Tile<LPE>& t, EnvS* S, const DevTables& T) {
+  PROF_BEGIN();
+  PHASE_SYNC();
   kinematics(t, S);
   mass_matrix(t, S);
   t.sync();
+  PROF_MARK(0);
+  PHASE_SYNC();
   smooth_forces(t, S);
   const float qas = smooth_acc(t, S);
+  PROF_MARK(1);
+  PHASE_SYNC();
   collide(t, S, T);
+  PROF_MARK(2);
+  PHASE_SYNC();
   make_contact_rows(t, S, T);
+  PROF_MARK(3);
   solve(t, S, T, qas, reinterpret_cast<uint32_t*>(&S->st[S_DIAG]));
+  PROF_MARK(4);
+  PHASE_SYNC();
   integrate(t, S);
+  PROF_MARK(5);
 }
 
 // utils.py:18-29 / single_arm.py:299-309 / env.py:322-334 on the device
@@ -112,9 +129,15 @@ __device__ __forceinline__ void write_obs(const Tile<LPE>& t, const EnvS* S, int
   }
 }
 
-template <unsigned LPE> __global__ void __launch_bounds__(128) step_kernel(StepArgs A, DevTables T) {
+#ifndef SO100_MINB
+#define SO100_MINB 3     // resident 128-thread blocks per SM the register allocation must allow
+#endif
+#ifndef SO100_BLOCK
+#define SO100_BLOCK 128  // threads per block of the fused step kernel
+#endif
+template <unsigned LPE> __global__ void __launch_bounds__(SO100_BLOCK, SO100_MINB) step_kernel(StepArgs A, DevTables T) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int EPB = 128 / LPE;
+  constexpr int EPB = SO100_BLOCK / LPE;
   cg::thread_block blk = cg::this_thread_block();
   Tile<LPE> t = cg::tiled_partition<LPE>(blk);
   const int env = blockIdx.x * EPB + t.meta_group_rank();

@@ -18,6 +18,17 @@ namespace cg = cooperative_groups;
 
 __constant__ DevModel c_m;
 
+#ifdef SO100_PROFILE
+// per-stage SM-cycle counters (development builds only: -DSO100_PROFILE); slots:
+// 0 kinematics+M, 1 bias/actuation, 2 collide total, 3 contact rows, 4 solve, 5 integrate, 6 broad phase, 7 box stage
+__device__ unsigned long long g_prof[8];
+#define PROF_MARK(k) do { long long now_ = clock64(); if (t.thread_rank() == 0) atomicAdd(&g_prof[k], (unsigned long long)(now_ - tp_)); tp_ = now_; } while (0)
+#define PROF_BEGIN() long long tp_ = clock64()
+#else
+#define PROF_MARK(k) do { } while (0)
+#define PROF_BEGIN() do { } while (0)
+#endif
+
 struct DevTables {
   const DevGeom* geom;
   const DevPair* pair;
@@ -424,6 +435,7 @@ template <unsigned LPE> __device__ void hull_stage(const Tile<LPE>& t, EnvS* S, 
 
 template <unsigned LPE> __device__ void collide(const Tile<LPE>& t, EnvS* S, const DevTables& T) {
   const int lane = t.thread_rank();
+  PROF_BEGIN();
   // world OBB centres
   for (int g = lane; g < c_m.ngeom; g += LPE) {
     const DevGeom& G = T.geom[g];
@@ -463,6 +475,7 @@ template <unsigned LPE> __device__ void collide(const Tile<LPE>& t, EnvS* S, con
     nbox += __popc(mb); nhull += __popc(mh);
   }
   t.sync();
+  PROF_MARK(6);
   // stage 2a: box-like pairs, one lane per pair, deterministic append order (pair order)
   for (int base = 0; base < nbox; base += LPE) {
     const int k = base + lane;
@@ -503,6 +516,7 @@ template <unsigned LPE> __device__ void collide(const Tile<LPE>& t, EnvS* S, con
     if (lane == 0) S->ncon = min(S->ncon + total, NC + 1);   // NC+1 marks overflow
     t.sync();
   }
+  PROF_MARK(7);
   // stage 2b: pairs that involve a general hull (so100_gjk.cuh)
   hull_stage(t, S, T, nhull);
 }

@@ -29,7 +29,7 @@ class So100Error(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB
+    return os.environ.get("SO100_LIB") or _build.LIB
 
 
 def load():
