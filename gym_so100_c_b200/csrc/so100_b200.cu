@@ -282,6 +282,22 @@ static int build_dev_model(const so100_model& m, DevModel& dm, std::vector<DevGe
 
 // ------------------------------------------------------------------ launches
 static size_t smem_bytes() { return (size_t)EPB * sizeof(EnvS); }
+// per-phase tile widths (lanes per env) of the phase pipeline
+#ifndef SO100_LPE_K1
+#define SO100_LPE_K1 SO100_LPE
+#endif
+#ifndef SO100_LPE_K2
+#define SO100_LPE_K2 SO100_LPE
+#endif
+#ifndef SO100_LPE_K3
+#define SO100_LPE_K3 SO100_LPE
+#endif
+#ifndef SO100_LPE_K4
+#define SO100_LPE_K4 SO100_LPE
+#endif
+constexpr unsigned LPE_K1 = SO100_LPE_K1, LPE_K2 = SO100_LPE_K2, LPE_K3 = SO100_LPE_K3, LPE_K4 = SO100_LPE_K4;
+static size_t phase_smem(unsigned lpe) { return (size_t)(BLOCK / lpe) * sizeof(EnvS); }
+static int phase_grid(int n, unsigned lpe) { const int epb = BLOCK / (int)lpe; return (n + epb - 1) / epb; }
 static int grid_for(int n) { return (n + EPB - 1) / EPB; }
 
 static int configure_kernels() {
@@ -292,10 +308,10 @@ static int configure_kernels() {
   CUDA_OK(cudaFuncSetAttribute(reset_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(substeps_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(forward_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_OK(cudaFuncSetAttribute(phase_kin_dyn<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_OK(cudaFuncSetAttribute(phase_collide<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_OK(cudaFuncSetAttribute(phase_solve<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_OK(cudaFuncSetAttribute(phase_task<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(phase_kin_dyn<LPE_K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase_smem(LPE_K1)));
+  CUDA_OK(cudaFuncSetAttribute(phase_collide<LPE_K2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase_smem(LPE_K2)));
+  CUDA_OK(cudaFuncSetAttribute(phase_solve<LPE_K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase_smem(LPE_K3)));
+  CUDA_OK(cudaFuncSetAttribute(phase_task<LPE_K4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase_smem(LPE_K4)));
   done = true;
   return SO100_OK;
 }
@@ -389,17 +405,16 @@ int so100_step(so100_handle h, const float* action, int autoreset, float* obs, f
     step_kernel<LPE><<<(h->n + epb_step - 1) / epb_step, SO100_BLOCK, (size_t)epb_step * sizeof(EnvS), st>>>(A, h->tables());
   } else {
     // phase pipeline (so100_phases.cuh): 3 small kernels per substep + trailing forward + task layer
-    const int grid = grid_for(h->n);
-    const size_t smem = smem_bytes();
     const DevTables T = h->tables();
+    const int n = h->n;
     for (int s = 0; s < h->nsub; s++) {
-      phase_kin_dyn<LPE><<<grid, BLOCK, smem, st>>>(h->state, h->work, s == 0 ? action : nullptr, h->n, 1);
-      phase_collide<LPE><<<grid, BLOCK, smem, st>>>(h->work, h->n, T);
-      phase_solve<LPE><<<grid, BLOCK, smem, st>>>(h->state, h->work, h->n, T);
+      phase_kin_dyn<LPE_K1><<<phase_grid(n, LPE_K1), BLOCK, phase_smem(LPE_K1), st>>>(h->state, h->work, s == 0 ? action : nullptr, n, 1);
+      phase_collide<LPE_K2><<<phase_grid(n, LPE_K2), BLOCK, phase_smem(LPE_K2), st>>>(h->work, n, T);
+      phase_solve<LPE_K3><<<phase_grid(n, LPE_K3), BLOCK, phase_smem(LPE_K3), st>>>(h->state, h->work, n, T);
     }
-    phase_kin_dyn<LPE><<<grid, BLOCK, smem, st>>>(h->state, h->work, h->nsub == 0 ? action : nullptr, h->n, 0);
-    phase_collide<LPE><<<grid, BLOCK, smem, st>>>(h->work, h->n, T);
-    phase_task<LPE><<<grid, BLOCK, smem, st>>>(A, h->work, T);
+    phase_kin_dyn<LPE_K1><<<phase_grid(n, LPE_K1), BLOCK, phase_smem(LPE_K1), st>>>(h->state, h->work, h->nsub == 0 ? action : nullptr, n, 0);
+    phase_collide<LPE_K2><<<phase_grid(n, LPE_K2), BLOCK, phase_smem(LPE_K2), st>>>(h->work, n, T);
+    phase_task<LPE_K4><<<phase_grid(n, LPE_K4), BLOCK, phase_smem(LPE_K4), st>>>(A, h->work, T);
   }
   CUDA_OK(cudaGetLastError());
   return SO100_OK;

@@ -1,0 +1,295 @@
+// Collision driver (App. A step 3): static candidate-pair list -> sphere / sphere-vs-box cull ->
+//   box-like pairs: separating-axis test with one lane per pair, then contact generation with the
+//                   whole tile per penetrating pair (24 candidate points, one per lane: incident-face
+//                   corners, incident-edge x reference-edge intersections, reference corners under the
+//                   incident face -- the vertices of the clipped incident polygon);
+//   hull pairs:     oriented-box cull, then GJK/EPA with the tile per pair (so100_gjk.cuh).
+// Contacts are appended in pair order, so the contact list is deterministic.
+#pragma once
+#include "so100_gjk.cuh"
+
+namespace so100 {
+
+// 15-axis separating-axis test.  Returns false when separated; otherwise `code` = 0..5 (face axis of
+// A / B) or 6 + 3 i + j (edge axis A_i x B_j) and `sep` < 0 the signed separation along it.
+__device__ __forceinline__ bool box_sat(const Obb& A, const Obb& B, int& code, float& sep_out) {
+  float R[3][3], aR[3][3], tA[3], tB[3];
+  const V3 t = B.c - A.c;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    tA[i] = dot(t, A.ax[i]);
+    tB[i] = dot(t, B.ax[i]);
+#pragma unroll
+    for (int j = 0; j < 3; j++) { R[i][j] = dot(A.ax[i], B.ax[j]); aR[i][j] = fabsf(R[i][j]); }
+  }
+  float best_face = -1e30f;
+  code = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float sep = fabsf(tA[i]) - (A.h[i] + B.h[0] * aR[i][0] + B.h[1] * aR[i][1] + B.h[2] * aR[i][2]);
+    if (sep > 0) return false;
+    if (sep > best_face) { best_face = sep; code = i; }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const float sep = fabsf(tB[j]) - (B.h[j] + A.h[0] * aR[0][j] + A.h[1] * aR[1][j] + A.h[2] * aR[2][j]);
+    if (sep > 0) return false;
+    if (sep > best_face) { best_face = sep; code = 3 + j; }
+  }
+  float best_edge = -1e30f, best_sel = -1e30f;
+  int ecode = -1;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const float l2 = 1.0f - R[i][j] * R[i][j];
+      if (l2 < EDGE_MIN_SIN2) continue;      // (near-)parallel edges: the face axes cover this direction
+      const float inv = rsqrtf(l2);
+      const float ra = A.h[i1] * aR[i2][j] + A.h[i2] * aR[i1][j];
+      const float rb = B.h[j1] * aR[i][j2] + B.h[j2] * aR[i][j1];
+      const float sep = (fabsf(tA[i2] * R[i1][j] - tA[i1] * R[i2][j]) - (ra + rb)) * inv;
+      if (sep > 0) return false;
+      const float sel = sep - EDGE_BIAS * inv;
+      if (sel > best_sel) { best_sel = sel; best_edge = sep; ecode = 6 + 3 * i + j; }
+    }
+  }
+  sep_out = best_face;
+  if (ecode >= 0 && best_sel * 1.05f > best_face) { code = ecode; sep_out = best_edge; }
+  return true;
+}
+
+template <unsigned LPE> __device__ __forceinline__ void tsum2x(const Tile<LPE>& t, float& a, float& b) {
+#pragma unroll
+  for (int off = LPE / 2; off > 0; off >>= 1) {
+    a += t.shfl_xor(a, off);
+    b += t.shfl_xor(b, off);
+  }
+}
+
+__device__ __forceinline__ V3 sel_axis(const Obb& b, int k) { return k == 0 ? b.ax[0] : (k == 1 ? b.ax[1] : b.ax[2]); }
+__device__ __forceinline__ float sel_h(const Obb& b, int k) { return k == 0 ? b.h[0] : (k == 1 ? b.h[1] : b.h[2]); }
+
+// Contact generation for one penetrating box pair with the whole tile.  Appends up to 8 contacts
+// (1 when `single`) at S->ncon; every lane returns the number appended.
+template <unsigned LPE>
+__device__ int box_contacts(const Tile<LPE>& t, EnvS* S, const Obb& A, const Obb& B, int code, float sep, bool single, int pair) {
+  static_assert(LPE >= 24, "box_contacts needs one lane per candidate point (24)");
+  const int lane = t.thread_rank();
+  const int base = S->ncon;
+  const V3 tAB = B.c - A.c;
+  if (code >= 6) {
+    // edge-edge: one point midway between the closest points of the two edges
+    const int ei = (code - 6) / 3, ej = (code - 6) % 3;
+    const V3 ea = sel_axis(A, ei), eb = sel_axis(B, ej);
+    V3 n = normalized(cross(ea, eb));
+    if (dot(n, tAB) < 0) n = -n;
+    V3 pA = A.c, pB = B.c;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (k != ei) pA = pA + A.ax[k] * (dot(n, A.ax[k]) > 0 ? A.h[k] : -A.h[k]);
+      if (k != ej) pB = pB + B.ax[k] * (dot(n, B.ax[k]) > 0 ? -B.h[k] : B.h[k]);
+    }
+    const V3 r = pA - pB;
+    const float b = dot(ea, eb), d = dot(ea, r), e = dot(eb, r), den = 1.0f - b * b;
+    const float s = (b * e - d) / den, u = (e - b * d) / den;
+    const V3 q = ((pA + ea * s) + (pB + eb * u)) * 0.5f;
+    if (lane == 0 && base < NC) { st3(S->cpos[base], q); st3(S->cnrm[base], n); S->cdist[base] = sep; S->cpair[base] = (unsigned char)pair; }
+    return 1;
+  }
+  // face contact: the reference box owns the axis
+  const bool refA = code < 3;
+  const Obb& Rf = refA ? A : B;
+  const Obb& If = refA ? B : A;
+  const int ax = refA ? code : code - 3;
+  const int ua = (ax + 1) % 3, va = (ax + 2) % 3;
+  const V3 axn = sel_axis(Rf, ax), axu = sel_axis(Rf, ua), axv = sel_axis(Rf, va);
+  const float hn = sel_h(Rf, ax), hu = sel_h(Rf, ua), hv = sel_h(Rf, va);
+  const V3 rel = If.c - Rf.c;
+  const V3 nref = dot(axn, rel) < 0 ? -axn : axn;              // outward normal of the reference face
+  // incident face: the face of the other box most anti-parallel to nref
+  const float d0 = dot(If.ax[0], nref), d1 = dot(If.ax[1], nref), d2 = dot(If.ax[2], nref);
+  int iax = 0; float bd = fabsf(d0), ds = d0;
+  if (fabsf(d1) > bd) { bd = fabsf(d1); iax = 1; ds = d1; }
+  if (fabsf(d2) > bd) { bd = fabsf(d2); iax = 2; ds = d2; }
+  const float isg = ds > 0 ? -1.0f : 1.0f;
+  const int iu = (iax + 1) % 3, iv = (iax + 2) % 3;
+  const V3 fc = rel + sel_axis(If, iax) * (isg * sel_h(If, iax));
+  const V3 eu = sel_axis(If, iu) * sel_h(If, iu), ev = sel_axis(If, iv) * sel_h(If, iv);
+  // incident corners in reference coordinates (u, v, n), counter-clockwise in the incident face
+  float pu[4], pv[4], pn[4];
+  {
+    const float su[4] = {1, -1, -1, 1}, sv[4] = {1, 1, -1, -1};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const V3 p = fc + eu * su[q] + ev * sv[q];
+      pu[q] = dot(p, axu); pv[q] = dot(p, axv); pn[q] = dot(p, nref);
+    }
+  }
+  bool valid = false;
+  float cu = 0, cv = 0, cn = 0;
+  {
+    const int k = lane;
+    if (k < 4) {
+      cu = k == 0 ? pu[0] : (k == 1 ? pu[1] : (k == 2 ? pu[2] : pu[3]));
+      cv = k == 0 ? pv[0] : (k == 1 ? pv[1] : (k == 2 ? pv[2] : pv[3]));
+      cn = k == 0 ? pn[0] : (k == 1 ? pn[1] : (k == 2 ? pn[2] : pn[3]));
+      valid = fabsf(cu) <= hu && fabsf(cv) <= hv;
+    } else if (k < 20) {
+      const int e = (k - 4) >> 2, l = (k - 4) & 3, e2 = (e + 1) & 3;
+      const float au = e == 0 ? pu[0] : (e == 1 ? pu[1] : (e == 2 ? pu[2] : pu[3]));
+      const float av = e == 0 ? pv[0] : (e == 1 ? pv[1] : (e == 2 ? pv[2] : pv[3]));
+      const float an = e == 0 ? pn[0] : (e == 1 ? pn[1] : (e == 2 ? pn[2] : pn[3]));
+      const float bu = e2 == 0 ? pu[0] : (e2 == 1 ? pu[1] : (e2 == 2 ? pu[2] : pu[3]));
+      const float bv = e2 == 0 ? pv[0] : (e2 == 1 ? pv[1] : (e2 == 2 ? pv[2] : pv[3]));
+      const float bn = e2 == 0 ? pn[0] : (e2 == 1 ? pn[1] : (e2 == 2 ? pn[2] : pn[3]));
+      const bool onu = l < 2;                                   // clip line u = +-hu, else v = +-hv
+      const float lim = (l & 1) ? -(onu ? hu : hv) : (onu ? hu : hv);
+      const float da = (onu ? au : av) - lim, db = (onu ? bu : bv) - lim;
+      if ((da < 0 && db > 0) || (da > 0 && db < 0)) {
+        const float tt = da / (da - db);
+        cu = au + tt * (bu - au); cv = av + tt * (bv - av); cn = an + tt * (bn - an);
+        if (onu) { cu = lim; valid = fabsf(cv) <= hv; } else { cv = lim; valid = fabsf(cu) <= hu; }
+      }
+    } else if (k < 24) {
+      const int q = k - 20;
+      cu = (q == 0 || q == 3) ? hu : -hu;
+      cv = (q < 2) ? hv : -hv;
+      // inside the incident quad (strictly: boundary cases are produced by the edge candidates)
+      bool pos = true, neg = true;
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int e2 = (e + 1) & 3;
+        const float cr = (pu[e2] - pu[e]) * (cv - pv[e]) - (pv[e2] - pv[e]) * (cu - pu[e]);
+        pos = pos && cr > 0; neg = neg && cr < 0;
+      }
+      if (pos || neg) {
+        // height of the incident plane above (cu, cv)
+        const float e1u = pu[1] - pu[0], e1v = pv[1] - pv[0], e1n = pn[1] - pn[0];
+        const float e2u = pu[3] - pu[0], e2v = pv[3] - pv[0], e2n = pn[3] - pn[0];
+        const float Nu = e1v * e2n - e1n * e2v, Nv = e1n * e2u - e1u * e2n, Nn = e1u * e2v - e1v * e2u;
+        cn = pn[0] - (Nu * (cu - pu[0]) + Nv * (cv - pv[0])) / Nn;
+        valid = fabsf(Nn) > 1e-20f;
+      }
+    }
+  }
+  const float depth = hn - cn;
+  valid = valid && depth > 0;
+  const V3 nout = refA ? nref : -nref;                          // always geom1 -> geom2
+  const V3 p = Rf.c + axu * cu + axv * cv + nref * (cn + 0.5f * depth);
+  if (single) {
+    // mjc_Convex semantics (one contact per pair): deepest feature, centroid if it is not a single vertex
+    float dmax = valid ? depth : -1.0f;
+#pragma unroll
+    for (int off = LPE / 2; off > 0; off >>= 1) dmax = fmaxf(dmax, t.shfl_xor(dmax, off));
+    if (dmax <= 0) return 0;
+    const bool deep = valid && depth >= dmax - 1e-6f;
+    float sx = deep ? p.x : 0, sy = deep ? p.y : 0, sz = deep ? p.z : 0, cnt = deep ? 1.0f : 0.0f;
+    tsum2x(t, sx, sy);
+    tsum2x(t, sz, cnt);
+    if (lane == 0 && base < NC) {
+      const float ic = 1.0f / cnt;
+      st3(S->cpos[base], mk(sx * ic, sy * ic, sz * ic)); st3(S->cnrm[base], nout); S->cdist[base] = -dmax; S->cpair[base] = (unsigned char)pair;
+    }
+    return 1;
+  }
+  const unsigned m = t.ballot(valid);
+  const int slot = __popc(m & ((1u << lane) - 1u));
+  const int total = min(__popc(m), 8);
+  if (valid && slot < 8 && base + slot < NC) {
+    const int c = base + slot;
+    st3(S->cpos[c], p); st3(S->cnrm[c], nout); S->cdist[c] = -depth; S->cpair[c] = (unsigned char)pair;
+  }
+  return total;
+}
+
+template <unsigned LPE> __device__ void collide_env(const Tile<LPE>& t, EnvS* S, const DevTables& T) {
+  const int lane = t.thread_rank();
+  PROF_BEGIN();
+  // world OBB centres
+  for (int g = lane; g < c_m.ngeom; g += LPE) {
+    const DevGeom& G = T.geom[g];
+    V3 c = ld3(G.center);
+    if (G.link >= 0) c = ld3(S->lpos[G.link]) + mulmv(S->lmat[G.link], c);
+    st3(S->gcen[g], c);
+  }
+  if (lane == 0) { S->ncon = 0; }
+  t.sync();
+  // stage 1: bounding sphere vs sphere, sphere vs oriented box (both ways); compact survivors by mode
+  int nbox = 0, nhull = 0;
+  for (int base = 0; base < c_m.npair; base += LPE) {
+    const int p = base + lane;
+    int pass = 0, mode = 0;
+    if (p < c_m.npair) {
+      const DevPair& P = T.pair[p];
+      const DevGeom& G1 = T.geom[P.g1];
+      const DevGeom& G2 = T.geom[P.g2];
+      const V3 c1 = ld3(S->gcen[P.g1]), c2 = ld3(S->gcen[P.g2]);
+      const V3 d = c2 - c1;
+      const float rr = G1.rbound + G2.rbound;
+      if (dot(d, d) <= rr * rr) {
+        Obb b1, b2;
+        load_obb(S, G1, P.g1, b1);
+        load_obb(S, G2, P.g2, b2);
+        if (point_obb_d2(c1, b2) <= G1.rbound * G1.rbound && point_obb_d2(c2, b1) <= G2.rbound * G2.rbound) {
+          pass = 1; mode = P.mode;
+        }
+      }
+    }
+    const unsigned mb = t.ballot(pass && mode != MODE_HULL), mh = t.ballot(pass && mode == MODE_HULL);
+    const unsigned lt = (1u << lane) - 1u;
+    if (pass) {
+      if (mode != MODE_HULL) S->w.col.qbox[nbox + __popc(mb & lt)] = (unsigned char)p;
+      else S->w.col.qhull[nhull + __popc(mh & lt)] = (unsigned char)p;
+    }
+    nbox += __popc(mb); nhull += __popc(mh);
+  }
+  t.sync();
+  PROF_MARK(6);
+  // stage 2a: separating-axis test, one lane per box-like pair; penetrating pairs are compacted into q1
+  // together with their axis code (kept in registers of the lane that found it and re-derived below)
+  int npen = 0;
+  for (int base = 0; base < nbox; base += LPE) {
+    const int k = base + lane;
+    bool hit = false;
+    int p = 0, code = 0;
+    float sep = 0;
+    if (k < nbox) {
+      p = S->w.col.qbox[k];
+      const DevPair& P = T.pair[p];
+      Obb A, B;
+      load_obb(S, T.geom[P.g1], P.g1, A);
+      load_obb(S, T.geom[P.g2], P.g2, B);
+      hit = box_sat(A, B, code, sep);
+    }
+    const unsigned m = t.ballot(hit);
+    if (hit) {
+      const int slot = npen + __popc(m & ((1u << lane) - 1u));
+      if (slot < 64) {
+        S->w.col.q1[slot] = (unsigned char)p;
+        S->w.col.qcode[slot] = (unsigned char)code;
+        S->w.col.qsep[slot] = sep;
+      }
+    }
+    npen = min(npen + __popc(m), 64);
+  }
+  t.sync();
+  // stage 2b: contact points, whole tile per penetrating pair
+  for (int k = 0; k < npen; k++) {
+    const int p = S->w.col.q1[k];
+    const DevPair& P = T.pair[p];
+    Obb A, B;
+    load_obb(S, T.geom[P.g1], P.g1, A);
+    load_obb(S, T.geom[P.g2], P.g2, B);
+    const int nc = box_contacts(t, S, A, B, (int)S->w.col.qcode[k], S->w.col.qsep[k], P.mode == MODE_BOX_SINGLE, p);
+    t.sync();
+    if (lane == 0) S->ncon = min(S->ncon + nc, NC + 1);   // NC + 1 marks overflow
+    t.sync();
+  }
+  PROF_MARK(7);
+  // stage 3: pairs that involve a general hull (so100_gjk.cuh)
+  hull_stage(t, S, T, nhull);
+}
+
+}  // namespace so100

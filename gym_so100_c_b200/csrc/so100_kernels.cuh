@@ -2,7 +2,7 @@
 // state pack/unpack.  Env e is handled by tile (e % EPB) of block (e / EPB).
 #pragma once
 #include "so100_solve.cuh"
-#include "so100_gjk.cuh"
+#include "so100_collide.cuh"
 
 namespace so100 {
 
@@ -45,7 +45,7 @@ template <unsigned LPE> __device__ void substep(const Tile<LPE>& t, EnvS* S, con
   const float qas = smooth_acc(t, S);
   PROF_MARK(1);
   PHASE_SYNC();
-  collide(t, S, T);
+  collide_env(t, S, T);
   PROF_MARK(2);
   PHASE_SYNC();
   make_contact_rows(t, S, T);
@@ -157,7 +157,7 @@ template <unsigned LPE> __global__ void __launch_bounds__(SO100_BLOCK, SO100_MIN
   for (int s = 0; s < c_m.nsub; s++) substep(t, S, T);
   // trailing mj_step1: positions + contacts of the new state
   kinematics(t, S);
-  collide(t, S, T);
+  collide_env(t, S, T);
   // ---- task layer
   uint32_t* diag = reinterpret_cast<uint32_t*>(&S->st[S_DIAG]);
   const int ncon_raw = S->ncon, ncon = min(ncon_raw, NC);
@@ -278,7 +278,7 @@ forward_kernel(const float* state, int n, float* qacc, int32_t* ncon_out, int32_
   t.sync();
   smooth_forces(t, S);
   const float qas = smooth_acc(t, S);
-  collide(t, S, T);
+  collide_env(t, S, T);
   make_contact_rows(t, S, T);
   solve(t, S, T, qas, nullptr);
   t.sync();

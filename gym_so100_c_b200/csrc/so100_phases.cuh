@@ -114,7 +114,7 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide(flo
   float* w = work + (size_t)env * WORK_WORDS;
   copy_words(t, &S->lpos[0][0], w + W_FRAMES, W_FRAMES_N);
   t.sync();
-  collide(t, S, T);
+  collide_env(t, S, T);
   store_contacts(t, S, w);
 }
 

@@ -1,15 +1,18 @@
 // Constraint rows + primal Newton solver with elliptic cones + semi-implicit Euler
-// (SURVEY.md Appendix A steps 7-9), one tile per env.  Row ownership:
-//   lane d < 12      dof d: its frictionloss row and (d < 6) its joint-limit row, kept in registers
-//   lane c (strided) contact c: impedance, cone state, per-iteration jar / jv in registers
-//   lane e (strided) packed Hessian entry e of the 12x12 lower triangle
-// The dense contact Jacobian J (<= 4 rows x 12 per contact) lives in shared memory.
+// (SURVEY.md Appendix A steps 7-9), one tile per env.  Work ownership inside the tile:
+//   lane d < 12       dof d: its frictionloss row and (d < 6) its joint-limit row, in registers
+//   lane r (strided)  contact row r = 4 c + k: the fp64 dot J_r . qacc; the quad leader (k = 0)
+//                     gathers the 4 rows of contact c and owns its cone state / jar / jv
+//   lane e (strided)  packed Hessian entry e
+// The Hessian is block diagonal (arm 6x6 | cube 6x6) unless a contact joins an arm link and the
+// cube; the common uncoupled case factors both blocks redundantly in registers (no barriers), the
+// coupled case falls back to a tile-parallel 12x12 Cholesky in shared memory.
 #pragma once
 #include "so100_step.cuh"
 
 namespace so100 {
 
-constexpr int S_DIAG = 49;   // per-env diagnostic counters inside the state record (uint32 words 49..56)
+constexpr int S_DIAG = 49;         // per-env diagnostic counters inside the state record (uint32 words 49..56)
 constexpr int NEWTON_MAXIT = 50;   // MuJoCo: 100; warm-started solves need 1-3
 constexpr int LS_MAXIT = 10;
 
@@ -33,11 +36,18 @@ __device__ __forceinline__ void make_frame(V3 n, V3& t1, V3& t2) {
   t2 = cross(n, t1);
 }
 
+// packed lower-triangle index -> (i, j), e < 78
 __device__ __forceinline__ void untri(int e, int& i, int& j) {
-  i = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-  if (tri(i + 1, 0) <= e) i++;
-  if (tri(i, 0) > e) i--;
+  i = (e >= 1) + (e >= 3) + (e >= 6) + (e >= 10) + (e >= 15) + (e >= 21) + (e >= 28) + (e >= 36) + (e >= 45) + (e >= 55) + (e >= 66);
   j = e - tri(i, 0);
+}
+
+template <unsigned LPE> __device__ __forceinline__ void tsum2(const Tile<LPE>& t, float& a, float& b) {
+#pragma unroll
+  for (int off = LPE / 2; off > 0; off >>= 1) {
+    a += t.shfl_xor(a, off);
+    b += t.shfl_xor(b, off);
+  }
 }
 
 // ------------------------------------------------------------------ contact rows
@@ -45,8 +55,13 @@ template <unsigned LPE> __device__ void make_contact_rows(const Tile<LPE>& t, En
   const int lane = t.thread_rank();
   const int ncon = min(S->ncon, NC);
   const float rs_imp = rsqrtf(fmaxf(c_m.impratio, 1e-15f));
+  int both = 0;
   for (int c = lane; c < ncon; c += LPE) {
     const DevPair& P = T.pair[S->cpair[c]];
+    const int l1 = T.geom[P.g1].link, l2 = T.geom[P.g2].link;
+    const int kind = (((l1 >= 0 && l1 < NL) || (l2 >= 0 && l2 < NL)) ? 1 : 0) | ((l1 == NL || l2 == NL) ? 2 : 0);
+    S->ckind[c] = (unsigned char)kind;
+    both |= (kind == 3);
     float dist = S->cdist[c];
     float imp = impedance(P.solimp, dist);
     float R0 = fmaxf((1.0f - imp) / imp * P.dtran, 1e-15f);
@@ -59,6 +74,7 @@ template <unsigned LPE> __device__ void make_contact_rows(const Tile<LPE>& t, En
     S->caref[c][0] = -P.K * imp * dist;
     S->caref[c][1] = S->caref[c][2] = S->caref[c][3] = 0.0f;
   }
+  S->nq1 = t.any(both) ? 1 : 0;                // arm and cube blocks of the Hessian are coupled
   for (int it = lane; it < ncon * NV; it += LPE) {
     const int c = it / NV, d = it - c * NV;
     const DevPair& P = T.pair[S->cpair[c]];
@@ -96,7 +112,7 @@ template <unsigned LPE> __device__ void make_contact_rows(const Tile<LPE>& t, En
     const int c = it >> 2, k = it & 3;
     const DevPair& P = T.pair[S->cpair[c]];
     float v = 0;
-#pragma unroll
+#pragma unroll 4
     for (int d = 0; d < NV; d++) v = fmaf(S->w.J[it][d], S->st[S_QVEL + d], v);
     S->caref[c][k] -= P.B * v;
   }
@@ -165,12 +181,12 @@ __device__ __forceinline__ float cone_eval(const float* x, const float* D, float
 }
 
 // first / second directional derivative of the cone cost along x + alpha v
-__device__ __forceinline__ void cone_ls(const double* x0, const float* v, float alpha, const float* D, float mu,
+__device__ __forceinline__ void cone_ls(const float* x0, const float* v, float alpha, const float* D, float mu,
                                         float f0, float f1, int dim, float& d1, float& d2) {
   const float fr[3] = {f0, f0, f1};
   float x[4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) x[j] = (float)fma((double)alpha, (double)v[j], x0[j]);
+  for (int j = 0; j < 4; j++) x[j] = fmaf(alpha, v[j], x0[j]);
   float N = x[0] * mu, Np = v[0] * mu, TT = 0, UV = 0, VV = 0;
 #pragma unroll
   for (int j = 1; j < 4; j++) {
@@ -195,20 +211,55 @@ __device__ __forceinline__ void cone_ls(const double* x0, const float* v, float 
   d2 += Dm * (dp * dp - NmT * mu * Tpp);
 }
 
+// x = -A^-1 b for a packed 6x6 SPD block (registers only, every lane of the half-tile redundantly)
+__device__ __forceinline__ void chol6_solve_neg(const float* A21, const float* b6, float* x) {
+  float L[21];
+#pragma unroll
+  for (int e = 0; e < 21; e++) L[e] = A21[e];
+#pragma unroll
+  for (int i = 0; i < NL; i++) x[i] = -b6[i];
+#pragma unroll
+  for (int j = 0; j < NL; j++) {
+    float d = L[tri(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; k++) d = fmaf(-L[tri(j, k)], L[tri(j, k)], d);
+    d = rsqrtf(fmaxf(d, 1e-20f));
+    L[tri(j, j)] = d;   // 1 / L_jj
+#pragma unroll
+    for (int i = j + 1; i < NL; i++) {
+      float s = L[tri(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) s = fmaf(-L[tri(i, k)], L[tri(j, k)], s);
+      L[tri(i, j)] = s * d;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    float s = x[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s = fmaf(-L[tri(i, k)], x[k], s);
+    x[i] = s * L[tri(i, i)];
+  }
+#pragma unroll
+  for (int i = NL - 1; i >= 0; i--) {
+    float s = x[i];
+#pragma unroll
+    for (int k = i + 1; k < NL; k++) s = fmaf(-L[tri(k, i)], x[k], s);
+    x[i] = s * L[tri(i, i)];
+  }
+}
+
 // ------------------------------------------------------------------ Newton solver
 template <unsigned LPE> struct SolveRegs {
-  static constexpr int CPL = (NC + LPE - 1) / LPE;   // contacts per lane
-  // dof rows
+  static constexpr int RPL = (NC * 4 + LPE - 1) / LPE;   // contact rows (and, on quad leaders, contacts) per lane
   float qfs, fr_aref, fr_R, fr_D, fr_fl;
   float lim_sgn, lim_D, lim_aref;
-  // contact rows
-  double jar[CPL][4];    // J a - aref cancels to ~1e-4 of its terms under stiff contacts: kept in fp64
-  float jv[CPL][4];
-  int dim[CPL];
-  float f0[CPL], f1[CPL];
+  float jar[RPL][4], jv[RPL][4];
+  int dim[RPL];
+  float f0[RPL], f1[RPL];
 };
 
-// cost at S->a (and forces / cone Hessians when HESS); returns the tile-wide total.
+// cost at S->ad (and forces / cone Hessians when HESS); returns the tile-wide total.
 // Per-lane outputs: Ma (dof lanes), dof_force (friction + limit force on dof d).
 template <unsigned LPE, bool HESS>
 __device__ float eval_cost(const Tile<LPE>& t, EnvS* S, SolveRegs<LPE>& r, int ncon, float& Ma, float& dof_force) {
@@ -230,20 +281,30 @@ __device__ float eval_cost(const Tile<LPE>& t, EnvS* S, SolveRegs<LPE>& r, int n
     }
     if (HESS) S->hdiag[lane] = hd;
   }
+  const int nrow = ncon * 4;
 #pragma unroll
-  for (int s = 0; s < SolveRegs<LPE>::CPL; s++) {
-    const int c = lane + s * LPE;
-    if (c < ncon) {
-      float x[4];
+  for (int s = 0; s < SolveRegs<LPE>::RPL; s++) {
+    if (s * (int)LPE >= nrow) break;
+    const int row = lane + s * LPE, c = row >> 2;
+    float xv = 0;
+    if (row < nrow) {
+      // jar = J a - aref cancels to ~1e-4 of its terms under stiff contacts: accumulate in fp64
+      const int kind = S->ckind[c];
+      const int d0 = (kind & 1) ? 0 : NL, d1 = (kind & 2) ? NV : NL;
+      double v = -(double)S->caref[c][row & 3];
+#pragma unroll 2
+      for (int d = d0; d < d1; d++) v = fma((double)S->w.J[row][d], S->ad[d], v);
+      xv = (float)v;
+    }
+    const int qb = lane & ~3;
+    float x[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        double v = -(double)S->caref[c][k];
-#pragma unroll
-        for (int d = 0; d < NV; d++) v = fma((double)S->w.J[c * 4 + k][d], S->ad[d], v);
-        x[k] = (float)v; r.jar[s][k] = v;
-      }
+    for (int k = 0; k < 4; k++) x[k] = t.shfl(xv, qb + k);
+    if ((lane & 3) == 0 && row < nrow) {
       float force[4], Hc[10];
       int zone;
+#pragma unroll
+      for (int k = 0; k < 4; k++) r.jar[s][k] = x[k];
       cost += cone_eval<HESS>(x, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], force, zone, Hc);
       if (HESS) {
 #pragma unroll
@@ -259,9 +320,32 @@ __device__ float eval_cost(const Tile<LPE>& t, EnvS* S, SolveRegs<LPE>& r, int n
   return tsum(t, cost);
 }
 
+// contribution of contact c to Hessian entry (i, j)
+__device__ __forceinline__ float hess_contact(const EnvS* S, int c, int zone, int i, int j) {
+  const float* Hc = S->cH[c];
+  float h = 0;
+  if (zone == 1) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) h = fmaf(Hc[tri(k, k)] * S->w.J[c * 4 + k][i], S->w.J[c * 4 + k][j], h);
+  } else {
+    float ji[4], jj[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { ji[k] = S->w.J[c * 4 + k][i]; jj[k] = S->w.J[c * 4 + k][j]; }
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      float tb = 0;
+#pragma unroll
+      for (int a2 = 0; a2 < 4; a2++) tb = fmaf(ji[a2], Hc[a2 >= b ? tri(a2, b) : tri(b, a2)], tb);
+      h = fmaf(tb, jj[b], h);
+    }
+  }
+  return h;
+}
+
 template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const DevTables& T, float qas_d, uint32_t* diag) {
   const int lane = t.thread_rank();
   const int ncon = min(S->ncon, NC);
+  const bool coupled = S->nq1 != 0;
   SolveRegs<LPE> r;
   // ---- dof rows
   r.qfs = 0; r.fr_aref = 0; r.fr_R = 1; r.fr_D = 0; r.fr_fl = 0; r.lim_sgn = 0; r.lim_D = 0; r.lim_aref = 0;
@@ -284,39 +368,44 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
     }
   }
 #pragma unroll
-  for (int s = 0; s < SolveRegs<LPE>::CPL; s++) {
-    const int c = lane + s * LPE;
+  for (int s = 0; s < SolveRegs<LPE>::RPL; s++) {
+    const int c = (lane + s * LPE) >> 2;
     r.dim[s] = 3; r.f0[s] = 1; r.f1[s] = 1;
-    if (c < ncon) {
+    if ((lane & 3) == 0 && c < ncon) {
       const DevPair& P = T.pair[S->cpair[c]];
       r.dim[s] = P.dim; r.f0[s] = P.f0; r.f1[s] = P.f1;
     }
   }
-  // ---- warm start: previous qacc unless the unconstrained acceleration is cheaper
+  // ---- start point: previous qacc (warm start) unless the unconstrained acceleration is cheaper
   float Ma, dof_force;
-  if (lane < NV) { S->a[lane] = S->st[S_WARM + lane]; S->ad[lane] = (double)S->st[S_WARM + lane]; }
-  t.sync();
-  const float cw = eval_cost<LPE, false>(t, S, r, ncon, Ma, dof_force);
-  t.sync();
   if (lane < NV) { S->a[lane] = qas_d; S->ad[lane] = (double)qas_d; }
   t.sync();
   const float cs = eval_cost<LPE, false>(t, S, r, ncon, Ma, dof_force);
   t.sync();
-  if (cw < cs) {
-    if (lane < NV) { S->a[lane] = S->st[S_WARM + lane]; S->ad[lane] = (double)S->st[S_WARM + lane]; }
+  if (lane < NV) { S->a[lane] = S->st[S_WARM + lane]; S->ad[lane] = (double)S->st[S_WARM + lane]; }
+  t.sync();
+  float cost = eval_cost<LPE, true>(t, S, r, ncon, Ma, dof_force);
+  t.sync();
+  if (cs < cost) {
+    if (lane < NV) { S->a[lane] = qas_d; S->ad[lane] = (double)qas_d; }
+    t.sync();
+    cost = eval_cost<LPE, true>(t, S, r, ncon, Ma, dof_force);
     t.sync();
   }
   int it = 0;
   bool converged = false, small_step = false;
   for (; it < NEWTON_MAXIT; it++) {
-    const float cost = eval_cost<LPE, true>(t, S, r, ncon, Ma, dof_force);
-    t.sync();
+    if (it > 0) {
+      cost = eval_cost<LPE, true>(t, S, r, ncon, Ma, dof_force);
+      t.sync();
+    }
     // ---- gradient: M a - qfrc_smooth - J^T f
     float g = 0, jtf = 0;
     if (lane < NV) {
       jtf = dof_force;
+      const int bit = lane < NL ? 1 : 2;
       for (int c = 0; c < ncon; c++) {
-        if (S->czone[c] == 0) continue;
+        if (S->czone[c] == 0 || !(S->ckind[c] & bit)) continue;
 #pragma unroll
         for (int k = 0; k < 4; k++) jtf = fmaf(S->w.J[c * 4 + k][lane], S->cfrc[c][k], jtf);
       }
@@ -325,90 +414,110 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
     }
     // float32 stopping rule: MuJoCo's 1e-8 is below the round-off of the cancelling terms, so the
     // tolerance is 2e-6 relative to their magnitude (|qfrc_smooth| + |J^T f|), scaled like MuJoCo's.
-    const float gnorm = sqrtf(tsum(t, g * g));
-    const float gscale = sqrtf(tsum(t, r.qfs * r.qfs + jtf * jtf));
-    if (gnorm * c_m.inv_scale < 2e-6f * (1.0f + gscale)) { converged = true; break; }
-    // ---- Hessian (packed lower triangle)
-    for (int e = lane; e < 78; e += LPE) {
-      int i, j;
-      untri(e, i, j);
-      float h = 0;
-      if (i < NL) h = S->Marm[e];
-      else if (i == j) h = (i < 9 ? c_m.cube_mass : c_m.cube_I[i - 9]);
-      if (i == j) h += S->hdiag[i];
-      for (int c = 0; c < ncon; c++) {
-        const int zone = S->czone[c];
-        if (zone == 0) continue;
-        const float* Hc = S->cH[c];
-        if (zone == 1) {
-#pragma unroll
-          for (int k = 0; k < 4; k++) h = fmaf(Hc[tri(k, k)] * S->w.J[c * 4 + k][i], S->w.J[c * 4 + k][j], h);
-        } else {
-          float ji[4], jj[4];
-#pragma unroll
-          for (int k = 0; k < 4; k++) { ji[k] = S->w.J[c * 4 + k][i]; jj[k] = S->w.J[c * 4 + k][j]; }
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            float tb = 0;
-#pragma unroll
-            for (int a2 = 0; a2 < 4; a2++) tb = fmaf(ji[a2], Hc[a2 >= b ? tri(a2, b) : tri(b, a2)], tb);
-            h = fmaf(tb, jj[b], h);
-          }
+    float gg = g * g, ss = r.qfs * r.qfs + jtf * jtf;
+    tsum2(t, gg, ss);
+    if (sqrtf(gg) * c_m.inv_scale < 2e-6f * (1.0f + sqrtf(ss))) { converged = true; break; }
+    float pd;
+    if (!coupled) {
+      // ---- block-diagonal Hessian: entries 0..20 arm block, 21..41 cube block
+      for (int e = lane; e < 42; e += LPE) {
+        const int blk = e >= 21 ? 1 : 0, rr = e - 21 * blk;
+        int i, j;
+        untri(rr, i, j);
+        float h;
+        if (blk == 0) h = S->Marm[rr];
+        else h = (i == j) ? (i < 3 ? c_m.cube_mass : c_m.cube_I[i - 3]) : 0.0f;
+        const int gi = i + NL * blk, gj = j + NL * blk;
+        if (i == j) h += S->hdiag[gi];
+        for (int c = 0; c < ncon; c++) {
+          const int zone = S->czone[c];
+          if (zone == 0 || !(S->ckind[c] & (1 << blk))) continue;
+          h += hess_contact(S, c, zone, gi, gj);
         }
-      }
-      S->u.sol.H[e] = h;
-    }
-    t.sync();
-    // ---- Cholesky in place; diagonal stores 1/L_kk
-    for (int k = 0; k < NV; k++) {
-      const float dk = rsqrtf(fmaxf(S->u.sol.H[tri(k, k)], 1e-20f));
-      t.sync();
-      for (int i = k + lane; i < NV; i += LPE) {
-        if (i == k) S->u.sol.H[tri(k, k)] = dk;
-        else S->u.sol.H[tri(i, k)] *= dk;
+        S->u.sol.H[e] = h;
       }
       t.sync();
+      // both blocks factored + solved in registers; lower half-tile: arm, upper half-tile: cube
+      const int hb = lane >= (int)(LPE / 2) ? 1 : 0;
+      float x[NL];
+      chol6_solve_neg(&S->u.sol.H[21 * hb], &S->vec[NL * hb], x);
+      t.sync();
+      if (lane == 0 || lane == (int)(LPE / 2)) {
+#pragma unroll
+        for (int k = 0; k < NL; k++) S->vec[NL * hb + k] = x[k];
+      }
+      t.sync();
+      pd = (lane < NV) ? S->vec[lane] : 0.0f;
+    } else {
+      // ---- dense 12x12: packed lower triangle in shared memory, tile-parallel Cholesky
       for (int e = lane; e < 78; e += LPE) {
         int i, j;
         untri(e, i, j);
-        if (j > k) S->u.sol.H[e] = fmaf(-S->u.sol.H[tri(i, k)], S->u.sol.H[tri(j, k)], S->u.sol.H[e]);
+        float h = 0;
+        if (i < NL) h = S->Marm[e];
+        else if (i == j) h = (i < 9 ? c_m.cube_mass : c_m.cube_I[i - 9]);
+        if (i == j) h += S->hdiag[i];
+        for (int c = 0; c < ncon; c++) {
+          const int zone = S->czone[c];
+          if (zone == 0) continue;
+          h += hess_contact(S, c, zone, i, j);
+        }
+        S->u.sol.H[e] = h;
       }
       t.sync();
+      for (int k = 0; k < NV; k++) {
+        const float dk = rsqrtf(fmaxf(S->u.sol.H[tri(k, k)], 1e-20f));
+        t.sync();
+        for (int i = k + lane; i < NV; i += LPE) {
+          if (i == k) S->u.sol.H[tri(k, k)] = dk;      // stores 1 / L_kk
+          else S->u.sol.H[tri(i, k)] *= dk;
+        }
+        t.sync();
+        for (int e = lane; e < 78; e += LPE) {
+          int i, j;
+          untri(e, i, j);
+          if (j > k) S->u.sol.H[e] = fmaf(-S->u.sol.H[tri(i, k)], S->u.sol.H[tri(j, k)], S->u.sol.H[e]);
+        }
+        t.sync();
+      }
+      float x = -g;
+      for (int k = 0; k < NV; k++) {
+        float xk = t.shfl(x, k) * S->u.sol.H[tri(k, k)];
+        if (lane == k) x = xk;
+        else if (lane > k && lane < NV) x = fmaf(-S->u.sol.H[tri(lane, k)], xk, x);
+      }
+      for (int k = NV - 1; k >= 0; k--) {
+        float xk = t.shfl(x, k) * S->u.sol.H[tri(k, k)];
+        if (lane == k) x = xk;
+        else if (lane < k) x = fmaf(-S->u.sol.H[tri(k, lane)], xk, x);
+      }
+      pd = (lane < NV) ? x : 0.0f;
+      if (lane < NV) S->vec[lane] = pd;
+      t.sync();
     }
-    // ---- p = -H^-1 g  (column-oriented substitutions, lane d holds component d)
-    float x = -g;
-    for (int k = 0; k < NV; k++) {
-      float xk = t.shfl(x, k) * S->u.sol.H[tri(k, k)];
-      if (lane == k) x = xk;
-      else if (lane > k && lane < NV) x = fmaf(-S->u.sol.H[tri(lane, k)], xk, x);
-    }
-    for (int k = NV - 1; k >= 0; k--) {
-      float xk = t.shfl(x, k) * S->u.sol.H[tri(k, k)];
-      if (lane == k) x = xk;
-      else if (lane < k) x = fmaf(-S->u.sol.H[tri(k, lane)], xk, x);
-    }
-    const float pd = (lane < NV) ? x : 0.0f;
-    if (lane < NV) S->vec[lane] = pd;
-    t.sync();
     // ---- line-search set-up
     float Mp = 0;
     if (lane < NV) Mp = mul_M(S, S->vec, lane);
-    const float pMp = tsum(t, pd * Mp);
-    const float pg = tsum(t, pd * (Ma - r.qfs));
+    float pMp = pd * Mp, pg = pd * (Ma - r.qfs);
+    tsum2(t, pMp, pg);
+    const int nrow = ncon * 4;
 #pragma unroll
-    for (int s = 0; s < SolveRegs<LPE>::CPL; s++) {
-      const int c = lane + s * LPE;
-      if (c < ncon) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          float v = 0;
-#pragma unroll
-          for (int d = 0; d < NV; d++) v = fmaf(S->w.J[c * 4 + k][d], S->vec[d], v);
-          r.jv[s][k] = v;
-        }
+    for (int s = 0; s < SolveRegs<LPE>::RPL; s++) {
+      if (s * (int)LPE >= nrow) break;
+      const int row = lane + s * LPE, c = row >> 2;
+      float v = 0;
+      if (row < nrow) {
+        const int kind = S->ckind[c];
+        const int d0 = (kind & 1) ? 0 : NL, d1 = (kind & 2) ? NV : NL;
+#pragma unroll 2
+        for (int d = d0; d < d1; d++) v = fmaf(S->w.J[row][d], S->vec[d], v);
       }
+      const int qb = lane & ~3;
+#pragma unroll
+      for (int k = 0; k < 4; k++) r.jv[s][k] = t.shfl(v, qb + k);
     }
-    const float xf0 = S->a[lane < NV ? lane : 0] - r.fr_aref, xl0 = r.lim_sgn * S->a[lane < NV ? lane : 0] - r.lim_aref;
+    const float a0 = S->a[lane < NV ? lane : 0];
+    const float xf0 = a0 - r.fr_aref, xl0 = r.lim_sgn * a0 - r.lim_aref;
     auto ls_eval = [&](float alpha, float& D1, float& D2) {
       float d1 = 0, d2 = 0;
       if (lane < NV) {
@@ -421,13 +530,16 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
           if (xl < 0) { d1 = fmaf(r.lim_D * xl, v, d1); d2 = fmaf(r.lim_D * v, v, d2); }
         }
       }
+      if ((lane & 3) == 0) {
 #pragma unroll
-      for (int s = 0; s < SolveRegs<LPE>::CPL; s++) {
-        const int c = lane + s * LPE;
-        if (c < ncon) cone_ls(r.jar[s], r.jv[s], alpha, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], d1, d2);
+        for (int s = 0; s < SolveRegs<LPE>::RPL; s++) {
+          const int c = (lane + s * LPE) >> 2;
+          if (c < ncon) cone_ls(r.jar[s], r.jv[s], alpha, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], d1, d2);
+        }
       }
-      D1 = tsum(t, d1) + pg + alpha * pMp;
-      D2 = tsum(t, d2) + pMp;
+      tsum2(t, d1, d2);
+      D1 = d1 + pg + alpha * pMp;
+      D2 = d2 + pMp;
     };
     // ---- exact line search: safeguarded 1-D Newton on phi'
     float alpha = 0, d1, d2, lo = 0, hi = -1;
@@ -451,8 +563,8 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
     // "improvement < tolerance" test, made relative because the arithmetic is float32)
     if (0.5f * alpha * d10 < 1e-9f * (1.0f + fabsf(cost))) { small_step = true; it++; break; }
   }
-  if (converged == false) {
-    // forces at the last iterate (loop ran out): refresh so cfrc matches S->a
+  if (!converged) {
+    // forces at the last iterate (small step / iteration cap): refresh so cfrc matches S->a
     eval_cost<LPE, true>(t, S, r, ncon, Ma, dof_force);
     t.sync();
   }

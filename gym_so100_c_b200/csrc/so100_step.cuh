@@ -54,13 +54,14 @@ struct __align__(16) EnvS {
   float cH[NC][10];
   unsigned char cpair[NC];
   unsigned char czone[NC];
+  unsigned char ckind[NC];   // bit 0: contact touches an arm link, bit 1: touches the cube
   union {
     struct { float com[NL][3], Iw[NL][6], U[21][3], Y[21][3], FN[NL][6]; } dyn;
     struct { float H[80]; } sol;
   } u;
   union {
     float J[NC * 4][JS];
-    struct { unsigned char q1[NPAIR_MAX], qbox[NPAIR_MAX], qhull[NPAIR_MAX]; float epa[900]; } col;
+    struct { unsigned char q1[NPAIR_MAX], qbox[NPAIR_MAX], qhull[NPAIR_MAX], qcode[64]; float qsep[64]; float epa[900]; } col;
   } w;
 };
 
