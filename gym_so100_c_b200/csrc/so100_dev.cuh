@@ -48,6 +48,8 @@ struct DevPair {
   float K, B;      // reference-acceleration stiffness / damping (solref, dmax folded in)
   float solimp[5]; // clamped
   float dtran, drot;  // diagApprox: body_invweight0 sums
+  float omd0, dd;     // 1 - solimp[0] and solimp[1] - solimp[0], formed in fp64 on the host: with the cube's
+                      // solimp clamped to 0.9999, (1 - imp) in float32 would lose 3 digits (R = (1-imp)/imp * diag)
   int pad;
 };
 

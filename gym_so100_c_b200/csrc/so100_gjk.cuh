@@ -315,6 +315,97 @@ __device__ inline bool obb_overlap(const Obb& A, const Obb& B) {
 
 static_assert(sizeof(EpaScratch) <= sizeof(float) * 900, "EPA scratch does not fit its shared-memory slot");
 
+// vertices of a shape within `tol` of its support plane in world direction d: count, centroid (world), radius and
+// the world vector from the centroid to the farthest member (the edge direction when count == 2)
+template <unsigned LPE>
+__device__ int support_set(const Tile<LPE>& t, const Shape& s, V3 d, float tol, const float4* __restrict__ vert, V3& centroid,
+                           float& radius, V3& far) {
+  const V3 dl = mulmtv(s.mat, d);
+  const int n = s.boxlike ? 8 : s.vnum;
+  auto vertex = [&](int i) {
+    if (s.boxlike) return mk((i & 1) ? s.h[0] : -s.h[0], (i & 2) ? s.h[1] : -s.h[1], (i & 4) ? s.h[2] : -s.h[2]);
+    const float4 p = __ldg(&vert[s.vadr + i]);
+    return mk(p.x, p.y, p.z);
+  };
+  float best = -3.0e38f;
+  for (int i = t.thread_rank(); i < n; i += LPE) best = fmaxf(best, dot(vertex(i), dl));
+#pragma unroll
+  for (int off = LPE / 2; off > 0; off >>= 1) best = fmaxf(best, t.shfl_xor(best, off));
+  float sx = 0, sy = 0, sz = 0, cnt = 0;
+  for (int i = t.thread_rank(); i < n; i += LPE) {
+    const V3 v = vertex(i);
+    if (dot(v, dl) >= best - tol) { sx += v.x; sy += v.y; sz += v.z; cnt += 1.0f; }
+  }
+#pragma unroll
+  for (int off = LPE / 2; off > 0; off >>= 1) {
+    sx += t.shfl_xor(sx, off); sy += t.shfl_xor(sy, off); sz += t.shfl_xor(sz, off); cnt += t.shfl_xor(cnt, off);
+  }
+  const float ic = 1.0f / cnt;
+  const V3 c = mk(sx * ic, sy * ic, sz * ic);
+  float r2 = -1.0f;
+  int bi = 0x7fffffff;
+  V3 fl = mk(0, 0, 0);
+  for (int i = t.thread_rank(); i < n; i += LPE) {
+    const V3 v = vertex(i);
+    if (dot(v, dl) >= best - tol) {
+      const V3 e = v - c;
+      const float q = dot(e, e);
+      if (q > r2) { r2 = q; bi = i; fl = e; }
+    }
+  }
+#pragma unroll
+  for (int off = LPE / 2; off > 0; off >>= 1) {
+    const float oq = t.shfl_xor(r2, off);
+    const int oi = t.shfl_xor(bi, off);
+    const V3 of = mk(t.shfl_xor(fl.x, off), t.shfl_xor(fl.y, off), t.shfl_xor(fl.z, off));
+    if (oq > r2 || (oq == r2 && oi < bi)) { r2 = oq; bi = oi; fl = of; }
+  }
+  radius = sqrtf(fmaxf(r2, 0.0f));
+  centroid = s.base + mulmv(s.mat, c);
+  far = mulmv(s.mat, fl);
+  return (int)(cnt + 0.5f);
+}
+
+// A normal within 1e-3 rad of a face normal of a box-like geom in the pair is snapped onto it and the
+// penetration is re-measured along the snapped direction (same rule as the oracle).
+template <unsigned LPE>
+__device__ void snap_normal(const Tile<LPE>& t, const Shape& A, const Shape& B, V3& n, float& depth, const float4* vert) {
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const Shape& X = s == 0 ? A : B;
+    if (!X.boxlike) continue;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const V3 ax = mcol(X.mat, k);
+      const float c = dot(n, ax);
+      if (fabsf(c) > 1.0f - 5e-7f) {
+        n = c > 0 ? ax : -ax;
+        const V3 pa = support(t, A, n, vert), pb = support(t, B, -n, vert);
+        depth = dot(n, pa) - dot(n, pb);
+        return;
+      }
+    }
+  }
+}
+
+// Contact point of a GJK/EPA hit: the EPA witness midpoint when it is unique (vertex-face, edge-edge),
+// otherwise the centroid of the smaller deepest feature moved half the depth towards the other geom
+// (same rule as the oracle: flat resting contacts stay torque-free and precision-independent).
+template <unsigned LPE>
+__device__ V3 deepest_feature_point(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 n, float depth, V3 pos,
+                                    const float4* vert) {
+  V3 cA, cB, fA, fB;
+  float rA, rB;
+  const int nA = support_set(t, A, n, 1e-6f, vert, cA, rA, fA);
+  const int nB = support_set(t, B, -n, 1e-6f, vert, cB, rB, fB);
+  if (nA == 2 && nB == 2) {
+    const V3 x = cross(fA, fB);
+    if (dot(x, x) > 1e-6f * dot(fA, fA) * dot(fB, fB)) return pos;   // crossing edges: the EPA witness is unique
+  }
+  if (nA == 1 || (nB != 1 && rA <= rB)) return cA - n * (0.5f * depth);
+  return cB + n * (0.5f * depth);
+}
+
 // hull pairs that survived the sphere tests: oriented-box cull (one lane per pair), then GJK/EPA
 // with the whole tile per pair, in pair order (deterministic contact order)
 template <unsigned LPE> __device__ void hull_stage(const Tile<LPE>& t, EnvS* S, const DevTables& T, int nhull) {
@@ -347,6 +438,8 @@ template <unsigned LPE> __device__ void hull_stage(const Tile<LPE>& t, EnvS* S, 
     V3 n, pos;
     float depth;
     if (gjk_epa(t, A, B, ld3(S->gcen[P.g1]), ld3(S->gcen[P.g2]), T.vert, E, n, depth, pos)) {
+      snap_normal(t, A, B, n, depth, T.vert);
+      pos = deepest_feature_point(t, A, B, n, depth, pos, T.vert);
       if (lane == 0) {
         const int c = S->ncon;
         if (c < NC) { st3(S->cpos[c], pos); st3(S->cnrm[c], n); S->cdist[c] = -depth; S->cpair[c] = (unsigned char)p; }

@@ -119,7 +119,10 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide(flo
 }
 
 // K3: contact rows, Newton solve, semi-implicit Euler
-template <unsigned LPE> __global__ void __launch_bounds__(128) phase_solve(float* state, const float* work, int n, DevTables T) {
+#ifndef SO100_MINB_K3
+#define SO100_MINB_K3 4
+#endif
+template <unsigned LPE> __global__ void __launch_bounds__(128, SO100_MINB_K3) phase_solve(float* state, const float* work, int n, DevTables T) {
   SO100_PHASE_PROLOGUE(LPE);
   float* rec = state + (size_t)env * STATE_WORDS;
   const float* w = work + (size_t)env * WORK_WORDS;

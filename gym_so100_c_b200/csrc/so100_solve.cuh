@@ -15,6 +15,12 @@ namespace so100 {
 constexpr int S_DIAG = 49;         // per-env diagnostic counters inside the state record (uint32 words 49..56)
 constexpr int NEWTON_MAXIT = 50;   // MuJoCo: 100; warm-started solves need 1-3
 constexpr int LS_MAXIT = 10;
+#ifndef SO100_GTOL
+#define SO100_GTOL 2e-6f     // gradient tolerance relative to |qfrc_smooth| + |J^T f|
+#endif
+#ifndef SO100_ITOL
+#define SO100_ITOL 1e-9f     // predicted-improvement tolerance relative to the cost
+#endif
 
 __device__ __forceinline__ float impedance(const float* si, float dist) {
   if (si[0] == si[1] || si[2] <= 1e-15f) return 0.5f * (si[0] + si[1]);
@@ -26,6 +32,20 @@ __device__ __forceinline__ float impedance(const float* si, float dist) {
   else if (x <= mid) y = __powf(x, p) / __powf(mid, p - 1.0f);
   else y = 1.0f - __powf(1.0f - x, p) / __powf(1.0f - mid, p - 1.0f);
   return si[0] + y * (si[1] - si[0]);
+}
+
+// interpolation weight y of the impedance sigmoid: imp = solimp[0] + y (solimp[1] - solimp[0])
+__device__ __forceinline__ float impedance_y(const float* si, float dist) {
+  if (si[0] == si[1]) return 0.0f;
+  if (si[2] <= 1e-15f) return 0.5f;
+  float x = fabsf(dist) / si[2];
+  if (x >= 1.0f) return 1.0f;
+  if (x <= 0.0f) return 0.0f;
+  const float p = si[4], mid = si[3];
+  if (p == 1.0f) return x;
+  if (p == 2.0f) return x <= mid ? x * x / mid : 1.0f - (1.0f - x) * (1.0f - x) / (1.0f - mid);   // MuJoCo default power
+  if (x <= mid) return powf(x, p) / powf(mid, p - 1.0f);
+  return 1.0f - powf(1.0f - x, p) / powf(1.0f - mid, p - 1.0f);
 }
 
 // mju_makeFrame: tangents of a unit normal
@@ -63,8 +83,10 @@ template <unsigned LPE> __device__ void make_contact_rows(const Tile<LPE>& t, En
     S->ckind[c] = (unsigned char)kind;
     both |= (kind == 3);
     float dist = S->cdist[c];
-    float imp = impedance(P.solimp, dist);
-    float R0 = fmaxf((1.0f - imp) / imp * P.dtran, 1e-15f);
+    // imp = d0 + y (d1 - d0); 1 - imp is formed from the host's fp64 (1 - d0), not as 1.0f - imp
+    const float y = impedance_y(P.solimp, dist);
+    const float imp = fmaf(y, P.dd, P.solimp[0]), omi = fmaf(-y, P.dd, P.omd0);
+    float R0 = fmaxf(omi / imp * P.dtran, 1e-15f);
     float R1 = R0 / fmaxf(c_m.impratio, 1e-15f);
     S->cD[c][0] = 1.0f / R0;
     S->cD[c][1] = 1.0f / R1;
@@ -416,7 +438,7 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
     // tolerance is 2e-6 relative to their magnitude (|qfrc_smooth| + |J^T f|), scaled like MuJoCo's.
     float gg = g * g, ss = r.qfs * r.qfs + jtf * jtf;
     tsum2(t, gg, ss);
-    if (sqrtf(gg) * c_m.inv_scale < 2e-6f * (1.0f + sqrtf(ss))) { converged = true; break; }
+    if (sqrtf(gg) * c_m.inv_scale < SO100_GTOL * (1.0f + sqrtf(ss))) { converged = true; break; }
     float pd;
     if (!coupled) {
       // ---- block-diagonal Hessian: entries 0..20 arm block, 21..41 cube block
@@ -561,7 +583,7 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
     t.sync();
     // predicted decrease 1/2 alpha |phi'(0)| below float32 resolution of the cost: stop (MuJoCo's
     // "improvement < tolerance" test, made relative because the arithmetic is float32)
-    if (0.5f * alpha * d10 < 1e-9f * (1.0f + fabsf(cost))) { small_step = true; it++; break; }
+    if (0.5f * alpha * d10 < SO100_ITOL * (1.0f + fabsf(cost))) { small_step = true; it++; break; }
   }
   if (!converged) {
     // forces at the last iterate (small step / iteration cap): refresh so cfrc matches S->a

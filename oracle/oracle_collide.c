@@ -428,6 +428,74 @@ static void add_contact(const so100_model* m, oenv* e, int pair, const double* p
   memset(c->force, 0, sizeof(c->force));
 }
 
+/* Vertices of a shape within `tol` of its support plane in direction d: count, centroid (world), radius
+   and the world vector from the centroid to the farthest member (the edge direction when count == 2). */
+static int support_set(const shape* s, const double* d, double tol, double* centroid, double* radius, double* far) {
+  double dl[3], best = -1e300, acc[3] = {0, 0, 0}, fl[3] = {0, 0, 0};
+  int n = s->type == SO100_GEOM_BOX ? 8 : s->nvert, cnt = 0;
+  mulmtv(dl, s->mat, d);
+  for (int pass = 0; pass < 3; pass++) {
+    double r2 = -1;
+    for (int i = 0; i < n; i++) {
+      double v[3];
+      if (s->type == SO100_GEOM_BOX) { v[0] = (i & 1 ? 1 : -1) * s->size[0]; v[1] = (i & 2 ? 1 : -1) * s->size[1]; v[2] = (i & 4 ? 1 : -1) * s->size[2]; }
+      else copy3(v, s->vert[i]);
+      double val = dot3(v, dl);
+      if (pass == 0) { if (val > best) best = val; continue; }
+      if (val < best - tol) continue;
+      if (pass == 1) { add3(acc, acc, v); cnt++; }
+      else { double t[3]; sub3(t, v, acc); double q = dot3(t, t); if (q > r2) { r2 = q; copy3(fl, t); } }
+    }
+    if (pass == 1) scl3(acc, acc, 1.0 / cnt);
+    if (pass == 2) *radius = sqrt(r2 > 0 ? r2 : 0);
+  }
+  mulmv(centroid, s->mat, acc);
+  add3(centroid, centroid, s->pos);
+  mulmv(far, s->mat, fl);
+  return cnt;
+}
+
+/* Contact point of a GJK/EPA hit.  The EPA witness midpoint is unique for vertex-face and for crossing
+   edge-edge configurations but arbitrary when faces, a face and an edge, or two edges are parallel; there
+   the point is defined as the centroid of the deepest feature (vertices within 1e-6 m of the support plane
+   along the normal) of the geom whose deepest feature is smaller, moved half the depth towards the other
+   geom.  This keeps flat resting contacts torque-free and makes the point independent of the
+   floating-point path. */
+static void deepest_feature_point(const shape* A, const shape* B, const double* n, double depth, double* pos) {
+  double cA[3], cB[3], rA, rB, fA[3], fB[3], nn[3] = {-n[0], -n[1], -n[2]};
+  int nA = support_set(A, n, 1e-6, cA, &rA, fA), nB = support_set(B, nn, 1e-6, cB, &rB, fB);
+  if (nA == 2 && nB == 2) {
+    double x[3];
+    cross3(x, fA, fB);
+    if (dot3(x, x) > 1e-6 * dot3(fA, fA) * dot3(fB, fB)) return;    /* crossing edges: EPA witness is unique */
+  }
+  if (nA == 1 || (nB != 1 && rA <= rB)) addscl3(pos, cA, n, -0.5 * depth);
+  else addscl3(pos, cB, n, 0.5 * depth);
+}
+
+/* A contact normal within 1e-3 rad of a face normal of a cuboid geom in the pair IS that face normal (the
+   cuboid's face carries the contact); EPA only resolves it to ~sqrt(tolerance / size).  Snap it and take the
+   penetration along the snapped direction, so that the deepest-feature selection below sees exact heights. */
+static void snap_normal(const shape* A, int cubA, const shape* B, int cubB, double* n, double* depth) {
+  for (int s = 0; s < 2; s++) {
+    const shape* X = s == 0 ? A : B;
+    if (!(s == 0 ? cubA : cubB)) continue;
+    for (int k = 0; k < 3; k++) {
+      double ax[3] = {X->mat[k], X->mat[3 + k], X->mat[6 + k]};
+      double c = dot3(n, ax);
+      if (fabs(c) > 1.0 - 5e-7) {
+        double pa[3], pb[3], nn[3];
+        scl3(n, ax, c > 0 ? 1.0 : -1.0);
+        scl3(nn, n, -1.0);
+        support(A, n, pa);
+        support(B, nn, pb);
+        *depth = dot3(n, pa) - dot3(n, pb);
+        return;
+      }
+    }
+  }
+}
+
 /* box geom, or mesh whose hull vertices are exactly the 8 corners of its bounding box */
 static int is_cuboid(const so100_model* m, int g) {
   if (m->geom_type[g] == SO100_GEOM_BOX) return 1;
@@ -492,6 +560,8 @@ void o_collide(const so100_model* m, oenv* e) {
       make_shape(m, e, g2, &B);
       if (gjk_epa(&A, &B, e->gcen[g1], e->gcen[g2], normal, &depth, pa, pb)) {
         for (int k = 0; k < 3; k++) pos[k] = 0.5 * (pa[k] + pb[k]);
+        snap_normal(&A, is_cuboid(m, g1), &B, is_cuboid(m, g2), normal, &depth);
+        deepest_feature_point(&A, &B, normal, depth, pos);
         add_contact(m, e, p, pos, normal, -depth);
       }
     }
