@@ -30,6 +30,12 @@ ALG_BYTES_PER_ENV_STEP = 432          # 188 B read + 244 B written
 FLOP_PER_ENV_STEP = 1.0e6             # SURVEY.md Appendix C convention F_contact (fp32 FLOPs, FMA = 2)
 FP32_PEAK_NOMINAL_TFLOPS = 74.4       # 148 SM x 128 lanes x 2 x 1.965 GHz
 METRIC = "env-steps/sec (bin-a-cube)"
+# Algorithmic bytes one env moves per launch of each phase kernel (4-byte words):
+#   kin_dyn  reads qpos13+qvel12+ctrl6, writes frames102 + Marm/qfs33 + qas12
+#   collide  reads frames102, writes ncon + 8 words per contact (1 contact typical)
+#   solve    reads state44 + frames102 + dyn45 + contacts9, writes state44 + counters8
+#   task     reads state64 + frames102 + contacts9, writes state64 + obs15 + final_obs15 + goals6 + reward + flags
+PHASE_ALG_BYTES = {"kin_dyn": (31 + 147) * 4, "collide": (102 + 9) * 4, "solve": (200 + 52) * 4, "task": (175 + 103) * 4}
 
 
 def measured_peaks():
@@ -170,6 +176,12 @@ def run_gpu(args):
     kernel_ms = float(np.mean(ms))
     diag = parallel.all_reduce_stats(sim.diagnostics(), device=dev)
 
+    # ---- per-kernel device time (CUDA events on the launching stream, inside the library) for the roofline
+    sim.phase_timing(True)
+    for s in range(min(K, 10)):
+        sim.step(acts[W + s], autoreset=True)
+    phase_ms, phase_cnt = sim.phase_timing(False, read=True)
+
     # ---- end to end through the host-buffer C-ABI call (pinned host actions -> device -> host results)
     Ke = max(3, min(K, 50))
     h_act = torch.empty((hi - lo, 6), dtype=torch.float32).pin_memory()
@@ -191,13 +203,16 @@ def run_gpu(args):
         hbm_peak, peak_src = measured_peaks()
         n_total = n * world
         value = n_total * K / (total_ms * 1e-3)
-        achieved = ALG_BYTES_PER_ENV_STEP * nl / (kernel_ms * 1e-3) / 1e9
+        # dominant kernel of the step = the phase with the largest share of device time
+        dom = max(phase_ms, key=lambda k: phase_ms[k])
+        dom_ms = phase_ms[dom] / max(phase_cnt[dom], 1)
+        achieved = PHASE_ALG_BYTES[dom] * nl / (dom_ms * 1e-3) / 1e9
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "phase_traffic.json")) as f:
                 tj = json.load(f)
             if int(tj.get("envs", -1)) == nl:
-                traffic = tj.get("dram_bytes_per_launch")
+                traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             pass
         fp32_tflops = FLOP_PER_ENV_STEP * nl / (kernel_ms * 1e-3) / 1e12
@@ -214,7 +229,11 @@ def run_gpu(args):
                        "envs_per_gpu": n, "envs_total": n_total, "substeps_per_step": 10, "l2": "flushed between timed steps "
                        "(256 MiB write, untimed)", "parallelism": f"env-shard x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": f"phase_{dom}",
+                         "kernel_ms_per_launch": dom_ms, "algorithmic_bytes_per_env_per_launch": PHASE_ALG_BYTES[dom],
+                         "step_algorithmic_bytes_per_env": ALG_BYTES_PER_ENV_STEP,
+                         "phase_share_of_step": {k: phase_ms[k] / max(sum(phase_ms.values()), 1e-9) for k in phase_ms},
+                         "phase_ms_per_launch": {k: phase_ms[k] / max(phase_cnt[k], 1) for k in phase_ms},
                          "note": "HBM is not the binding roof for this path (SURVEY 8d): the step is FP32-issue bound",
                          "fp32_convention": {"flop_per_env_step": FLOP_PER_ENV_STEP, "achieved_tflops": fp32_tflops,
                                              "peak_tflops_nominal": FP32_PEAK_NOMINAL_TFLOPS,
@@ -223,7 +242,7 @@ def run_gpu(args):
                              "sample": f"{cpu_n} envs x {cpu_steps} steps of the same workload, fp64 C restatement (oracle/), OpenMP over envs"},
             "e2e": {"value": n_total * Ke / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "steps": Ke},
-            "gpu_launches": K,
+            "gpu_launches": K * 33,      # per step: 10 x (kin_dyn, collide, solve) + kin_dyn + collide + task
             "clocks": clocks,
             "physics_substeps_per_s": value * 10,
             "wall_s_timed_region": t_wall,

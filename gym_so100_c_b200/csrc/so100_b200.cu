@@ -44,6 +44,8 @@ struct so100_ctx {
   unsigned long long* diag = nullptr;
   float* work = nullptr;      // [N, WORK_WORDS] phase-pipeline workspace (L2-resident)
   bool fused = false;         // SO100_FUSED=1: single fused step kernel (kept for A/B measurements)
+  bool timing = false;        // so100_phase_timing: CUDA-event pairs around every phase-kernel launch
+  std::vector<std::pair<cudaEvent_t, int>> events;   // (event, kernel class) begin markers, class -1 = end marker
   // staging for the host-buffer entry point
   float *h_action = nullptr, *h_obs = nullptr, *h_ag = nullptr, *h_dg = nullptr, *h_rew = nullptr, *h_fin = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_succ = nullptr;
@@ -409,14 +411,30 @@ int so100_step(so100_handle h, const float* action, int autoreset, float* obs, f
     // phase pipeline (so100_phases.cuh): 3 small kernels per substep + trailing forward + task layer
     const DevTables T = h->tables();
     const int n = h->n;
+    // optional per-kernel CUDA-event timing (so100_phase_timing): an event pair around each launch
+    auto mark = [&](int cls, bool begin) {
+      if (!h->timing) return;
+      cudaEvent_t ev;
+      cudaEventCreate(&ev);
+      cudaEventRecord(ev, st);
+      h->events.push_back({ev, begin ? cls : -1});
+    };
     for (int s = 0; s < h->nsub; s++) {
+      mark(0, true);
       phase_kin_dyn<LPE_K1><<<phase_grid(n, LPE_K1), BLOCK, phase_smem(LPE_K1), st>>>(h->state, h->work, s == 0 ? action : nullptr, n, 1);
+      mark(0, false); mark(1, true);
       phase_collide<LPE_K2><<<phase_grid(n, LPE_K2), BLOCK, phase_smem(LPE_K2), st>>>(h->work, n, T);
+      mark(1, false); mark(2, true);
       phase_solve<LPE_K3><<<phase_grid(n, LPE_K3), BLOCK, phase_smem(LPE_K3), st>>>(h->state, h->work, n, T);
+      mark(2, false);
     }
+    mark(0, true);
     phase_kin_dyn<LPE_K1><<<phase_grid(n, LPE_K1), BLOCK, phase_smem(LPE_K1), st>>>(h->state, h->work, h->nsub == 0 ? action : nullptr, n, 0);
+    mark(0, false); mark(1, true);
     phase_collide<LPE_K2><<<phase_grid(n, LPE_K2), BLOCK, phase_smem(LPE_K2), st>>>(h->work, n, T);
+    mark(1, false); mark(3, true);
     phase_task<LPE_K4><<<phase_grid(n, LPE_K4), BLOCK, phase_smem(LPE_K4), st>>>(A, h->work, T);
+    mark(3, false);
   }
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
@@ -498,6 +516,25 @@ int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom,
   forward_kernel<LPE><<<grid_for(h->n), BLOCK, smem_bytes(), (cudaStream_t)stream>>>(h->state, h->n, qacc, ncon, con_geom, con_data,
                                                                                      sites, h->tables());
   CUDA_OK(cudaGetLastError());
+  return SO100_OK;
+}
+
+int so100_phase_timing(so100_handle h, int enable, float* ms4, int32_t* launches4, void* stream) {
+  if (!h) return fail(SO100_ERR_ARG, "so100_phase_timing: null handle");
+  if (ms4 || launches4) {
+    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    float ms[4] = {0, 0, 0, 0};
+    int cnt[4] = {0, 0, 0, 0};
+    for (size_t i = 0; i + 1 < h->events.size(); i += 2) {
+      const int cls = h->events[i].second;
+      float e = 0;
+      if (cls >= 0 && cls < 4 && cudaEventElapsedTime(&e, h->events[i].first, h->events[i + 1].first) == cudaSuccess) { ms[cls] += e; cnt[cls]++; }
+    }
+    for (int k = 0; k < 4; k++) { if (ms4) ms4[k] = ms[k]; if (launches4) launches4[k] = cnt[k]; }
+  }
+  for (auto& e : h->events) cudaEventDestroy(e.first);
+  h->events.clear();
+  h->timing = enable != 0;
   return SO100_OK;
 }
 

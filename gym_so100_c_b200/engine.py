@@ -165,6 +165,16 @@ class BatchedSim:
                   "so100_forward")
         return dict(qacc=qacc, ncon=ncon, con_geom=geom, con_data=data, sites=sites)
 
+    def phase_timing(self, enable: bool, read: bool = False):
+        """Toggle per-kernel CUDA-event timing of `step`; with read=True returns ({class: ms}, {class: launches})
+        accumulated since the previous call (synchronises the stream)."""
+        ms = np.zeros(4, dtype=np.float32)
+        cnt = np.zeros(4, dtype=np.int32)
+        ext.check(self.lib.so100_phase_timing(self.h, int(enable), ms.ctypes.data_as(C.c_void_p) if read else None,
+                                              cnt.ctypes.data_as(C.c_void_p) if read else None, self._stream()), "so100_phase_timing")
+        names = ["kin_dyn", "collide", "solve", "task"]
+        return dict(zip(names, ms.tolist())), dict(zip(names, cnt.tolist()))
+
     def diagnostics(self) -> Dict[str, int]:
         out = np.zeros(ext.NDIAG, dtype=np.int64)
         ext.check(self.lib.so100_diagnostics(self.h, out.ctypes.data_as(C.c_void_p), self._stream()), "so100_diagnostics")

@@ -108,6 +108,12 @@ int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom,
  * [6] total solver runs, [7] total contacts seen. */
 int so100_diagnostics(so100_handle h, int64_t* out8, void* stream);
 
+/* Measurement aid (bench.py roofline): when enabled, every kernel launched by so100_step is bracketed by a CUDA
+ * event pair on `stream`.  A call first reports (if ms4 / launches4 are non-NULL; synchronises the stream) the
+ * accumulated device time and launch count per kernel class since the previous call -- [0] kinematics+dynamics,
+ * [1] collision, [2] constraint solve + integration, [3] task layer -- then clears the record and sets the mode. */
+int so100_phase_timing(so100_handle h, int enable, float* ms4, int32_t* launches4, void* stream);
+
 const char* so100_last_error(void);
 
 #ifdef __cplusplus
