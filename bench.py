@@ -31,11 +31,15 @@ FLOP_PER_ENV_STEP = 1.0e6             # SURVEY.md Appendix C convention F_contac
 FP32_PEAK_NOMINAL_TFLOPS = 74.4       # 148 SM x 128 lanes x 2 x 1.965 GHz
 METRIC = "env-steps/sec (bin-a-cube)"
 # Algorithmic bytes one env moves per launch of each phase kernel (4-byte words):
-#   kin_dyn  reads qpos13+qvel12+ctrl6, writes frames102 + Marm/qfs33 + qas12
-#   collide  reads frames102, writes ncon + 8 words per contact (1 contact typical)
-#   solve    reads state44 + frames102 + dyn45 + contacts9, writes state44 + counters8
-#   task     reads state64 + frames102 + contacts9, writes state64 + obs15 + final_obs15 + goals6 + reward + flags
-PHASE_ALG_BYTES = {"kin_dyn": (31 + 147) * 4, "collide": (102 + 9) * 4, "solve": (200 + 52) * 4, "task": (175 + 103) * 4}
+#   kin_dyn       reads qpos13+qvel12+ctrl6, writes frames102 + Marm/qfs/qas45
+#   collide_box   reads frames102, writes header4 + 8 words per contact (1 contact typical)
+#   collide_hull  (queued envs only, ~14 %) reads frames102 + header8, writes 8 words per contact + header
+#   solve_light   reads state43 + frames102 + dyn45 + header1 + contacts8, writes state43 + counters4
+#   solve_heavy   (queued envs only, < 1 %) the same with up to 24 contacts
+#   task          reads state64 + frames102 + contacts9, writes state64 + obs15 + final_obs15 + goals6 + reward + flags
+PHASE_ALG_BYTES = {"kin_dyn": (31 + 147) * 4, "collide_box": (102 + 12) * 4, "collide_hull": (110 + 9) * 4,
+                   "solve_light": (199 + 47) * 4, "solve_heavy": (199 + 47) * 4, "task": (175 + 103) * 4}
+LAUNCHES_PER_STEP = 10 * 5 + 3 + 1    # 10 x (kin_dyn, collide_box, collide_hull, solve_light, solve_heavy) + 3 + task
 
 
 def measured_peaks():
@@ -165,7 +169,7 @@ def run_gpu(args):
     for s in range(K):
         flush.fill_(float(s))                       # evict L2 between timed iterations (not timed)
         ev[s][0].record()
-        sim.step(acts[W + s], autoreset=True)       # ONE kernel launch of this repo
+        sim.step(acts[W + s], autoreset=True)       # one C-ABI call = LAUNCHES_PER_STEP kernel launches
         ev[s][1].record()
     torch.cuda.synchronize()
     parallel.barrier()
@@ -242,7 +246,7 @@ def run_gpu(args):
                              "sample": f"{cpu_n} envs x {cpu_steps} steps of the same workload, fp64 C restatement (oracle/), OpenMP over envs"},
             "e2e": {"value": n_total * Ke / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "steps": Ke},
-            "gpu_launches": K * 33,      # per step: 10 x (kin_dyn, collide, solve) + kin_dyn + collide + task
+            "gpu_launches": K * LAUNCHES_PER_STEP,
             "clocks": clocks,
             "physics_substeps_per_s": value * 10,
             "wall_s_timed_region": t_wall,

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libso100_b200.so")
 SOURCES = ["so100_b200.cu"]
-HEADERS = ["so100_dev.cuh", "so100_step.cuh", "so100_solve.cuh", "so100_kernels.cuh", "so100_gjk.cuh"]
+HEADERS = ["so100_dev.cuh", "so100_scratch.cuh", "so100_dyn.cuh", "so100_box.cuh", "so100_gjk.cuh", "so100_solve.cuh", "so100_task.cuh", "so100_phases.cuh"]
 
 
 def _nvcc() -> str:
@@ -29,19 +29,16 @@ def needs_build() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, lanes_per_env: int | None = None, profile: bool = False,
-          out: str | None = None) -> str:
-    """`profile=True` builds the development variant with per-stage clock64 counters (libso100_b200_prof.so);
-    point SO100_LIB at it to load it instead of the product library."""
-    target = out or (os.path.join(HERE, "libso100_b200_prof.so") if profile else LIB)
-    if not force and not profile and out is None and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines: dict | None = None, out: str | None = None) -> str:
+    """`defines` / `out` build tuning variants (e.g. {"SO100_LPE_K3L": 32}) next to the product library;
+    point SO100_LIB at one to load it instead."""
+    target = out or LIB
+    if not force and out is None and not defines and not needs_build():
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-o", target]
-    if profile:
-        cmd.append("-DSO100_PROFILE")
-    if lanes_per_env:
-        cmd.append(f"-DSO100_LPE={int(lanes_per_env)}")
+    for k, v in (defines or {}).items():
+        cmd.append(f"-D{k}={v}")
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]

@@ -11,19 +11,22 @@
 #include "../../include/so100_model.h"
 
 namespace so100 { constexpr int SO100_NDIAG_K = SO100_NDIAG; }
-#include "so100_kernels.cuh"
 #include "so100_phases.cuh"
 
 using namespace so100;
 
 static_assert(NC == SO100_MAX_CONTACTS, "contact capacity mismatch");
 
-#ifndef SO100_LPE
-#define SO100_LPE 32          // lanes per env (tile width)
+// lanes per env (tile width) of each phase kernel; the box collision stage needs >= 24 lanes (one per clipping candidate)
+#ifndef SO100_LPE_K1
+#define SO100_LPE_K1 16
 #endif
-constexpr unsigned LPE = SO100_LPE;
+#ifndef SO100_LPE_K3L
+#define SO100_LPE_K3L 16
+#endif
+constexpr unsigned LPE_K1 = SO100_LPE_K1, LPE_K2A = 32, LPE_K2B = 32, LPE_K3L = SO100_LPE_K3L, LPE_K3H = 32, LPE_K4 = 32;
 constexpr int BLOCK = 128;
-constexpr int EPB = BLOCK / LPE;
+enum { CLS_KIN = 0, CLS_BOX = 1, CLS_SOLVE = 2, CLS_TASK = 3, CLS_HULL = 4, CLS_HEAVY = 5, CLS_N = 6 };
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -43,13 +46,15 @@ struct so100_ctx {
   float4* vert = nullptr;
   unsigned long long* diag = nullptr;
   float* work = nullptr;      // [N, WORK_WORDS] phase-pipeline workspace (L2-resident)
-  bool fused = false;         // SO100_FUSED=1: single fused step kernel (kept for A/B measurements)
+  int* qmem = nullptr;        // queue control words + hull queue [N] + heavy queue [N]
+  int sm_count = 148;
   bool timing = false;        // so100_phase_timing: CUDA-event pairs around every phase-kernel launch
   std::vector<std::pair<cudaEvent_t, int>> events;   // (event, kernel class) begin markers, class -1 = end marker
   // staging for the host-buffer entry point
   float *h_action = nullptr, *h_obs = nullptr, *h_ag = nullptr, *h_dg = nullptr, *h_rew = nullptr, *h_fin = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_succ = nullptr;
   DevTables tables() const { return DevTables{geom, pair, vert}; }
+  Queues queues() const { return Queues{qmem, qmem + 32, qmem + 32 + n}; }
 };
 
 // ------------------------------------------------------------------ small host math (double)
@@ -285,39 +290,53 @@ static int build_dev_model(const so100_model& m, DevModel& dm, std::vector<DevGe
 }
 
 // ------------------------------------------------------------------ launches
-static size_t smem_bytes() { return (size_t)EPB * sizeof(EnvS); }
-// per-phase tile widths (lanes per env) of the phase pipeline
-#ifndef SO100_LPE_K1
-#define SO100_LPE_K1 SO100_LPE
-#endif
-#ifndef SO100_LPE_K2
-#define SO100_LPE_K2 SO100_LPE
-#endif
-#ifndef SO100_LPE_K3
-#define SO100_LPE_K3 SO100_LPE
-#endif
-#ifndef SO100_LPE_K4
-#define SO100_LPE_K4 SO100_LPE
-#endif
-constexpr unsigned LPE_K1 = SO100_LPE_K1, LPE_K2 = SO100_LPE_K2, LPE_K3 = SO100_LPE_K3, LPE_K4 = SO100_LPE_K4;
-static size_t phase_smem(unsigned lpe) { return (size_t)(BLOCK / lpe) * sizeof(EnvS); }
-static int phase_grid(int n, unsigned lpe) { const int epb = BLOCK / (int)lpe; return (n + epb - 1) / epb; }
-static int grid_for(int n) { return (n + EPB - 1) / EPB; }
+template <class ST> static size_t smem_of(unsigned lpe) { return (size_t)(BLOCK / lpe) * sizeof(ST); }
+static int grid_of(int n, unsigned lpe) { const int epb = BLOCK / (int)lpe; return (n + epb - 1) / epb; }
 
 static int configure_kernels() {
   static bool done = false;
   if (done) return SO100_OK;
-  const int bytes = (int)smem_bytes();
-  CUDA_OK(cudaFuncSetAttribute(step_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SO100_BLOCK / LPE) * sizeof(EnvS))));
-  CUDA_OK(cudaFuncSetAttribute(reset_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_OK(cudaFuncSetAttribute(substeps_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_OK(cudaFuncSetAttribute(forward_kernel<LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_OK(cudaFuncSetAttribute(phase_kin_dyn<LPE_K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase_smem(LPE_K1)));
-  CUDA_OK(cudaFuncSetAttribute(phase_collide<LPE_K2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase_smem(LPE_K2)));
-  CUDA_OK(cudaFuncSetAttribute(phase_solve<LPE_K3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase_smem(LPE_K3)));
-  CUDA_OK(cudaFuncSetAttribute(phase_task<LPE_K4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phase_smem(LPE_K4)));
+  CUDA_OK(cudaFuncSetAttribute(phase_kin_dyn<LPE_K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<KinS>(LPE_K1)));
+  CUDA_OK(cudaFuncSetAttribute(phase_collide_box<LPE_K2A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<BoxS>(LPE_K2A)));
+  CUDA_OK(cudaFuncSetAttribute(phase_collide_hull<LPE_K2B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<HullS>(LPE_K2B)));
+  CUDA_OK(cudaFuncSetAttribute(phase_solve_light<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L)));
+  CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NC>>(LPE_K3H)));
   done = true;
   return SO100_OK;
+}
+
+// optional per-kernel CUDA-event timing (so100_phase_timing): an event pair around each launch
+static void mark(so100_ctx* h, cudaStream_t st, int cls, bool begin) {
+  if (!h->timing) return;
+  cudaEvent_t ev;
+  cudaEventCreate(&ev);
+  cudaEventRecord(ev, st);
+  h->events.push_back({ev, begin ? cls : -1});
+}
+
+// K1: kinematics (+ dynamics), K2a/K2b: collision.  Leaves frames, M, qfrc_smooth and the contact list in the workspace.
+static void launch_position_stage(so100_ctx* h, cudaStream_t st, const float* action, int with_dyn) {
+  const int n = h->n;
+  const DevTables T = h->tables();
+  const Queues Q = h->queues();
+  mark(h, st, CLS_KIN, true);
+  phase_kin_dyn<LPE_K1><<<grid_of(n, LPE_K1), BLOCK, smem_of<KinS>(LPE_K1), st>>>(h->state, h->work, action, n, with_dyn, Q);
+  mark(h, st, CLS_KIN, false); mark(h, st, CLS_BOX, true);
+  phase_collide_box<LPE_K2A><<<grid_of(n, LPE_K2A), BLOCK, smem_of<BoxS>(LPE_K2A), st>>>(h->work, n, T, Q);
+  mark(h, st, CLS_BOX, false); mark(h, st, CLS_HULL, true);
+  phase_collide_hull<LPE_K2B><<<std::min(grid_of(n, LPE_K2B), h->sm_count * 8), BLOCK, smem_of<HullS>(LPE_K2B), st>>>(h->work, T, Q);
+  mark(h, st, CLS_HULL, false);
+}
+
+// K3l/K3h: constraint solve (+ Euler unless O.forward)
+static void launch_solve_stage(so100_ctx* h, cudaStream_t st, const SolveOut& O) {
+  const int n = h->n;
+  const DevTables T = h->tables();
+  mark(h, st, CLS_SOLVE, true);
+  phase_solve_light<LPE_K3L><<<grid_of(n, LPE_K3L), BLOCK, smem_of<SolS<NCL>>(LPE_K3L), st>>>(h->state, h->work, n, T, O);
+  mark(h, st, CLS_SOLVE, false); mark(h, st, CLS_HEAVY, true);
+  phase_solve_heavy<LPE_K3H><<<std::min(grid_of(n, LPE_K3H), h->sm_count * 4), BLOCK, smem_of<SolS<NC>>(LPE_K3H), st>>>(h->state, h->work, T, h->queues(), O);
+  mark(h, st, CLS_HEAVY, false);
 }
 
 extern "C" {
@@ -357,10 +376,9 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   CUDA_OK(cudaMalloc(&h->diag, SO100_NDIAG * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&h->work, (size_t)num_envs * WORK_WORDS * sizeof(float)));
   CUDA_OK(cudaMemset(h->work, 0, (size_t)num_envs * WORK_WORDS * sizeof(float)));
-  {
-    const char* f = getenv("SO100_FUSED");
-    h->fused = f && f[0] == '1';
-  }
+  CUDA_OK(cudaMalloc(&h->qmem, (32 + 2 * (size_t)num_envs) * sizeof(int)));
+  CUDA_OK(cudaMemset(h->qmem, 0, (32 + 2 * (size_t)num_envs) * sizeof(int)));
+  CUDA_OK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
   CUDA_OK(cudaMemcpy(h->geom, geoms.data(), geoms.size() * sizeof(DevGeom), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(h->pair, pairs.data(), pairs.size() * sizeof(DevPair), cudaMemcpyHostToDevice));
   if (!verts.empty()) CUDA_OK(cudaMemcpy(h->vert, verts.data(), verts.size() * sizeof(float4), cudaMemcpyHostToDevice));
@@ -375,7 +393,7 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
 int so100_destroy(so100_handle h) {
   if (!h) return SO100_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->state); cudaFree(h->geom); cudaFree(h->pair); cudaFree(h->vert); cudaFree(h->diag); cudaFree(h->work);
+  cudaFree(h->state); cudaFree(h->geom); cudaFree(h->pair); cudaFree(h->vert); cudaFree(h->diag); cudaFree(h->work); cudaFree(h->qmem);
   cudaFree(h->h_action); cudaFree(h->h_obs); cudaFree(h->h_ag); cudaFree(h->h_dg); cudaFree(h->h_rew); cudaFree(h->h_fin);
   cudaFree(h->h_term); cudaFree(h->h_trunc); cudaFree(h->h_succ);
   delete h;
@@ -388,9 +406,9 @@ int so100_reset(so100_handle h, const uint8_t* mask, const float* box_pose, floa
                 void* stream) {
   if (!h) return fail(SO100_ERR_ARG, "so100_reset: null handle");
   cudaStream_t st = (cudaStream_t)stream;
-  reset_kernel<LPE><<<grid_for(h->n), BLOCK, smem_bytes(), st>>>(h->state, mask, box_pose, obs, achieved, desired, h->n, h->task,
-                                                                (uint32_t)h->seed, (uint32_t)(h->seed >> 32), h->env_offset,
-                                                                h->tables());
+  reset_kernel<LPE_K4><<<grid_of(h->n, LPE_K4), BLOCK, smem_of<TaskS>(LPE_K4), st>>>(h->state, mask, box_pose, obs, achieved, desired, h->n,
+                                                                                      h->task, (uint32_t)h->seed, (uint32_t)(h->seed >> 32),
+                                                                                      h->env_offset);
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
@@ -404,38 +422,16 @@ int so100_step(so100_handle h, const float* action, int autoreset, float* obs, f
   A.n = h->n; A.autoreset = autoreset; A.task = h->task;
   A.seed_lo = (uint32_t)h->seed; A.seed_hi = (uint32_t)(h->seed >> 32); A.env_offset = h->env_offset;
   cudaStream_t st = (cudaStream_t)stream;
-  if (h->fused) {
-    constexpr int epb_step = SO100_BLOCK / LPE;
-    step_kernel<LPE><<<(h->n + epb_step - 1) / epb_step, SO100_BLOCK, (size_t)epb_step * sizeof(EnvS), st>>>(A, h->tables());
-  } else {
-    // phase pipeline (so100_phases.cuh): 3 small kernels per substep + trailing forward + task layer
-    const DevTables T = h->tables();
-    const int n = h->n;
-    // optional per-kernel CUDA-event timing (so100_phase_timing): an event pair around each launch
-    auto mark = [&](int cls, bool begin) {
-      if (!h->timing) return;
-      cudaEvent_t ev;
-      cudaEventCreate(&ev);
-      cudaEventRecord(ev, st);
-      h->events.push_back({ev, begin ? cls : -1});
-    };
-    for (int s = 0; s < h->nsub; s++) {
-      mark(0, true);
-      phase_kin_dyn<LPE_K1><<<phase_grid(n, LPE_K1), BLOCK, phase_smem(LPE_K1), st>>>(h->state, h->work, s == 0 ? action : nullptr, n, 1);
-      mark(0, false); mark(1, true);
-      phase_collide<LPE_K2><<<phase_grid(n, LPE_K2), BLOCK, phase_smem(LPE_K2), st>>>(h->work, n, T);
-      mark(1, false); mark(2, true);
-      phase_solve<LPE_K3><<<phase_grid(n, LPE_K3), BLOCK, phase_smem(LPE_K3), st>>>(h->state, h->work, n, T);
-      mark(2, false);
-    }
-    mark(0, true);
-    phase_kin_dyn<LPE_K1><<<phase_grid(n, LPE_K1), BLOCK, phase_smem(LPE_K1), st>>>(h->state, h->work, h->nsub == 0 ? action : nullptr, n, 0);
-    mark(0, false); mark(1, true);
-    phase_collide<LPE_K2><<<phase_grid(n, LPE_K2), BLOCK, phase_smem(LPE_K2), st>>>(h->work, n, T);
-    mark(1, false); mark(3, true);
-    phase_task<LPE_K4><<<phase_grid(n, LPE_K4), BLOCK, phase_smem(LPE_K4), st>>>(A, h->work, T);
-    mark(3, false);
+  const SolveOut O{nullptr, nullptr, 0};
+  for (int s = 0; s < h->nsub; s++) {
+    launch_position_stage(h, st, s == 0 ? action : nullptr, 1);
+    launch_solve_stage(h, st, O);
   }
+  // trailing mj_step1 (dm_control's legacy step): positions + contacts of the new state, then the task layer
+  launch_position_stage(h, st, h->nsub == 0 ? action : nullptr, 0);
+  mark(h, st, CLS_TASK, true);
+  phase_task<LPE_K4><<<grid_of(h->n, LPE_K4), BLOCK, smem_of<TaskS>(LPE_K4), st>>>(A, h->work, h->tables());
+  mark(h, st, CLS_TASK, false);
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
@@ -506,31 +502,39 @@ int so100_set_aux(so100_handle h, const float* goal, const int32_t* step_count, 
 
 int so100_substeps(so100_handle h, int nsub, void* stream) {
   if (!h || nsub < 0) return fail(SO100_ERR_ARG, "so100_substeps: bad argument");
-  substeps_kernel<LPE><<<grid_for(h->n), BLOCK, smem_bytes(), (cudaStream_t)stream>>>(h->state, h->n, nsub, h->tables());
+  cudaStream_t st = (cudaStream_t)stream;
+  const SolveOut O{nullptr, nullptr, 0};
+  for (int s = 0; s < nsub; s++) {
+    launch_position_stage(h, st, nullptr, 1);
+    launch_solve_stage(h, st, O);
+  }
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
 
 int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom, float* con_data, float* sites, void* stream) {
   if (!h) return fail(SO100_ERR_ARG, "so100_forward: null handle");
-  forward_kernel<LPE><<<grid_for(h->n), BLOCK, smem_bytes(), (cudaStream_t)stream>>>(h->state, h->n, qacc, ncon, con_geom, con_data,
-                                                                                     sites, h->tables());
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_position_stage(h, st, nullptr, 1);
+  const int threads = h->n * 32;
+  export_forward_kernel<<<(threads + 255) / 256, 256, 0, st>>>(h->work, h->n, ncon, con_geom, con_data, sites, h->tables());
+  launch_solve_stage(h, st, SolveOut{qacc, con_data, 1});
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
 
-int so100_phase_timing(so100_handle h, int enable, float* ms4, int32_t* launches4, void* stream) {
+int so100_phase_timing(so100_handle h, int enable, float* ms6, int32_t* launches6, void* stream) {
   if (!h) return fail(SO100_ERR_ARG, "so100_phase_timing: null handle");
-  if (ms4 || launches4) {
+  if (ms6 || launches6) {
     CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
-    float ms[4] = {0, 0, 0, 0};
-    int cnt[4] = {0, 0, 0, 0};
+    float ms[CLS_N] = {0};
+    int cnt[CLS_N] = {0};
     for (size_t i = 0; i + 1 < h->events.size(); i += 2) {
       const int cls = h->events[i].second;
       float e = 0;
-      if (cls >= 0 && cls < 4 && cudaEventElapsedTime(&e, h->events[i].first, h->events[i + 1].first) == cudaSuccess) { ms[cls] += e; cnt[cls]++; }
+      if (cls >= 0 && cls < CLS_N && cudaEventElapsedTime(&e, h->events[i].first, h->events[i + 1].first) == cudaSuccess) { ms[cls] += e; cnt[cls]++; }
     }
-    for (int k = 0; k < 4; k++) { if (ms4) ms4[k] = ms[k]; if (launches4) launches4[k] = cnt[k]; }
+    for (int k = 0; k < CLS_N; k++) { if (ms6) ms6[k] = ms[k]; if (launches6) launches6[k] = cnt[k]; }
   }
   for (auto& e : h->events) cudaEventDestroy(e.first);
   h->events.clear();
@@ -538,16 +542,15 @@ int so100_phase_timing(so100_handle h, int enable, float* ms4, int32_t* launches
   return SO100_OK;
 }
 
-#ifdef SO100_PROFILE
-// development builds only: read and clear the per-stage SM-cycle counters
-int so100_profile(unsigned long long* out8) {
-  CUDA_OK(cudaDeviceSynchronize());
-  CUDA_OK(cudaMemcpyFromSymbol(out8, g_prof, 8 * sizeof(unsigned long long)));
-  unsigned long long zero[8] = {0};
-  CUDA_OK(cudaMemcpyToSymbol(g_prof, zero, sizeof(zero)));
+int so100_debug_read(so100_handle h, int what, float* out, int64_t* words_per_env, void* stream) {
+  if (!h || (what != 0 && what != 1)) return fail(SO100_ERR_ARG, "so100_debug_read: bad argument");
+  const size_t words = what == 0 ? STATE_WORDS : WORK_WORDS;
+  if (words_per_env) *words_per_env = (int64_t)words;
+  if (out)
+    CUDA_OK(cudaMemcpyAsync(out, what == 0 ? h->state : h->work, (size_t)h->n * words * sizeof(float), cudaMemcpyDeviceToDevice,
+                            (cudaStream_t)stream));
   return SO100_OK;
 }
-#endif
 
 int so100_diagnostics(so100_handle h, int64_t* out8, void* stream) {
   if (!h || !out8) return fail(SO100_ERR_ARG, "so100_diagnostics: bad argument");

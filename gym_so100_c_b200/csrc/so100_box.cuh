@@ -1,18 +1,58 @@
-// Collision driver (App. A step 3): static candidate-pair list -> sphere / sphere-vs-box cull ->
+// Collision, stage A (App. A step 3): static candidate-pair list -> sphere / sphere-vs-box cull ->
 //   box-like pairs: separating-axis test with one lane per pair, then contact generation with the
 //                   whole tile per penetrating pair (24 candidate points, one per lane: incident-face
 //                   corners, incident-edge x reference-edge intersections, reference corners under the
 //                   incident face -- the vertices of the clipped incident polygon);
-//   hull pairs:     oriented-box cull, then GJK/EPA with the tile per pair (so100_gjk.cuh).
+//   hull pairs:     oriented-box cull only; survivors are listed in the workspace header and the env
+//                   is queued for the GJK/EPA kernel (so100_gjk.cuh).
 // Contacts are appended in pair order, so the contact list is deterministic.
 #pragma once
-#include "so100_gjk.cuh"
+#include "so100_scratch.cuh"
 
 namespace so100 {
 
+struct Obb { V3 c, ax[3]; float h[3]; };
+// Edge-edge axes A_i x B_j: skipped below sin^2 = 1e-6 and penalised by 2e-6 m / sin so that
+// round-off on nearly parallel edges can never beat a face axis (same rule in the oracle).
+constexpr float EDGE_MIN_SIN2 = 1e-6f;
+constexpr float EDGE_BIAS = 2e-6f;
+
+__device__ __forceinline__ V3 geom_center(const FrameBlock& f, const DevGeom& g) {
+  V3 c = ld3(g.center);
+  if (g.link >= 0) c = ld3(f.lpos[g.link]) + mulmv(f.lmat[g.link], c);
+  return c;
+}
+
+__device__ __forceinline__ void load_obb(const FrameBlock& f, const DevGeom& g, V3 center, Obb& b) {
+  b.c = center;
+  b.h[0] = g.half[0]; b.h[1] = g.half[1]; b.h[2] = g.half[2];
+  const float* m = g.link >= 0 ? f.lmat[g.link] : g.wmat;
+  b.ax[0] = mcol(m, 0); b.ax[1] = mcol(m, 1); b.ax[2] = mcol(m, 2);
+}
+
+// distance^2 from point p to an oriented box
+__device__ __forceinline__ float point_obb_d2(V3 p, const Obb& b) {
+  V3 d = p - b.c;
+  float s = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float x = dot(d, b.ax[k]);
+    float e = fmaxf(fabsf(x) - b.h[k], 0.0f);
+    s = fmaf(e, e, s);
+  }
+  return s;
+}
+
+__device__ __forceinline__ void put_contact(float* con, int c, V3 p, V3 n, float dist, int pair) {
+  float4* q = reinterpret_cast<float4*>(con + c * CON_WORDS);
+  q[0] = make_float4(p.x, p.y, p.z, n.x);
+  q[1] = make_float4(n.y, n.z, dist, __int_as_float(pair));
+}
+
 // 15-axis separating-axis test.  Returns false when separated; otherwise `code` = 0..5 (face axis of
 // A / B) or 6 + 3 i + j (edge axis A_i x B_j) and `sep` < 0 the signed separation along it.
-__device__ __forceinline__ bool box_sat(const Obb& A, const Obb& B, int& code, float& sep_out) {
+// FULL = false: overlap test only (cull), with a 1e-6 slack on |R|.
+template <bool FULL> __device__ __forceinline__ bool box_sat(const Obb& A, const Obb& B, int& code, float& sep_out) {
   float R[3][3], aR[3][3], tA[3], tB[3];
   const V3 t = B.c - A.c;
 #pragma unroll
@@ -20,7 +60,7 @@ __device__ __forceinline__ bool box_sat(const Obb& A, const Obb& B, int& code, f
     tA[i] = dot(t, A.ax[i]);
     tB[i] = dot(t, B.ax[i]);
 #pragma unroll
-    for (int j = 0; j < 3; j++) { R[i][j] = dot(A.ax[i], B.ax[j]); aR[i][j] = fabsf(R[i][j]); }
+    for (int j = 0; j < 3; j++) { R[i][j] = dot(A.ax[i], B.ax[j]); aR[i][j] = fabsf(R[i][j]) + (FULL ? 0.0f : 1e-6f); }
   }
   float best_face = -1e30f;
   code = 0;
@@ -44,12 +84,17 @@ __device__ __forceinline__ bool box_sat(const Obb& A, const Obb& B, int& code, f
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const float ra = A.h[i1] * aR[i2][j] + A.h[i2] * aR[i1][j];
+      const float rb = B.h[j1] * aR[i][j2] + B.h[j2] * aR[i][j1];
+      const float num = fabsf(tA[i2] * R[i1][j] - tA[i1] * R[i2][j]) - (ra + rb);
+      if (!FULL) {
+        if (num > 0) return false;
+        continue;
+      }
       const float l2 = 1.0f - R[i][j] * R[i][j];
       if (l2 < EDGE_MIN_SIN2) continue;      // (near-)parallel edges: the face axes cover this direction
       const float inv = rsqrtf(l2);
-      const float ra = A.h[i1] * aR[i2][j] + A.h[i2] * aR[i1][j];
-      const float rb = B.h[j1] * aR[i][j2] + B.h[j2] * aR[i][j1];
-      const float sep = (fabsf(tA[i2] * R[i1][j] - tA[i1] * R[i2][j]) - (ra + rb)) * inv;
+      const float sep = num * inv;
       if (sep > 0) return false;
       const float sel = sep - EDGE_BIAS * inv;
       if (sel > best_sel) { best_sel = sel; best_edge = sep; ecode = 6 + 3 * i + j; }
@@ -60,24 +105,16 @@ __device__ __forceinline__ bool box_sat(const Obb& A, const Obb& B, int& code, f
   return true;
 }
 
-template <unsigned LPE> __device__ __forceinline__ void tsum2x(const Tile<LPE>& t, float& a, float& b) {
-#pragma unroll
-  for (int off = LPE / 2; off > 0; off >>= 1) {
-    a += t.shfl_xor(a, off);
-    b += t.shfl_xor(b, off);
-  }
-}
-
 __device__ __forceinline__ V3 sel_axis(const Obb& b, int k) { return k == 0 ? b.ax[0] : (k == 1 ? b.ax[1] : b.ax[2]); }
 __device__ __forceinline__ float sel_h(const Obb& b, int k) { return k == 0 ? b.h[0] : (k == 1 ? b.h[1] : b.h[2]); }
 
 // Contact generation for one penetrating box pair with the whole tile.  Appends up to 8 contacts
-// (1 when `single`) at S->ncon; every lane returns the number appended.
+// (1 when `single`) to `con` at index `base`; every lane returns the number appended.
 template <unsigned LPE>
-__device__ int box_contacts(const Tile<LPE>& t, EnvS* S, const Obb& A, const Obb& B, int code, float sep, bool single, int pair) {
+__device__ int box_contacts(const Tile<LPE>& t, float* con, int base, const Obb& A, const Obb& B, int code, float sep, bool single,
+                            int pair) {
   static_assert(LPE >= 24, "box_contacts needs one lane per candidate point (24)");
   const int lane = t.thread_rank();
-  const int base = S->ncon;
   const V3 tAB = B.c - A.c;
   if (code >= 6) {
     // edge-edge: one point midway between the closest points of the two edges
@@ -95,7 +132,7 @@ __device__ int box_contacts(const Tile<LPE>& t, EnvS* S, const Obb& A, const Obb
     const float b = dot(ea, eb), d = dot(ea, r), e = dot(eb, r), den = 1.0f - b * b;
     const float s = (b * e - d) / den, u = (e - b * d) / den;
     const V3 q = ((pA + ea * s) + (pB + eb * u)) * 0.5f;
-    if (lane == 0 && base < NC) { st3(S->cpos[base], q); st3(S->cnrm[base], n); S->cdist[base] = sep; S->cpair[base] = (unsigned char)pair; }
+    if (lane == 0 && base < NC) put_contact(con, base, q, n, sep, pair);
     return 1;
   }
   // face contact: the reference box owns the axis
@@ -186,35 +223,28 @@ __device__ int box_contacts(const Tile<LPE>& t, EnvS* S, const Obb& A, const Obb
     if (dmax <= 0) return 0;
     const bool deep = valid && depth >= dmax - 1e-6f;
     float sx = deep ? p.x : 0, sy = deep ? p.y : 0, sz = deep ? p.z : 0, cnt = deep ? 1.0f : 0.0f;
-    tsum2x(t, sx, sy);
-    tsum2x(t, sz, cnt);
+    tsum2(t, sx, sy);
+    tsum2(t, sz, cnt);
     if (lane == 0 && base < NC) {
       const float ic = 1.0f / cnt;
-      st3(S->cpos[base], mk(sx * ic, sy * ic, sz * ic)); st3(S->cnrm[base], nout); S->cdist[base] = -dmax; S->cpair[base] = (unsigned char)pair;
+      put_contact(con, base, mk(sx * ic, sy * ic, sz * ic), nout, -dmax, pair);
     }
     return 1;
   }
   const unsigned m = t.ballot(valid);
   const int slot = __popc(m & ((1u << lane) - 1u));
   const int total = min(__popc(m), 8);
-  if (valid && slot < 8 && base + slot < NC) {
-    const int c = base + slot;
-    st3(S->cpos[c], p); st3(S->cnrm[c], nout); S->cdist[c] = -depth; S->cpair[c] = (unsigned char)pair;
-  }
+  if (valid && slot < 8 && base + slot < NC) put_contact(con, base + slot, p, nout, -depth, pair);
   return total;
 }
 
-template <unsigned LPE> __device__ void collide_env(const Tile<LPE>& t, EnvS* S, const DevTables& T) {
+// Stage A for one env.  Writes the contact list and the header of workspace record `w`; returns (on every lane)
+// the number of hull pairs that need GJK/EPA, with *ncon_out the contact count so far (NC + 1 = overflow).
+template <unsigned LPE> __device__ int collide_box_env(const Tile<LPE>& t, BoxS* S, float* w, const DevTables& T, int* ncon_out) {
   const int lane = t.thread_rank();
-  PROF_BEGIN();
+  float* con = w + W_CON;
   // world OBB centres
-  for (int g = lane; g < c_m.ngeom; g += LPE) {
-    const DevGeom& G = T.geom[g];
-    V3 c = ld3(G.center);
-    if (G.link >= 0) c = ld3(S->lpos[G.link]) + mulmv(S->lmat[G.link], c);
-    st3(S->gcen[g], c);
-  }
-  if (lane == 0) { S->ncon = 0; }
+  for (int g = lane; g < c_m.ngeom; g += LPE) st3(S->gcen[g], geom_center(S->f, T.geom[g]));
   t.sync();
   // stage 1: bounding sphere vs sphere, sphere vs oriented box (both ways); compact survivors by mode
   int nbox = 0, nhull = 0;
@@ -230,8 +260,8 @@ template <unsigned LPE> __device__ void collide_env(const Tile<LPE>& t, EnvS* S,
       const float rr = G1.rbound + G2.rbound;
       if (dot(d, d) <= rr * rr) {
         Obb b1, b2;
-        load_obb(S, G1, P.g1, b1);
-        load_obb(S, G2, P.g2, b2);
+        load_obb(S->f, G1, c1, b1);
+        load_obb(S->f, G2, c2, b2);
         if (point_obb_d2(c1, b2) <= G1.rbound * G1.rbound && point_obb_d2(c2, b1) <= G2.rbound * G2.rbound) {
           pass = 1; mode = P.mode;
         }
@@ -240,15 +270,13 @@ template <unsigned LPE> __device__ void collide_env(const Tile<LPE>& t, EnvS* S,
     const unsigned mb = t.ballot(pass && mode != MODE_HULL), mh = t.ballot(pass && mode == MODE_HULL);
     const unsigned lt = (1u << lane) - 1u;
     if (pass) {
-      if (mode != MODE_HULL) S->w.col.qbox[nbox + __popc(mb & lt)] = (unsigned char)p;
-      else S->w.col.qhull[nhull + __popc(mh & lt)] = (unsigned char)p;
+      if (mode != MODE_HULL) S->qbox[nbox + __popc(mb & lt)] = (unsigned char)p;
+      else S->qhull[nhull + __popc(mh & lt)] = (unsigned char)p;
     }
     nbox += __popc(mb); nhull += __popc(mh);
   }
   t.sync();
-  PROF_MARK(6);
   // stage 2a: separating-axis test, one lane per box-like pair; penetrating pairs are compacted into q1
-  // together with their axis code (kept in registers of the lane that found it and re-derived below)
   int npen = 0;
   for (int base = 0; base < nbox; base += LPE) {
     const int k = base + lane;
@@ -256,40 +284,65 @@ template <unsigned LPE> __device__ void collide_env(const Tile<LPE>& t, EnvS* S,
     int p = 0, code = 0;
     float sep = 0;
     if (k < nbox) {
-      p = S->w.col.qbox[k];
+      p = S->qbox[k];
       const DevPair& P = T.pair[p];
       Obb A, B;
-      load_obb(S, T.geom[P.g1], P.g1, A);
-      load_obb(S, T.geom[P.g2], P.g2, B);
-      hit = box_sat(A, B, code, sep);
+      load_obb(S->f, T.geom[P.g1], ld3(S->gcen[P.g1]), A);
+      load_obb(S->f, T.geom[P.g2], ld3(S->gcen[P.g2]), B);
+      hit = box_sat<true>(A, B, code, sep);
     }
     const unsigned m = t.ballot(hit);
     if (hit) {
       const int slot = npen + __popc(m & ((1u << lane) - 1u));
       if (slot < 64) {
-        S->w.col.q1[slot] = (unsigned char)p;
-        S->w.col.qcode[slot] = (unsigned char)code;
-        S->w.col.qsep[slot] = sep;
+        S->q1[slot] = (unsigned char)p;
+        S->qcode[slot] = (unsigned char)code;
+        S->qsep[slot] = sep;
       }
     }
     npen = min(npen + __popc(m), 64);
   }
   t.sync();
   // stage 2b: contact points, whole tile per penetrating pair
+  int ncon = 0;
   for (int k = 0; k < npen; k++) {
-    const int p = S->w.col.q1[k];
+    const int p = S->q1[k];
     const DevPair& P = T.pair[p];
     Obb A, B;
-    load_obb(S, T.geom[P.g1], P.g1, A);
-    load_obb(S, T.geom[P.g2], P.g2, B);
-    const int nc = box_contacts(t, S, A, B, (int)S->w.col.qcode[k], S->w.col.qsep[k], P.mode == MODE_BOX_SINGLE, p);
-    t.sync();
-    if (lane == 0) S->ncon = min(S->ncon + nc, NC + 1);   // NC + 1 marks overflow
-    t.sync();
+    load_obb(S->f, T.geom[P.g1], ld3(S->gcen[P.g1]), A);
+    load_obb(S->f, T.geom[P.g2], ld3(S->gcen[P.g2]), B);
+    const int nc = box_contacts(t, con, ncon, A, B, (int)S->qcode[k], S->qsep[k], P.mode == MODE_BOX_SINGLE, p);
+    ncon = min(ncon + nc, NC + 1);   // NC + 1 marks overflow
   }
-  PROF_MARK(7);
-  // stage 3: pairs that involve a general hull (so100_gjk.cuh)
-  hull_stage(t, S, T, nhull);
+  // stage 3: oriented-box cull of the hull pairs, one lane per pair; survivors go to the workspace header
+  int nsurv = 0;
+  for (int base = 0; base < nhull; base += LPE) {
+    const int k = base + lane;
+    bool pass = false;
+    int p = 0;
+    if (k < nhull) {
+      p = S->qhull[k];
+      const DevPair& P = T.pair[p];
+      Obb A, B;
+      load_obb(S->f, T.geom[P.g1], ld3(S->gcen[P.g1]), A);
+      load_obb(S->f, T.geom[P.g2], ld3(S->gcen[P.g2]), B);
+      int code; float sep;
+      pass = box_sat<false>(A, B, code, sep);
+    }
+    const unsigned m = t.ballot(pass);
+    if (pass) {
+      const int slot = nsurv + __popc(m & ((1u << lane) - 1u));
+      if (slot < NHP) reinterpret_cast<unsigned char*>(w + W_HULLP)[slot] = (unsigned char)p;
+    }
+    nsurv += __popc(m);
+  }
+  if (nsurv > NHP) { ncon = NC + 1; nsurv = NHP; }   // more hull pairs than the list holds: counted as a contact overflow
+  if (lane == 0) {
+    int4 hdr = make_int4(ncon, nsurv, min(nbox, 255) | (npen << 8) | (min(nhull, 255) << 16), 0);
+    *reinterpret_cast<int4*>(w + W_HDR) = hdr;
+  }
+  *ncon_out = ncon;
+  return nsurv;
 }
 
 }  // namespace so100

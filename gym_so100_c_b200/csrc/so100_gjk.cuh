@@ -1,11 +1,11 @@
-// GJK + EPA for the pairs that involve a general convex hull (arm links, jaw hulls, base),
-// one tile per env: the support map over the hull vertices is lane-parallel (float4 loads +
-// shuffle arg-max), the simplex / polytope logic is tile-uniform, the EPA polytope lives in
-// the shared-memory region that later holds the contact Jacobian.  One contact per pair
-// (MuJoCo mjc_Convex with multiccd off): normal and depth are the minimum-translation
-// solution, the point is the midpoint of the EPA witness points.
+// Collision, stage B: GJK + EPA for the pairs that involve a general convex hull (arm links, jaw
+// hulls, base), one tile per queued env: the support map over the hull vertices is lane-parallel
+// (float4 loads + shuffle arg-max), the simplex / polytope logic is tile-uniform, the EPA polytope
+// lives in shared memory.  One contact per pair (MuJoCo mjc_Convex with multiccd off): normal and
+// depth are the minimum-translation solution, the point is the midpoint of the EPA witness points
+// (or the deepest-feature centroid when the witness is not unique).
 #pragma once
-#include "so100_step.cuh"
+#include "so100_box.cuh"
 
 namespace so100 {
 
@@ -17,14 +17,13 @@ struct Shape {
   int vadr, vnum;
 };
 
-template <unsigned LPE>
-__device__ __forceinline__ void load_shape(const EnvS* S, const DevGeom& G, int gi, Shape& s) {
+__device__ __forceinline__ void load_shape(const FrameBlock& f, const DevGeom& G, V3 center, Shape& s) {
   s.boxlike = G.boxlike;
-  s.mat = G.link >= 0 ? S->lmat[G.link] : G.wmat;
+  s.mat = G.link >= 0 ? f.lmat[G.link] : G.wmat;
   s.h[0] = G.half[0]; s.h[1] = G.half[1]; s.h[2] = G.half[2];
   s.vadr = G.vadr; s.vnum = G.vnum;
-  if (G.boxlike) s.base = ld3(S->gcen[gi]);
-  else s.base = G.link >= 0 ? ld3(S->lpos[G.link]) : ld3(G.org);
+  if (G.boxlike) s.base = center;
+  else s.base = G.link >= 0 ? ld3(f.lpos[G.link]) : ld3(G.org);
 }
 
 // support point in world direction d; identical on every lane of the tile
@@ -142,7 +141,7 @@ __device__ inline float tri_closest(V3 a, V3 b, V3 c, float* lam) {
   return dot(p, p);
 }
 
-// EPA polytope in shared memory (aliases the contact-Jacobian region; see EnvS::w)
+// EPA polytope in shared memory (HullS::epa)
 constexpr int EPA_MAXV = 32;
 constexpr int EPA_MAXF = 64;
 struct EpaScratch {
@@ -283,36 +282,6 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
   return depth > 0;
 }
 
-// 15-axis oriented-box overlap test (cull only)
-__device__ inline bool obb_overlap(const Obb& A, const Obb& B) {
-  float R[3][3], aR[3][3], tA[3];
-  const V3 t = B.c - A.c;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    tA[i] = dot(t, A.ax[i]);
-#pragma unroll
-    for (int j = 0; j < 3; j++) { R[i][j] = dot(A.ax[i], B.ax[j]); aR[i][j] = fabsf(R[i][j]) + 1e-6f; }
-  }
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-    if (fabsf(tA[i]) > A.h[i] + B.h[0] * aR[i][0] + B.h[1] * aR[i][1] + B.h[2] * aR[i][2]) return false;
-#pragma unroll
-  for (int j = 0; j < 3; j++)
-    if (fabsf(tA[0] * R[0][j] + tA[1] * R[1][j] + tA[2] * R[2][j]) > B.h[j] + A.h[0] * aR[0][j] + A.h[1] * aR[1][j] + A.h[2] * aR[2][j]) return false;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-      const float ra = A.h[i1] * aR[i2][j] + A.h[i2] * aR[i1][j];
-      const float rb = B.h[j1] * aR[i][j2] + B.h[j2] * aR[i][j1];
-      if (fabsf(tA[i2] * R[i1][j] - tA[i1] * R[i2][j]) > ra + rb) return false;
-    }
-  }
-  return true;
-}
-
 static_assert(sizeof(EpaScratch) <= sizeof(float) * 900, "EPA scratch does not fit its shared-memory slot");
 
 // vertices of a shape within `tol` of its support plane in world direction d: count, centroid (world), radius and
@@ -406,48 +375,41 @@ __device__ V3 deepest_feature_point(const Tile<LPE>& t, const Shape& A, const Sh
   return cB + n * (0.5f * depth);
 }
 
-// hull pairs that survived the sphere tests: oriented-box cull (one lane per pair), then GJK/EPA
-// with the whole tile per pair, in pair order (deterministic contact order)
-template <unsigned LPE> __device__ void hull_stage(const Tile<LPE>& t, EnvS* S, const DevTables& T, int nhull) {
+// Stage B for one queued env: GJK/EPA with the whole tile per listed hull pair, in pair order (deterministic
+// contact order); contacts are appended to the workspace list after the box contacts.  Returns the final count.
+template <unsigned LPE> __device__ int collide_hull_env(const Tile<LPE>& t, HullS* S, float* w, const DevTables& T) {
   const int lane = t.thread_rank();
-  int nsurv = 0;
-  for (int base = 0; base < nhull; base += LPE) {
-    const int k = base + lane;
-    bool pass = false;
-    int p = 0;
-    if (k < nhull) {
-      p = S->w.col.qhull[k];
-      const DevPair& P = T.pair[p];
-      Obb A, B;
-      load_obb(S, T.geom[P.g1], P.g1, A);
-      load_obb(S, T.geom[P.g2], P.g2, B);
-      pass = obb_overlap(A, B);
-    }
-    const unsigned m = t.ballot(pass);
-    if (pass) S->w.col.q1[nsurv + __popc(m & ((1u << lane) - 1u))] = (unsigned char)p;
-    nsurv += __popc(m);
-  }
-  t.sync();
-  EpaScratch* E = reinterpret_cast<EpaScratch*>(S->w.col.epa);
+  const int4 hdr = *reinterpret_cast<const int4*>(w + W_HDR);
+  int ncon = hdr.x;
+  const int nsurv = min(hdr.y, NHP);
+  const uint4 plist = *reinterpret_cast<const uint4*>(w + W_HULLP);
+  float* con = w + W_CON;
+  EpaScratch* E = reinterpret_cast<EpaScratch*>(S->epa);
   for (int k = 0; k < nsurv; k++) {
-    const int p = S->w.col.q1[k];
+    const unsigned word = (k >> 2) == 0 ? plist.x : ((k >> 2) == 1 ? plist.y : ((k >> 2) == 2 ? plist.z : plist.w));
+    const int p = (int)((word >> (8 * (k & 3))) & 0xffu);
     const DevPair& P = T.pair[p];
+    const DevGeom& G1 = T.geom[P.g1];
+    const DevGeom& G2 = T.geom[P.g2];
+    const V3 c1 = geom_center(S->f, G1), c2 = geom_center(S->f, G2);
     Shape A, B;
-    load_shape<LPE>(S, T.geom[P.g1], P.g1, A);
-    load_shape<LPE>(S, T.geom[P.g2], P.g2, B);
+    load_shape(S->f, G1, c1, A);
+    load_shape(S->f, G2, c2, B);
     V3 n, pos;
     float depth;
-    if (gjk_epa(t, A, B, ld3(S->gcen[P.g1]), ld3(S->gcen[P.g2]), T.vert, E, n, depth, pos)) {
+    if (gjk_epa(t, A, B, c1, c2, T.vert, E, n, depth, pos)) {
       snap_normal(t, A, B, n, depth, T.vert);
       pos = deepest_feature_point(t, A, B, n, depth, pos, T.vert);
-      if (lane == 0) {
-        const int c = S->ncon;
-        if (c < NC) { st3(S->cpos[c], pos); st3(S->cnrm[c], n); S->cdist[c] = -depth; S->cpair[c] = (unsigned char)p; }
-        S->ncon = min(c + 1, NC + 1);
-      }
+      if (lane == 0 && ncon < NC) put_contact(con, ncon, pos, n, -depth, p);
+      ncon = min(ncon + 1, NC + 1);
     }
     t.sync();
   }
+  if (lane == 0) {
+    reinterpret_cast<int*>(w + W_HDR)[0] = ncon;
+    reinterpret_cast<int*>(w + W_HDR)[3] = nsurv;      // statistics: GJK runs
+  }
+  return ncon;
 }
 
 }  // namespace so100

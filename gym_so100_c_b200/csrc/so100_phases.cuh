@@ -1,87 +1,39 @@
-// Phase-split step pipeline.
+// The step pipeline: a short sequence of small kernels per physics substep, linked by an L2-resident
+// workspace record per env (so100_scratch.cuh), with the rare heavy work classes pulled out of the
+// regular grid into queue-driven persistent kernels:
 //
-// ncu on the single fused step kernel (profiles/r01_fused_step_ncu.txt) showed the dominant stall
-// to be `no_instruction` (10.2 stalled warps per issue): one substep executes ~10 k distinct SASS
-// instructions (~160 KB), and the resident warps of an SM sit in different regions of that code, so
-// the instruction cache thrashes.  The step is therefore issued as a short sequence of small
-// kernels -- all warps of a launch run the same few KB of code -- and the per-env intermediate
-// data (link frames, mass matrix, smooth forces, contact list: <= 1.4 KB) is streamed through a
-// workspace record that stays L2-resident (16384 envs x 1.4 KB = 23 MB of the 126 MB L2):
+//   per substep:  K1  phase_kin_dyn       kinematics, mass matrix, RNE bias, actuators      state -> work
+//                 K2a phase_collide_box   broad phase, box SAT + clipping, hull-pair cull   work  -> work (+ hull queue)
+//                 K2b phase_collide_hull  GJK/EPA for queued envs (~14 % of envs)           work  -> work (+ heavy queue)
+//                 K3l phase_solve_light   contact rows, Newton, Euler; envs <= 8 contacts   state, work -> state
+//                 K3h phase_solve_heavy   the same for queued envs with 9..24 contacts
+//   per step:     K1 (kinematics only) + K2a + K2b + K4 phase_task (reward / flags / obs / auto-reset)
 //
-//   per substep:  K1 kinematics + mass matrix + RNE bias + actuators      state -> work
-//                 K2 collision (broad phase, box SAT, hull GJK/EPA)       work  -> work
-//                 K3 contact rows + Newton solve + Euler                  state, work -> state
-//   per step:     K1 (kinematics only) + K2 + K4 task layer (reward / flags / obs / auto-reset)
+// Why not one fused kernel: ncu on the fused step (profiles/r01_fused_step_ncu.txt) showed it to be instruction-fetch
+// bound (356 KB of SASS, stall_no_instruction = 10 warps per issue); small kernels keep every resident warp in the same
+// few KB of code, and per-phase scratch layouts (1.2-4 KB per env instead of 10.4 KB) lift the shared-memory limit on
+// resident warps.  Why queues: GJK/EPA and many-contact solves take 5-20x the time of the common case; run inside
+// the regular grid they pin a whole block (and its registers / shared memory) while three of its four tiles idle.
 #pragma once
-#include "so100_kernels.cuh"
+#include "so100_gjk.cuh"
+#include "so100_task.cuh"
 
 namespace so100 {
 
-// workspace record (float words)
-constexpr int W_FRAMES = 0;                 // lpos[7][3] lmat[7][9] axis[6][3]  (contiguous in EnvS)
-constexpr int W_FRAMES_N = 21 + 63 + 18;    // 102
-constexpr int W_DYN = W_FRAMES + W_FRAMES_N;  // Marm[21] qfs[12]              (contiguous in EnvS)
-constexpr int W_DYN_N = 21 + 12;
-constexpr int W_QAS = W_DYN + W_DYN_N;      // qacc_smooth[12]
-constexpr int W_NCON = W_QAS + NV;
-constexpr int W_CON = W_NCON + 1;           // contact c: pos[3] nrm[3] dist pair
-constexpr int WORK_WORDS = ((W_CON + 8 * NC + 31) / 32) * 32;
+#ifndef SO100_MINB_K3L
+#define SO100_MINB_K3L 5
+#endif
 
-static_assert(offsetof(EnvS, lmat) == offsetof(EnvS, lpos) + 21 * sizeof(float), "frames must be contiguous");
-static_assert(offsetof(EnvS, axis) == offsetof(EnvS, lpos) + 84 * sizeof(float), "frames must be contiguous");
-static_assert(offsetof(EnvS, qfs) == offsetof(EnvS, Marm) + 21 * sizeof(float), "dyn must be contiguous");
-
-template <unsigned LPE> __device__ __forceinline__ void copy_words(const Tile<LPE>& t, float* dst, const float* src, int n) {
-  for (int k = t.thread_rank(); k < n; k += LPE) dst[k] = src[k];
-}
-
-template <unsigned LPE> __device__ __forceinline__ void store_contacts(const Tile<LPE>& t, const EnvS* S, float* w) {
-  const int lane = t.thread_rank();
-  const int ncon = min(S->ncon, NC);
-  if (lane == 0) w[W_NCON] = __int_as_float(S->ncon);
-  for (int k = lane; k < ncon * 8; k += LPE) {
-    const int c = k >> 3, f = k & 7;
-    float v;
-    if (f < 3) v = S->cpos[c][f];
-    else if (f < 6) v = S->cnrm[c][f - 3];
-    else if (f == 6) v = S->cdist[c];
-    else v = __int_as_float((int)S->cpair[c]);
-    w[W_CON + k] = v;
-  }
-}
-template <unsigned LPE> __device__ __forceinline__ void load_contacts(const Tile<LPE>& t, EnvS* S, const float* w) {
-  const int lane = t.thread_rank();
-  const int nraw = __float_as_int(w[W_NCON]);
-  const int ncon = min(nraw, NC);
-  if (lane == 0) S->ncon = nraw;
-  for (int k = lane; k < ncon * 8; k += LPE) {
-    const int c = k >> 3, f = k & 7;
-    const float v = w[W_CON + k];
-    if (f < 3) S->cpos[c][f] = v;
-    else if (f < 6) S->cnrm[c][f - 3] = v;
-    else if (f == 6) S->cdist[c] = v;
-    else S->cpair[c] = (unsigned char)__float_as_int(v);
-  }
-}
-
-#define SO100_PHASE_PROLOGUE(LPE_)                                             \
-  extern __shared__ __align__(16) unsigned char smem_raw[];                    \
-  constexpr int EPB = 128 / LPE_;                                              \
-  cg::thread_block blk = cg::this_thread_block();                              \
-  Tile<LPE_> t = cg::tiled_partition<LPE_>(blk);                               \
-  const int env = blockIdx.x * EPB + t.meta_group_rank();                      \
-  if (env >= n) return;                                                        \
-  EnvS* S = reinterpret_cast<EnvS*>(smem_raw) + t.meta_group_rank();           \
-  const int lane = t.thread_rank();                                            \
-  (void)lane
-
-// K1: state -> frames (+ mass matrix, smooth forces, unconstrained acceleration)
+// K1: state -> frames (+ mass matrix, smooth forces, unconstrained acceleration); also re-arms the queues
 template <unsigned LPE>
-__global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, const float* action, int n, int with_dyn) {
-  SO100_PHASE_PROLOGUE(LPE);
+__global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, const float* action, int n, int with_dyn, Queues Q) {
+  SO100_TILE_PROLOGUE(LPE, KinS);
+  if (blockIdx.x == 0 && threadIdx.x < Q_WORDS) Q.ctl[threadIdx.x] = 0;
+  const int env = blockIdx.x * EPB + t.meta_group_rank();
+  if (env >= n) return;
   float* rec = state + (size_t)env * STATE_WORDS;
   float* w = work + (size_t)env * WORK_WORDS;
-  copy_words(t, S->st, rec, S_GOAL);       // qpos qvel ctrl warm
+  copy_vec<LPE, 32>(t, S->st, rec);       // qpos qvel ctrl (+ 1 word of warm)
   t.sync();
   if (action) {
     // before_step: unnormalize_so100 in float32 (constants.py:44-47, 78-86)
@@ -96,126 +48,229 @@ __global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, 
     }
     t.sync();
   }
-  kinematics(t, S);
+  kinematics<true>(t, S);
   if (with_dyn) {
     mass_matrix(t, S);
-    t.sync();
     smooth_forces(t, S);
-    const float qas = smooth_acc(t, S);
-    if (lane < NV) w[W_QAS + lane] = qas;
-    copy_words(t, w + W_DYN, S->Marm, W_DYN_N);
+    smooth_acc(t, S);
+    copy_vec<LPE, W_DYN_N>(t, w + W_DYN, reinterpret_cast<const float*>(&S->d));
   }
-  copy_words(t, w + W_FRAMES, &S->lpos[0][0], W_FRAMES_N);
+  copy_vec<LPE, W_FRAMES_N>(t, w + W_FRAMES, reinterpret_cast<const float*>(&S->f));
 }
 
-// K2: frames -> contact list
-template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide(float* work, int n, DevTables T) {
-  SO100_PHASE_PROLOGUE(LPE);
+// K2a: frames -> box contacts + surviving hull pairs; classifies the env
+template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_box(float* work, int n, DevTables T, Queues Q) {
+  SO100_TILE_PROLOGUE(LPE, BoxS);
+  const int env = blockIdx.x * EPB + t.meta_group_rank();
+  if (env >= n) return;
   float* w = work + (size_t)env * WORK_WORDS;
-  copy_words(t, &S->lpos[0][0], w + W_FRAMES, W_FRAMES_N);
+  copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
   t.sync();
-  collide_env(t, S, T);
-  store_contacts(t, S, w);
+  int ncon;
+  const int nsurv = collide_box_env(t, S, w, T, &ncon);
+  if (lane == 0) {
+    if (nsurv > 0) Q.hull[atomicAdd(&Q.ctl[Q_HULL_COUNT], 1)] = env;
+    else if (ncon > NCL) Q.heavy[atomicAdd(&Q.ctl[Q_HEAVY_COUNT], 1)] = env;
+  }
 }
 
-// K3: contact rows, Newton solve, semi-implicit Euler
-#ifndef SO100_MINB_K3
-#define SO100_MINB_K3 4
-#endif
-template <unsigned LPE> __global__ void __launch_bounds__(128, SO100_MINB_K3) phase_solve(float* state, const float* work, int n, DevTables T) {
-  SO100_PHASE_PROLOGUE(LPE);
-  float* rec = state + (size_t)env * STATE_WORDS;
-  const float* w = work + (size_t)env * WORK_WORDS;
-  copy_words(t, S->st, rec, STATE_WORDS);
-  copy_words(t, &S->lpos[0][0], w + W_FRAMES, W_FRAMES_N);
-  copy_words(t, S->Marm, w + W_DYN, W_DYN_N);
-  load_contacts(t, S, w);
-  const float qas = lane < NV ? w[W_QAS + lane] : 0.0f;
+// K2b: persistent tiles drain the hull queue
+template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_hull(float* work, DevTables T, Queues Q) {
+  SO100_TILE_PROLOGUE(LPE, HullS);
+  const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_HULL_COUNT]);
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&Q.ctl[Q_HULL_NEXT], 1);
+    i = t.shfl(i, 0);
+    if (i >= count) break;
+    const int env = Q.hull[i];
+    float* w = work + (size_t)env * WORK_WORDS;
+    copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
+    t.sync();
+    const int ncon = collide_hull_env(t, S, w, T);
+    if (lane == 0 && ncon > NCL) Q.heavy[atomicAdd(&Q.ctl[Q_HEAVY_COUNT], 1)] = env;
+    t.sync();
+  }
+}
+
+// forward-mode outputs of the solve kernels (so100_forward): nothing is integrated or stored
+struct SolveOut {
+  float* qacc;       // [N,12] or null
+  float* con_data;   // [N,NC,11] or null: forces go to columns 7..10
+  int forward;       // 0: integrate and store the state (the step path)
+};
+
+template <unsigned LPE, class ES>
+__device__ void solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w, int env, int ncon_raw, const DevTables& T,
+                          const SolveOut& O) {
+  const int lane = t.thread_rank();
+  copy_vec<LPE, 48>(t, S->st, rec);
+  copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
+  copy_vec<LPE, W_DYN_N>(t, reinterpret_cast<float*>(&S->d), w + W_DYN);
+  const int ncon = min(ncon_raw, ES::NCAP);
+  for (int k = lane; k < ncon * 2; k += LPE)
+    reinterpret_cast<float4*>(&S->con[0][0])[k] = reinterpret_cast<const float4*>(w + W_CON)[k];
+  if (lane == 0) S->ncon = ncon;
   t.sync();
   make_contact_rows(t, S, T);
-  solve(t, S, T, qas, reinterpret_cast<uint32_t*>(&S->st[S_DIAG]));
+  solve(t, S, T, O.forward ? nullptr : reinterpret_cast<uint32_t*>(rec + S_DIAG));
+  if (O.forward) {
+    t.sync();
+    if (O.qacc && lane < NV) O.qacc[(size_t)env * NV + lane] = S->a[lane];
+    if (O.con_data)
+      for (int k = lane; k < ncon * 4; k += LPE) O.con_data[((size_t)env * NC + (k >> 2)) * 11 + 7 + (k & 3)] = S->cfrc[k >> 2][k & 3];
+    return;
+  }
   integrate(t, S);
-  // qpos qvel (ctrl unchanged) warm + diagnostics
-  copy_words(t, rec, S->st, S_GOAL);
-  for (int k = S_DIAG + lane; k < S_DIAG + SO100_NDIAG_K; k += LPE) rec[k] = S->st[k];
+  copy_vec<LPE, 48>(t, rec, S->st);   // qpos qvel (ctrl unchanged) warm (+ goal / counters unchanged)
 }
 
-// K4: reward / success / termination / observation / same-call auto-reset on the post-step state
-// (single_arm.py:322-380, env.py:137-145, 172-182, 372-406)
-template <unsigned LPE> __global__ void __launch_bounds__(128) phase_task(StepArgs A, const float* work, DevTables T) {
-  const int n = A.n;
-  SO100_PHASE_PROLOGUE(LPE);
+// K3l: regular grid, one tile per env; envs with more than NCL contacts are left to K3h
+template <unsigned LPE>
+__global__ void __launch_bounds__(128, SO100_MINB_K3L) phase_solve_light(float* state, const float* work, int n, DevTables T, SolveOut O) {
+  SO100_TILE_PROLOGUE(LPE, SolS<NCL>);
+  const int env = blockIdx.x * EPB + t.meta_group_rank();
+  if (env >= n) return;
   const float* w = work + (size_t)env * WORK_WORDS;
-  load_state(t, S, A.state, env);
-  copy_words(t, &S->lpos[0][0], w + W_FRAMES, W_FRAMES_N);
-  load_contacts(t, S, w);
-  t.sync();
-  uint32_t* diag = reinterpret_cast<uint32_t*>(&S->st[S_DIAG]);
-  const int ncon_raw = S->ncon, ncon = min(ncon_raw, NC);
-  bool bad = false;
-  for (int k = lane; k < S_GOAL; k += LPE) bad |= !isfinite(S->st[k]);
-  bad = t.any(bad);
-  int tg = 0, tt = 0;
-  for (int c = lane; c < ncon; c += LPE) {
-    const DevPair& P = T.pair[S->cpair[c]];
-    if ((P.g2 == c_m.cg_cube && ((c_m.pad_mask >> P.g1) & 1u)) || (P.g1 == c_m.cg_cube && ((c_m.pad_mask >> P.g2) & 1u))) tg = 1;
-    if (P.g1 == c_m.cg_cube && P.g2 == c_m.cg_table) tt = 1;     // ordered pair ("red_box", "table")
+  const int ncon_raw = __float_as_int(w[W_HDR]);
+  if (ncon_raw > NCL) return;
+  solve_env(t, S, state + (size_t)env * STATE_WORDS, w, env, ncon_raw, T, O);
+}
+
+// K3h: persistent tiles drain the heavy queue
+template <unsigned LPE>
+__global__ void __launch_bounds__(128) phase_solve_heavy(float* state, const float* work, DevTables T, Queues Q, SolveOut O) {
+  SO100_TILE_PROLOGUE(LPE, SolS<NC>);
+  const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_HEAVY_COUNT]);
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&Q.ctl[Q_HEAVY_NEXT], 1);
+    i = t.shfl(i, 0);
+    if (i >= count) break;
+    const int env = Q.heavy[i];
+    const float* w = work + (size_t)env * WORK_WORDS;
+    solve_env(t, S, state + (size_t)env * STATE_WORDS, w, env, __float_as_int(w[W_HDR]), T, O);
+    t.sync();
   }
-  const bool touch_gripper = t.any(tg), touch_table = t.any(tt);
-  const SiteOut so = sites(S);
-  const int step_count = __float_as_int(S->st[S_STEP]) + 1;
-  const int total = __float_as_int(S->st[S_TOTAL]) + 1;
-  float reward;
-  bool succ, trunc;
-  if (A.task == 0) {
-    // float32 cube_pos compared against float64 bin bounds, exactly as numpy does in the reference
-    const double cx = (double)so.cube.x, cy = (double)so.cube.y;
-    const bool over_bin = (c_m.bin_min[0] < cx && cx < c_m.bin_max[0]) && (c_m.bin_min[1] < cy && cy < c_m.bin_max[1]);
-    bool inside = true;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const float lower = __fsub_rn(comp(so.cube, k), c_m.cube_half), upper = __fadd_rn(comp(so.cube, k), c_m.cube_half);
-      inside = inside && ((double)lower > c_m.bin_min[k]) && ((double)upper < c_m.bin_max[k]);
+}
+
+// K4: task layer on the post-step state
+template <unsigned LPE> __global__ void __launch_bounds__(128) phase_task(StepArgs A, const float* work, DevTables T) {
+  SO100_TILE_PROLOGUE(LPE, TaskS);
+  const int env = blockIdx.x * EPB + t.meta_group_rank();
+  if (env >= A.n) return;
+  const float* w = work + (size_t)env * WORK_WORDS;
+  float* rec = A.state + (size_t)env * STATE_WORDS;
+  copy_vec<LPE, STATE_WORDS>(t, S->st, rec);
+  copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
+  t.sync();
+  task_env(t, S, A, w, env, T);
+  t.sync();
+  copy_vec<LPE, STATE_WORDS>(t, rec, S->st);
+}
+
+template <unsigned LPE>
+__global__ void __launch_bounds__(128)
+reset_kernel(float* state, const uint8_t* mask, const float* box_pose, float* obs, float* achieved, float* desired, int n,
+             int task, uint32_t seed_lo, uint32_t seed_hi, long long env_offset) {
+  SO100_TILE_PROLOGUE(LPE, TaskS);
+  const int env = blockIdx.x * EPB + t.meta_group_rank();
+  if (env >= n) return;
+  float* rec = state + (size_t)env * STATE_WORDS;
+  copy_vec<LPE, STATE_WORDS>(t, S->st, rec);
+  t.sync();
+  if (!mask || mask[env]) reset_env(t, S, env_offset + env, box_pose ? box_pose + (size_t)env * 7 : nullptr, task, seed_lo, seed_hi);
+  kinematics<false>(t, S);
+  write_obs(t, S, env, obs, achieved, desired);
+  t.sync();
+  copy_vec<LPE, STATE_WORDS>(t, rec, S->st);
+}
+
+// so100_forward: contact list and sites of the workspace in the caller's layout (forces are filled in by the solve kernels)
+__global__ void export_forward_kernel(const float* work, int n, int32_t* ncon_out, int32_t* con_geom, float* con_data, float* sites_out,
+                                      DevTables T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int env = i / 32, c = i % 32;
+  if (env >= n) return;
+  const float* w = work + (size_t)env * WORK_WORDS;
+  const int ncon_raw = __float_as_int(w[W_HDR]), ncon = min(ncon_raw, NC);
+  if (c == 0 && ncon_out) ncon_out[env] = ncon_raw;
+  if (c < NC) {
+    const bool live = c < ncon;
+    const float* q = w + W_CON + c * CON_WORDS;
+    if (con_geom) {
+      int g1 = -1, g2 = -1;
+      if (live) { const DevPair& P = T.pair[__float_as_int(q[7])]; g1 = T.geom[P.g1].mjid; g2 = T.geom[P.g2].mjid; }
+      con_geom[((size_t)env * NC + c) * 2] = g1;
+      con_geom[((size_t)env * NC + c) * 2 + 1] = g2;
     }
-    const bool released = inside && !touch_gripper;
-    reward = 0.0f;
-    if (touch_gripper) reward = 1.0f;
-    if (touch_gripper && !touch_table) reward = 2.0f;
-    if (over_bin) reward = 2.5f;
-    if (inside) reward = 3.0f;
-    if (released) reward = 4.0f;
-    succ = reward == 4.0f;
-    trunc = step_count >= c_m.max_episode_steps;
-  } else {
-    const float dx = __fsub_rn(so.cube.x, S->st[S_GOAL]), dy = __fsub_rn(so.cube.y, S->st[S_GOAL + 1]),
-                dz = __fsub_rn(so.cube.z, S->st[S_GOAL + 2]);
-    const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-    succ = d < c_m.goal_threshold;
-    reward = succ ? 0.0f : -1.0f;
-    trunc = step_count >= c_m.goal_max_steps;
+    if (con_data) {
+      float* d = con_data + ((size_t)env * NC + c) * 11;
+      d[0] = live ? q[6] : 0.0f;
+      for (int k = 0; k < 6; k++) d[1 + k] = live ? q[k] : 0.0f;
+      for (int k = 0; k < 4; k++) d[7 + k] = 0.0f;
+    }
+  } else if (c == NC && sites_out) {
+    const FrameBlock& f = *reinterpret_cast<const FrameBlock*>(w + W_FRAMES);
+    const SiteOut so = sites(f);
+    float* o = sites_out + (size_t)env * 9;
+    o[0] = so.cube.x; o[1] = so.cube.y; o[2] = so.cube.z;
+    o[3] = c_m.bin_center[0]; o[4] = c_m.bin_center[1]; o[5] = c_m.bin_center[2];
+    o[6] = so.ee.x; o[7] = so.ee.y; o[8] = so.ee.z;
   }
-  if (bad) { succ = false; trunc = true; reward = 0.0f; }
-  const bool term = succ;
-  t.sync();
-  if (lane == 0) {
-    S->st[S_STEP] = __int_as_float(step_count);
-    S->st[S_TOTAL] = __int_as_float(total);
-    if (ncon_raw > NC) diag[0] += 1u;
-    if (bad) diag[2] += 1u;
-    if (term || trunc) diag[3] += 1u;
-    if (succ) diag[4] += 1u;
-    if (A.reward) A.reward[env] = reward;
-    if (A.terminated) A.terminated[env] = term ? 1 : 0;
-    if (A.truncated) A.truncated[env] = trunc ? 1 : 0;
-    if (A.success) A.success[env] = succ ? 1 : 0;
+}
+
+// env.py:346-349 on a batch
+__global__ void compute_reward_kernel(const float* ag, const float* dg, long long n, float thr, float* out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float dx = __fsub_rn(ag[3 * i], dg[3 * i]), dy = __fsub_rn(ag[3 * i + 1], dg[3 * i + 1]),
+              dz = __fsub_rn(ag[3 * i + 2], dg[3 * i + 2]);
+  const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  out[i] = d < thr ? 0.0f : -1.0f;
+}
+
+// record <-> user arrays.  dir = 0: record -> arrays (get), 1: arrays -> record (set)
+__global__ void state_io_kernel(float* state, int n, int dir, float* qpos, float* qvel, float* ctrl, float* warm, float* goal,
+                                int32_t* step_count, int32_t* total_steps, uint32_t* episode) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int env = i / STATE_WORDS, k = i % STATE_WORDS;
+  if (env >= n) return;
+  float* rec = state + (size_t)env * STATE_WORDS + k;
+  float* p = nullptr;
+  if (k < S_QVEL) { if (qpos) p = qpos + (size_t)env * 13 + k; }
+  else if (k < S_CTRL) { if (qvel) p = qvel + (size_t)env * 12 + (k - S_QVEL); }
+  else if (k < S_WARM) { if (ctrl) p = ctrl + (size_t)env * 6 + (k - S_CTRL); }
+  else if (k < S_GOAL) { if (warm) p = warm + (size_t)env * 12 + (k - S_WARM); }
+  else if (k < S_STEP) { if (goal) p = goal + (size_t)env * 3 + (k - S_GOAL); }
+  else if (k == S_STEP) { if (step_count) p = reinterpret_cast<float*>(step_count) + env; }
+  else if (k == S_TOTAL) { if (total_steps) p = reinterpret_cast<float*>(total_steps) + env; }
+  else if (k == S_EPISODE) { if (episode) p = reinterpret_cast<float*>(episode) + env; }
+  if (!p) return;
+  if (dir == 0) *p = *rec; else *rec = *p;
+}
+
+__global__ void init_state_kernel(float* state, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int env = i / STATE_WORDS, k = i % STATE_WORDS;
+  if (env >= n) return;
+  float v = 0.0f;
+  if (k == S_QPOS + 9) v = 1.0f;
+  state[(size_t)env * STATE_WORDS + k] = v;
+}
+
+// sums the per-env uint32 counters into out[8] (uint64)
+__global__ void diag_reduce_kernel(const float* state, int n, unsigned long long* out) {
+  __shared__ unsigned long long acc[SO100_NDIAG_K];
+  if (threadIdx.x < SO100_NDIAG_K) acc[threadIdx.x] = 0;
+  __syncthreads();
+  for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < n; env += gridDim.x * blockDim.x) {
+    const uint32_t* d = reinterpret_cast<const uint32_t*>(state + (size_t)env * STATE_WORDS + S_DIAG);
+    for (int k = 0; k < SO100_NDIAG_K; k++)
+      if (d[k]) atomicAdd(&acc[k], (unsigned long long)d[k]);
   }
-  if (A.final_obs) write_obs(t, S, env, A.final_obs, nullptr, nullptr);
-  if ((A.autoreset && (term || trunc)) || bad) {
-    reset_env(t, S, A.env_offset + env, nullptr, A.task, A.seed_lo, A.seed_hi);
-    kinematics(t, S);
-  }
-  write_obs(t, S, env, A.obs, A.achieved, A.desired);
-  store_state(t, S, A.state, env);
+  __syncthreads();
+  if (threadIdx.x < SO100_NDIAG_K) atomicAdd(&out[threadIdx.x], acc[threadIdx.x]);
 }
 
 }  // namespace so100

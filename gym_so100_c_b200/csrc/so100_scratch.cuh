@@ -1,0 +1,167 @@
+// Per-phase shared-memory layouts, the L2-resident workspace record that links the phase kernels,
+// and the work-class queues.
+//
+// Every phase kernel owns one cooperative tile of LPE lanes per env and a scratch struct that holds
+// only what that phase touches (1.7 KB for kinematics/dynamics, 1.2 KB for the box collision stage,
+// 4 KB for a hull (GJK/EPA) env, 4 KB for a solve with <= 8 contacts, 9.5 KB for the rare solve with
+// up to 24), so that shared memory never limits the number of resident warps.  The device functions
+// are templates over the scratch type and only name the members they use.
+#pragma once
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+#include "so100_dev.cuh"
+
+namespace so100 {
+namespace cg = cooperative_groups;
+
+__constant__ DevModel c_m;
+
+struct DevTables {
+  const DevGeom* geom;
+  const DevPair* pair;
+  const float4* vert;
+};
+
+template <unsigned LPE> using Tile = cg::thread_block_tile<LPE>;
+
+constexpr int NCL = 8;             // contact capacity of the light solve kernel (99.7 % of all solves)
+constexpr int NHP = 16;            // hull pairs per env that may reach GJK/EPA after the oriented-box cull
+
+// ---------------------------------------------------------------- workspace record (float words)
+// 16-byte aligned sections so that tiles move them with 128-bit loads.
+constexpr int W_FRAMES = 0;        // lpos[7][3] lmat[7][9] axis[6][3] (+2 pad)
+constexpr int W_FRAMES_N = 104;
+constexpr int W_DYN = 104;         // Marm[21] qfs[12] qas[12] (+3 pad)
+constexpr int W_DYN_N = 48;
+constexpr int W_HDR = 152;         // ncon, nhullpairs, stats (nbox | npen << 8 | nhull << 16), spare
+constexpr int W_HULLP = 156;       // NHP pair ids, one byte each
+constexpr int W_CON = 160;         // contact c: pos[3] nrm[3] dist pair
+constexpr int CON_WORDS = 8;
+constexpr int WORK_WORDS = W_CON + CON_WORDS * NC;   // 352 words = 1408 B = 44 sectors
+static_assert(WORK_WORDS % 8 == 0, "workspace records must stay 32-byte aligned");
+static_assert(NHP <= 16, "hull pair list is 4 words");
+
+// queue control words (device ints)
+enum { Q_HULL_COUNT = 0, Q_HULL_NEXT = 1, Q_HEAVY_COUNT = 2, Q_HEAVY_NEXT = 3, Q_WORDS = 4 };
+
+struct Queues {
+  int* ctl;      // [Q_WORDS]
+  int* hull;     // [N] envs with at least one hull pair for GJK/EPA this substep
+  int* heavy;    // [N] envs with more than NCL contacts this substep
+};
+
+// ---------------------------------------------------------------- scratch structs
+struct FrameBlock {                // image of W_FRAMES
+  float lpos[7][3];                // link origins: 6 arm links + cube
+  float lmat[7][9];                // link axes (row-major)
+  float axis[NL][3];               // hinge axes, world
+  float fpad[2];
+};
+static_assert(sizeof(FrameBlock) == W_FRAMES_N * 4, "frame block layout");
+
+struct DynBlock {                  // image of W_DYN
+  float Marm[21];                  // arm mass matrix, packed lower triangle
+  float qfs[NV];                   // qfrc_smooth
+  float qas[NV];                   // unconstrained acceleration M^-1 qfrc_smooth
+  float dpad[3];
+};
+static_assert(sizeof(DynBlock) == W_DYN_N * 4, "dyn block layout");
+
+// K1: kinematics + dynamics
+struct __align__(16) KinS {
+  float st[32];                    // qpos[13] qvel[12] ctrl[6]
+  FrameBlock f;
+  DynBlock d;
+  float com[NL][3], Iw[NL][6], U[21][3], Y[21][3], FN[NL][6];
+};
+
+// K2a: broad phase + box-like pairs
+struct __align__(16) BoxS {
+  FrameBlock f;
+  float gcen[NGEOM][3];            // world OBB centres of the collidable geoms
+  float gpad;
+  unsigned char qbox[NPAIR_MAX], qhull[NPAIR_MAX], q1[64], qcode[64];
+  float qsep[64];
+};
+
+// K2b: GJK / EPA for hull pairs
+struct __align__(16) HullS {
+  FrameBlock f;
+  float epa[900];
+};
+
+// K3: constraint rows + Newton solve, NCAP contacts
+template <int NCAP_> struct __align__(16) SolS {
+  static constexpr int NCAP = NCAP_;
+  double ad[NV];                   // qacc iterate in fp64 (jar cancellation, see so100_solve.cuh)
+  float st[48];                    // qpos[13] qvel[12] ctrl[6] warm[12] (image of the state record head)
+  FrameBlock f;
+  DynBlock d;
+  float a[NV];                     // qacc iterate
+  float hdiag[NV];                 // active diagonal curvature of friction / limit rows
+  float vec[NV];                   // gradient -> search direction
+  float H[80];                     // packed Hessian (block diagonal: 42 entries, dense: 78)
+  float con[NCAP_][CON_WORDS];     // image of the workspace contact list
+  float cD[NCAP_][4], caref[NCAP_][4], cmu[NCAP_];
+  float cfrc[NCAP_][4];
+  float cH[NCAP_][10];
+  unsigned char czone[NCAP_];
+  unsigned char ckind[NCAP_];      // bit 0: contact touches an arm link, bit 1: touches the cube
+  int ncon, coupled;
+  float J[NCAP_ * 4][JS];
+};
+
+// K4 / reset: task layer
+struct __align__(16) TaskS {
+  float st[STATE_WORDS];
+  FrameBlock f;
+};
+
+// ---------------------------------------------------------------- tile helpers
+template <unsigned LPE> __device__ __forceinline__ V3 shfl_up3(const Tile<LPE>& t, V3 v, int d) {
+  return mk(t.shfl_up(v.x, d), t.shfl_up(v.y, d), t.shfl_up(v.z, d));
+}
+template <unsigned LPE> __device__ __forceinline__ float tsum(const Tile<LPE>& t, float v) {
+#pragma unroll
+  for (int off = LPE / 2; off > 0; off >>= 1) v += t.shfl_xor(v, off);
+  return v;
+}
+template <unsigned LPE> __device__ __forceinline__ void tsum2(const Tile<LPE>& t, float& a, float& b) {
+#pragma unroll
+  for (int off = LPE / 2; off > 0; off >>= 1) {
+    a += t.shfl_xor(a, off);
+    b += t.shfl_xor(b, off);
+  }
+}
+
+// Copy NW words (a multiple of 4, both sides 16-byte aligned) with one 128-bit load per lane and round;
+// all loads are issued before the first store so their latencies overlap.
+template <unsigned LPE, int NW> __device__ __forceinline__ void copy_vec(const Tile<LPE>& t, float* dst, const float* src) {
+  static_assert(NW % 4 == 0, "copy_vec moves whole float4s");
+  constexpr int NV4 = NW / 4, R = (NV4 + LPE - 1) / LPE;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  float4 v[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int k = t.thread_rank() + r * LPE;
+    if (k < NV4) v[r] = s4[k];
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int k = t.thread_rank() + r * LPE;
+    if (k < NV4) d4[k] = v[r];
+  }
+}
+
+// tile and env bookkeeping shared by all phase kernels (blockDim.x = 128)
+#define SO100_TILE_PROLOGUE(LPE_, STYPE_)                                      \
+  extern __shared__ __align__(16) unsigned char smem_raw[];                    \
+  constexpr int EPB = 128 / LPE_;                                              \
+  cg::thread_block blk = cg::this_thread_block();                              \
+  Tile<LPE_> t = cg::tiled_partition<LPE_>(blk);                               \
+  STYPE_* S = reinterpret_cast<STYPE_*>(smem_raw) + t.meta_group_rank();       \
+  const int lane = t.thread_rank();                                            \
+  (void)lane; (void)EPB
+
+}  // namespace so100

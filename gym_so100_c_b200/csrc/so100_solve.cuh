@@ -7,8 +7,13 @@
 // The Hessian is block diagonal (arm 6x6 | cube 6x6) unless a contact joins an arm link and the
 // cube; the common uncoupled case factors both blocks redundantly in registers (no barriers), the
 // coupled case falls back to a tile-parallel 12x12 Cholesky in shared memory.
+//
+// The cost/force evaluation and the line-search derivative each have exactly ONE call site (the start-point
+// selection, the Newton loop and the final force refresh all run through the same loop body): the kernel is
+// instruction-fetch sensitive (ncu: stall_no_instruction), so code size is kept down on purpose.
+// The scratch type ES is SolS<8> (light kernel) or SolS<24> (heavy kernel), see so100_scratch.cuh.
 #pragma once
-#include "so100_step.cuh"
+#include "so100_dyn.cuh"
 
 namespace so100 {
 
@@ -62,32 +67,35 @@ __device__ __forceinline__ void untri(int e, int& i, int& j) {
   j = e - tri(i, 0);
 }
 
-template <unsigned LPE> __device__ __forceinline__ void tsum2(const Tile<LPE>& t, float& a, float& b) {
+// M a for dof d (arm block dense, cube block diagonal)
+template <class ES> __device__ __forceinline__ float mul_M(const ES* S, const float* a, int d) {
+  if (d < NL) {
+    float s = 0;
 #pragma unroll
-  for (int off = LPE / 2; off > 0; off >>= 1) {
-    a += t.shfl_xor(a, off);
-    b += t.shfl_xor(b, off);
+    for (int j = 0; j < NL; j++) s = fmaf(S->d.Marm[d >= j ? tri(d, j) : tri(j, d)], a[j], s);
+    return s;
   }
+  return (d < 9 ? c_m.cube_mass : c_m.cube_I[d - 9]) * a[d];
 }
 
 // ------------------------------------------------------------------ contact rows
-template <unsigned LPE> __device__ void make_contact_rows(const Tile<LPE>& t, EnvS* S, const DevTables& T) {
+template <unsigned LPE, class ES> __device__ void make_contact_rows(const Tile<LPE>& t, ES* S, const DevTables& T) {
   const int lane = t.thread_rank();
-  const int ncon = min(S->ncon, NC);
+  const int ncon = S->ncon;
   const float rs_imp = rsqrtf(fmaxf(c_m.impratio, 1e-15f));
   int both = 0;
   for (int c = lane; c < ncon; c += LPE) {
-    const DevPair& P = T.pair[S->cpair[c]];
+    const DevPair& P = T.pair[__float_as_int(S->con[c][7])];
     const int l1 = T.geom[P.g1].link, l2 = T.geom[P.g2].link;
     const int kind = (((l1 >= 0 && l1 < NL) || (l2 >= 0 && l2 < NL)) ? 1 : 0) | ((l1 == NL || l2 == NL) ? 2 : 0);
     S->ckind[c] = (unsigned char)kind;
     both |= (kind == 3);
-    float dist = S->cdist[c];
+    const float dist = S->con[c][6];
     // imp = d0 + y (d1 - d0); 1 - imp is formed from the host's fp64 (1 - d0), not as 1.0f - imp
     const float y = impedance_y(P.solimp, dist);
     const float imp = fmaf(y, P.dd, P.solimp[0]), omi = fmaf(-y, P.dd, P.omd0);
-    float R0 = fmaxf(omi / imp * P.dtran, 1e-15f);
-    float R1 = R0 / fmaxf(c_m.impratio, 1e-15f);
+    const float R0 = fmaxf(omi / imp * P.dtran, 1e-15f);
+    const float R1 = R0 / fmaxf(c_m.impratio, 1e-15f);
     S->cD[c][0] = 1.0f / R0;
     S->cD[c][1] = 1.0f / R1;
     S->cD[c][2] = 1.0f / R1;
@@ -96,20 +104,20 @@ template <unsigned LPE> __device__ void make_contact_rows(const Tile<LPE>& t, En
     S->caref[c][0] = -P.K * imp * dist;
     S->caref[c][1] = S->caref[c][2] = S->caref[c][3] = 0.0f;
   }
-  S->nq1 = t.any(both) ? 1 : 0;                // arm and cube blocks of the Hessian are coupled
+  S->coupled = t.any(both) ? 1 : 0;            // arm and cube blocks of the Hessian are coupled
   for (int it = lane; it < ncon * NV; it += LPE) {
     const int c = it / NV, d = it - c * NV;
-    const DevPair& P = T.pair[S->cpair[c]];
+    const DevPair& P = T.pair[__float_as_int(S->con[c][7])];
     const int l1 = T.geom[P.g1].link, l2 = T.geom[P.g2].link;
-    V3 n = ld3(S->cnrm[c]), t1, t2, pos = ld3(S->cpos[c]);
+    V3 n = ld3(&S->con[c][3]), t1, t2, pos = ld3(&S->con[c][0]);
     make_frame(n, t1, t2);
     V3 jp = mk(0, 0, 0), jr = mk(0, 0, 0);
     if (d < NL) {
       float s = ((l2 >= d && l2 < NL) ? 1.0f : 0.0f) - ((l1 >= d && l1 < NL) ? 1.0f : 0.0f);
       if (s != 0.0f) {
-        V3 ax = ld3(S->axis[d]);
+        V3 ax = ld3(S->f.axis[d]);
         jr = ax * s;
-        jp = cross(ax, pos - ld3(S->lpos[d])) * s;
+        jp = cross(ax, pos - ld3(S->f.lpos[d])) * s;
       }
     } else {
       float s = (l2 == NL ? 1.0f : 0.0f) - (l1 == NL ? 1.0f : 0.0f);
@@ -118,32 +126,31 @@ template <unsigned LPE> __device__ void make_contact_rows(const Tile<LPE>& t, En
         if (k < 3) {
           jp = mk(k == 0 ? s : 0.0f, k == 1 ? s : 0.0f, k == 2 ? s : 0.0f);
         } else {
-          V3 col = mcol(S->lmat[NL], k - 3);
+          V3 col = mcol(S->f.lmat[NL], k - 3);
           jr = col * s;
-          jp = cross(col, pos - ld3(S->lpos[NL])) * s;
+          jp = cross(col, pos - ld3(S->f.lpos[NL])) * s;
         }
       }
     }
-    S->w.J[c * 4 + 0][d] = dot(n, jp);
-    S->w.J[c * 4 + 1][d] = dot(t1, jp);
-    S->w.J[c * 4 + 2][d] = dot(t2, jp);
-    S->w.J[c * 4 + 3][d] = P.dim > 3 ? dot(n, jr) : 0.0f;
+    S->J[c * 4 + 0][d] = dot(n, jp);
+    S->J[c * 4 + 1][d] = dot(t1, jp);
+    S->J[c * 4 + 2][d] = dot(t2, jp);
+    S->J[c * 4 + 3][d] = P.dim > 3 ? dot(n, jr) : 0.0f;
   }
   t.sync();
   for (int it = lane; it < ncon * 4; it += LPE) {
     const int c = it >> 2, k = it & 3;
-    const DevPair& P = T.pair[S->cpair[c]];
+    const DevPair& P = T.pair[__float_as_int(S->con[c][7])];
     float v = 0;
 #pragma unroll 4
-    for (int d = 0; d < NV; d++) v = fmaf(S->w.J[it][d], S->st[S_QVEL + d], v);
+    for (int d = 0; d < NV; d++) v = fmaf(S->J[it][d], S->st[S_QVEL + d], v);
     S->caref[c][k] -= P.B * v;
   }
   t.sync();
 }
 
-// elliptic cone: cost, force and (optionally) the 4x4 Hessian block, packed lower triangle
-template <bool HESS>
-__device__ __forceinline__ float cone_eval(const float* x, const float* D, float mu, float f0, float f1, int dim,
+// elliptic cone: cost, force and (when hess) the 4x4 Hessian block, packed lower triangle
+__device__ __forceinline__ float cone_eval(bool hess, const float* x, const float* D, float mu, float f0, float f1, int dim,
                                            float* force, int& zone, float* Hc) {
   const float fr[3] = {f0, f0, f1};
   float U[4];
@@ -167,7 +174,7 @@ __device__ __forceinline__ float cone_eval(const float* x, const float* D, float
       cost = fmaf(0.5f * dj * x[j], x[j], cost);
       force[j] = -dj * x[j];
     }
-    if (HESS) {
+    if (hess) {
 #pragma unroll
       for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -181,7 +188,7 @@ __device__ __forceinline__ float cone_eval(const float* x, const float* D, float
   force[0] = -Dm * NmT * mu;
 #pragma unroll
   for (int j = 1; j < 4; j++) force[j] = (j < dim) ? -force[0] * invT * U[j] * fr[j - 1] : 0.0f;
-  if (HESS) {
+  if (hess) {
     float g[4], wv[4];
     g[0] = mu; wv[0] = 0;
 #pragma unroll
@@ -233,47 +240,9 @@ __device__ __forceinline__ void cone_ls(const float* x0, const float* v, float a
   d2 += Dm * (dp * dp - NmT * mu * Tpp);
 }
 
-// x = -A^-1 b for a packed 6x6 SPD block (registers only, every lane of the half-tile redundantly)
-__device__ __forceinline__ void chol6_solve_neg(const float* A21, const float* b6, float* x) {
-  float L[21];
-#pragma unroll
-  for (int e = 0; e < 21; e++) L[e] = A21[e];
-#pragma unroll
-  for (int i = 0; i < NL; i++) x[i] = -b6[i];
-#pragma unroll
-  for (int j = 0; j < NL; j++) {
-    float d = L[tri(j, j)];
-#pragma unroll
-    for (int k = 0; k < j; k++) d = fmaf(-L[tri(j, k)], L[tri(j, k)], d);
-    d = rsqrtf(fmaxf(d, 1e-20f));
-    L[tri(j, j)] = d;   // 1 / L_jj
-#pragma unroll
-    for (int i = j + 1; i < NL; i++) {
-      float s = L[tri(i, j)];
-#pragma unroll
-      for (int k = 0; k < j; k++) s = fmaf(-L[tri(i, k)], L[tri(j, k)], s);
-      L[tri(i, j)] = s * d;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < NL; i++) {
-    float s = x[i];
-#pragma unroll
-    for (int k = 0; k < i; k++) s = fmaf(-L[tri(i, k)], x[k], s);
-    x[i] = s * L[tri(i, i)];
-  }
-#pragma unroll
-  for (int i = NL - 1; i >= 0; i--) {
-    float s = x[i];
-#pragma unroll
-    for (int k = i + 1; k < NL; k++) s = fmaf(-L[tri(k, i)], x[k], s);
-    x[i] = s * L[tri(i, i)];
-  }
-}
-
 // ------------------------------------------------------------------ Newton solver
-template <unsigned LPE> struct SolveRegs {
-  static constexpr int RPL = (NC * 4 + LPE - 1) / LPE;   // contact rows (and, on quad leaders, contacts) per lane
+template <unsigned LPE, int NCAP> struct SolveRegs {
+  static constexpr int RPL = (NCAP * 4 + LPE - 1) / LPE;   // contact rows (and, on quad leaders, contacts) per lane
   float qfs, fr_aref, fr_R, fr_D, fr_fl;
   float lim_sgn, lim_D, lim_aref;
   float jar[RPL][4], jv[RPL][4];
@@ -281,11 +250,13 @@ template <unsigned LPE> struct SolveRegs {
   float f0[RPL], f1[RPL];
 };
 
-// cost at S->ad (and forces / cone Hessians when HESS); returns the tile-wide total.
+// cost at S->ad (and forces / cone Hessians when hess); returns the tile-wide total.
 // Per-lane outputs: Ma (dof lanes), dof_force (friction + limit force on dof d).
-template <unsigned LPE, bool HESS>
-__device__ float eval_cost(const Tile<LPE>& t, EnvS* S, SolveRegs<LPE>& r, int ncon, float& Ma, float& dof_force) {
+template <unsigned LPE, class ES>
+__device__ __forceinline__ float eval_cost(const Tile<LPE>& t, ES* S, SolveRegs<LPE, ES::NCAP>& r, bool hess, float& Ma, float& dof_force) {
+  constexpr int RPL = SolveRegs<LPE, ES::NCAP>::RPL;
   const int lane = t.thread_rank();
+  const int ncon = S->ncon;
   float cost = 0;
   Ma = 0; dof_force = 0;
   if (lane < NV) {
@@ -301,11 +272,11 @@ __device__ float eval_cost(const Tile<LPE>& t, EnvS* S, SolveRegs<LPE>& r, int n
       float xl = r.lim_sgn * ad - r.lim_aref;
       if (xl < 0) { cost += 0.5f * r.lim_D * xl * xl; dof_force += -r.lim_sgn * r.lim_D * xl; hd += r.lim_D; }
     }
-    if (HESS) S->hdiag[lane] = hd;
+    if (hess) S->hdiag[lane] = hd;
   }
   const int nrow = ncon * 4;
 #pragma unroll
-  for (int s = 0; s < SolveRegs<LPE>::RPL; s++) {
+  for (int s = 0; s < RPL; s++) {
     if (s * (int)LPE >= nrow) break;
     const int row = lane + s * LPE, c = row >> 2;
     float xv = 0;
@@ -315,7 +286,7 @@ __device__ float eval_cost(const Tile<LPE>& t, EnvS* S, SolveRegs<LPE>& r, int n
       const int d0 = (kind & 1) ? 0 : NL, d1 = (kind & 2) ? NV : NL;
       double v = -(double)S->caref[c][row & 3];
 #pragma unroll 2
-      for (int d = d0; d < d1; d++) v = fma((double)S->w.J[row][d], S->ad[d], v);
+      for (int d = d0; d < d1; d++) v = fma((double)S->J[row][d], S->ad[d], v);
       xv = (float)v;
     }
     const int qb = lane & ~3;
@@ -327,8 +298,8 @@ __device__ float eval_cost(const Tile<LPE>& t, EnvS* S, SolveRegs<LPE>& r, int n
       int zone;
 #pragma unroll
       for (int k = 0; k < 4; k++) r.jar[s][k] = x[k];
-      cost += cone_eval<HESS>(x, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], force, zone, Hc);
-      if (HESS) {
+      cost += cone_eval(hess, x, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], force, zone, Hc);
+      if (hess) {
 #pragma unroll
         for (int k = 0; k < 4; k++) S->cfrc[c][k] = force[k];
         S->czone[c] = (unsigned char)zone;
@@ -343,16 +314,16 @@ __device__ float eval_cost(const Tile<LPE>& t, EnvS* S, SolveRegs<LPE>& r, int n
 }
 
 // contribution of contact c to Hessian entry (i, j)
-__device__ __forceinline__ float hess_contact(const EnvS* S, int c, int zone, int i, int j) {
+template <class ES> __device__ __forceinline__ float hess_contact(const ES* S, int c, int zone, int i, int j) {
   const float* Hc = S->cH[c];
   float h = 0;
   if (zone == 1) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) h = fmaf(Hc[tri(k, k)] * S->w.J[c * 4 + k][i], S->w.J[c * 4 + k][j], h);
+    for (int k = 0; k < 4; k++) h = fmaf(Hc[tri(k, k)] * S->J[c * 4 + k][i], S->J[c * 4 + k][j], h);
   } else {
     float ji[4], jj[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) { ji[k] = S->w.J[c * 4 + k][i]; jj[k] = S->w.J[c * 4 + k][j]; }
+    for (int k = 0; k < 4; k++) { ji[k] = S->J[c * 4 + k][i]; jj[k] = S->J[c * 4 + k][j]; }
 #pragma unroll
     for (int b = 0; b < 4; b++) {
       float tb = 0;
@@ -364,15 +335,20 @@ __device__ __forceinline__ float hess_contact(const EnvS* S, int c, int zone, in
   return h;
 }
 
-template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const DevTables& T, float qas_d, uint32_t* diag) {
+// Solves for qacc (left in S->a / S->ad, contact forces in S->cfrc).  `diag` (nullable): the env's uint32 counters.
+template <unsigned LPE, class ES> __device__ void solve(const Tile<LPE>& t, ES* S, const DevTables& T, uint32_t* diag) {
+  using Regs = SolveRegs<LPE, ES::NCAP>;
   const int lane = t.thread_rank();
-  const int ncon = min(S->ncon, NC);
-  const bool coupled = S->nq1 != 0;
-  SolveRegs<LPE> r;
+  const int ncon = S->ncon;
+  const bool coupled = S->coupled != 0;
+  Regs r;
   // ---- dof rows
   r.qfs = 0; r.fr_aref = 0; r.fr_R = 1; r.fr_D = 0; r.fr_fl = 0; r.lim_sgn = 0; r.lim_D = 0; r.lim_aref = 0;
+  float qas_d = 0, warm_d = 0;
   if (lane < NV) {
-    r.qfs = S->qfs[lane];
+    r.qfs = S->d.qfs[lane];
+    qas_d = S->d.qas[lane];
+    warm_d = S->st[S_WARM + lane];
     r.fr_R = c_m.fr_R[lane]; r.fr_D = c_m.fr_D[lane]; r.fr_fl = c_m.fr_floss[lane];
     const float qd = S->st[S_QVEL + lane];
     r.fr_aref = -c_m.fr_B * qd;
@@ -390,37 +366,37 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
     }
   }
 #pragma unroll
-  for (int s = 0; s < SolveRegs<LPE>::RPL; s++) {
+  for (int s = 0; s < Regs::RPL; s++) {
     const int c = (lane + s * LPE) >> 2;
     r.dim[s] = 3; r.f0[s] = 1; r.f1[s] = 1;
     if ((lane & 3) == 0 && c < ncon) {
-      const DevPair& P = T.pair[S->cpair[c]];
+      const DevPair& P = T.pair[__float_as_int(S->con[c][7])];
       r.dim[s] = P.dim; r.f0[s] = P.f0; r.f1[s] = P.f1;
     }
   }
-  // ---- start point: previous qacc (warm start) unless the unconstrained acceleration is cheaper
-  float Ma, dof_force;
-  if (lane < NV) { S->a[lane] = qas_d; S->ad[lane] = (double)qas_d; }
-  t.sync();
-  const float cs = eval_cost<LPE, false>(t, S, r, ncon, Ma, dof_force);
-  t.sync();
-  if (lane < NV) { S->a[lane] = S->st[S_WARM + lane]; S->ad[lane] = (double)S->st[S_WARM + lane]; }
-  t.sync();
-  float cost = eval_cost<LPE, true>(t, S, r, ncon, Ma, dof_force);
-  t.sync();
-  if (cs < cost) {
-    if (lane < NV) { S->a[lane] = qas_d; S->ad[lane] = (double)qas_d; }
+  // ---- one loop body for: the start-point selection (stage 0: cost of the unconstrained acceleration, stage 1:
+  //      cost + forces of the warm start), the Newton iterations (stage 2) and the final force refresh
+  auto set_a = [&](float v) {
+    if (lane < NV) { S->a[lane] = v; S->ad[lane] = (double)v; }
     t.sync();
-    cost = eval_cost<LPE, true>(t, S, r, ncon, Ma, dof_force);
-    t.sync();
-  }
-  int it = 0;
-  bool converged = false, small_step = false;
-  for (; it < NEWTON_MAXIT; it++) {
-    if (it > 0) {
-      cost = eval_cost<LPE, true>(t, S, r, ncon, Ma, dof_force);
+  };
+  set_a(qas_d);
+  int stage = 0, it = 0;
+  bool need_eval = true, last = false, converged = false;
+  float Ma = 0, dof_force = 0, cost = 0, cost_qas = 0;
+#pragma unroll 1
+  for (;;) {
+    if (need_eval) {
+      cost = eval_cost(t, S, r, stage != 0, Ma, dof_force);
       t.sync();
     }
+    need_eval = true;
+    if (stage == 0) { cost_qas = cost; stage = 1; set_a(warm_d); continue; }
+    if (stage == 1) {
+      stage = 2;
+      if (cost_qas < cost) { set_a(qas_d); continue; }
+    }
+    if (last || it >= NEWTON_MAXIT) break;
     // ---- gradient: M a - qfrc_smooth - J^T f
     float g = 0, jtf = 0;
     if (lane < NV) {
@@ -429,7 +405,7 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
       for (int c = 0; c < ncon; c++) {
         if (S->czone[c] == 0 || !(S->ckind[c] & bit)) continue;
 #pragma unroll
-        for (int k = 0; k < 4; k++) jtf = fmaf(S->w.J[c * 4 + k][lane], S->cfrc[c][k], jtf);
+        for (int k = 0; k < 4; k++) jtf = fmaf(S->J[c * 4 + k][lane], S->cfrc[c][k], jtf);
       }
       g = Ma - r.qfs - jtf;
       S->vec[lane] = g;
@@ -444,10 +420,9 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
       // ---- block-diagonal Hessian: entries 0..20 arm block, 21..41 cube block
       for (int e = lane; e < 42; e += LPE) {
         const int blk = e >= 21 ? 1 : 0, rr = e - 21 * blk;
-        int i, j;
-        untri(rr, i, j);
+        const int i = tri_row6(rr), j = rr - tri(i, 0);
         float h;
-        if (blk == 0) h = S->Marm[rr];
+        if (blk == 0) h = S->d.Marm[rr];
         else h = (i == j) ? (i < 3 ? c_m.cube_mass : c_m.cube_I[i - 3]) : 0.0f;
         const int gi = i + NL * blk, gj = j + NL * blk;
         if (i == j) h += S->hdiag[gi];
@@ -456,13 +431,13 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
           if (zone == 0 || !(S->ckind[c] & (1 << blk))) continue;
           h += hess_contact(S, c, zone, gi, gj);
         }
-        S->u.sol.H[e] = h;
+        S->H[e] = h;
       }
       t.sync();
       // both blocks factored + solved in registers; lower half-tile: arm, upper half-tile: cube
       const int hb = lane >= (int)(LPE / 2) ? 1 : 0;
       float x[NL];
-      chol6_solve_neg(&S->u.sol.H[21 * hb], &S->vec[NL * hb], x);
+      chol6_solve(&S->H[21 * hb], &S->vec[NL * hb], -1.0f, x);
       t.sync();
       if (lane == 0 || lane == (int)(LPE / 2)) {
 #pragma unroll
@@ -476,7 +451,7 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
         int i, j;
         untri(e, i, j);
         float h = 0;
-        if (i < NL) h = S->Marm[e];
+        if (i < NL) h = S->d.Marm[e];
         else if (i == j) h = (i < 9 ? c_m.cube_mass : c_m.cube_I[i - 9]);
         if (i == j) h += S->hdiag[i];
         for (int c = 0; c < ncon; c++) {
@@ -484,36 +459,37 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
           if (zone == 0) continue;
           h += hess_contact(S, c, zone, i, j);
         }
-        S->u.sol.H[e] = h;
+        S->H[e] = h;
       }
       t.sync();
       for (int k = 0; k < NV; k++) {
-        const float dk = rsqrtf(fmaxf(S->u.sol.H[tri(k, k)], 1e-20f));
+        const float dk = rsqrtf(fmaxf(S->H[tri(k, k)], 1e-20f));
         t.sync();
         for (int i = k + lane; i < NV; i += LPE) {
-          if (i == k) S->u.sol.H[tri(k, k)] = dk;      // stores 1 / L_kk
-          else S->u.sol.H[tri(i, k)] *= dk;
+          if (i == k) S->H[tri(k, k)] = dk;      // stores 1 / L_kk
+          else S->H[tri(i, k)] *= dk;
         }
         t.sync();
         for (int e = lane; e < 78; e += LPE) {
           int i, j;
           untri(e, i, j);
-          if (j > k) S->u.sol.H[e] = fmaf(-S->u.sol.H[tri(i, k)], S->u.sol.H[tri(j, k)], S->u.sol.H[e]);
+          if (j > k) S->H[e] = fmaf(-S->H[tri(i, k)], S->H[tri(j, k)], S->H[e]);
         }
         t.sync();
       }
       float x = -g;
       for (int k = 0; k < NV; k++) {
-        float xk = t.shfl(x, k) * S->u.sol.H[tri(k, k)];
+        float xk = t.shfl(x, k) * S->H[tri(k, k)];
         if (lane == k) x = xk;
-        else if (lane > k && lane < NV) x = fmaf(-S->u.sol.H[tri(lane, k)], xk, x);
+        else if (lane > k && lane < NV) x = fmaf(-S->H[tri(lane, k)], xk, x);
       }
       for (int k = NV - 1; k >= 0; k--) {
-        float xk = t.shfl(x, k) * S->u.sol.H[tri(k, k)];
+        float xk = t.shfl(x, k) * S->H[tri(k, k)];
         if (lane == k) x = xk;
-        else if (lane < k) x = fmaf(-S->u.sol.H[tri(k, lane)], xk, x);
+        else if (lane < k) x = fmaf(-S->H[tri(k, lane)], xk, x);
       }
       pd = (lane < NV) ? x : 0.0f;
+      t.sync();
       if (lane < NV) S->vec[lane] = pd;
       t.sync();
     }
@@ -524,7 +500,7 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
     tsum2(t, pMp, pg);
     const int nrow = ncon * 4;
 #pragma unroll
-    for (int s = 0; s < SolveRegs<LPE>::RPL; s++) {
+    for (int s = 0; s < Regs::RPL; s++) {
       if (s * (int)LPE >= nrow) break;
       const int row = lane + s * LPE, c = row >> 2;
       float v = 0;
@@ -532,7 +508,7 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
         const int kind = S->ckind[c];
         const int d0 = (kind & 1) ? 0 : NL, d1 = (kind & 2) ? NV : NL;
 #pragma unroll 2
-        for (int d = d0; d < d1; d++) v = fmaf(S->w.J[row][d], S->vec[d], v);
+        for (int d = d0; d < d1; d++) v = fmaf(S->J[row][d], S->vec[d], v);
       }
       const int qb = lane & ~3;
 #pragma unroll
@@ -540,58 +516,58 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
     }
     const float a0 = S->a[lane < NV ? lane : 0];
     const float xf0 = a0 - r.fr_aref, xl0 = r.lim_sgn * a0 - r.lim_aref;
-    auto ls_eval = [&](float alpha, float& D1, float& D2) {
-      float d1 = 0, d2 = 0;
+    // ---- exact line search: safeguarded 1-D Newton on phi' (first trip: alpha = 0)
+    float alpha = 0, d1 = 0, d2 = 1, lo = 0, hi = -1, d10 = 0;
+    bool descent = true;
+#pragma unroll 1
+    for (int ls = -1; ls < LS_MAXIT; ls++) {
+      if (ls >= 0) {
+        float na = alpha - d1 / d2;
+        if (hi >= 0 && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
+        alpha = na;
+      }
+      float e1 = 0, e2 = 0;
       if (lane < NV) {
         const float x = fmaf(alpha, pd, xf0), rf = r.fr_R * r.fr_fl;
-        if (x <= -rf) d1 = -r.fr_fl * pd;
-        else if (x >= rf) d1 = r.fr_fl * pd;
-        else { d1 = r.fr_D * x * pd; d2 = r.fr_D * pd * pd; }
+        if (x <= -rf) e1 = -r.fr_fl * pd;
+        else if (x >= rf) e1 = r.fr_fl * pd;
+        else { e1 = r.fr_D * x * pd; e2 = r.fr_D * pd * pd; }
         if (r.lim_sgn != 0.0f) {
           const float v = r.lim_sgn * pd, xl = fmaf(alpha, v, xl0);
-          if (xl < 0) { d1 = fmaf(r.lim_D * xl, v, d1); d2 = fmaf(r.lim_D * v, v, d2); }
+          if (xl < 0) { e1 = fmaf(r.lim_D * xl, v, e1); e2 = fmaf(r.lim_D * v, v, e2); }
         }
       }
       if ((lane & 3) == 0) {
 #pragma unroll
-        for (int s = 0; s < SolveRegs<LPE>::RPL; s++) {
+        for (int s = 0; s < Regs::RPL; s++) {
           const int c = (lane + s * LPE) >> 2;
-          if (c < ncon) cone_ls(r.jar[s], r.jv[s], alpha, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], d1, d2);
+          if (c < ncon) cone_ls(r.jar[s], r.jv[s], alpha, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], e1, e2);
         }
       }
-      tsum2(t, d1, d2);
-      D1 = d1 + pg + alpha * pMp;
-      D2 = d2 + pMp;
-    };
-    // ---- exact line search: safeguarded 1-D Newton on phi'
-    float alpha = 0, d1, d2, lo = 0, hi = -1;
-    ls_eval(0.0f, d1, d2);
-    const float d10 = fabsf(d1);
-    if (!(d1 < 0)) { converged = true; break; }   // no descent left at float32 resolution
-    for (int ls = 0; ls < LS_MAXIT; ls++) {
-      float na = alpha - d1 / d2;
-      if (hi >= 0 && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
-      alpha = na;
-      ls_eval(alpha, d1, d2);
+      tsum2(t, e1, e2);
+      d1 = e1 + pg + alpha * pMp;
+      d2 = e2 + pMp;
+      if (ls < 0) {
+        d10 = fabsf(d1);
+        if (!(d1 < 0)) { descent = false; break; }   // no descent left at float32 resolution
+        continue;
+      }
       if (fabsf(d1) <= 1e-4f * d10) break;
       if (d1 < 0) lo = alpha; else hi = alpha;
     }
+    if (!descent) { converged = true; break; }
     if (lane < NV) {
       const double na = fma((double)alpha, (double)pd, S->ad[lane]);
       S->ad[lane] = na; S->a[lane] = (float)na;
     }
     t.sync();
-    // predicted decrease 1/2 alpha |phi'(0)| below float32 resolution of the cost: stop (MuJoCo's
-    // "improvement < tolerance" test, made relative because the arithmetic is float32)
-    if (0.5f * alpha * d10 < SO100_ITOL * (1.0f + fabsf(cost))) { small_step = true; it++; break; }
-  }
-  if (!converged) {
-    // forces at the last iterate (small step / iteration cap): refresh so cfrc matches S->a
-    eval_cost<LPE, true>(t, S, r, ncon, Ma, dof_force);
-    t.sync();
+    it++;
+    // predicted decrease 1/2 alpha |phi'(0)| below float32 resolution of the cost: stop after refreshing the forces
+    // (MuJoCo's "improvement < tolerance" test, made relative because the arithmetic is float32)
+    if (0.5f * alpha * d10 < SO100_ITOL * (1.0f + fabsf(cost))) last = true;
   }
   if (lane == 0 && diag) {
-    diag[1] += (converged || small_step) ? 0u : 1u;
+    diag[1] += (converged || last) ? 0u : 1u;
     diag[5] += (uint32_t)it;
     diag[6] += 1u;
     diag[7] += (uint32_t)ncon;
@@ -599,7 +575,7 @@ template <unsigned LPE> __device__ void solve(const Tile<LPE>& t, EnvS* S, const
 }
 
 // ------------------------------------------------------------------ semi-implicit Euler
-template <unsigned LPE> __device__ void integrate(const Tile<LPE>& t, EnvS* S) {
+template <unsigned LPE, class ES> __device__ void integrate(const Tile<LPE>& t, ES* S) {
   const int lane = t.thread_rank();
   const float h = c_m.timestep;
   if (lane < NV) {

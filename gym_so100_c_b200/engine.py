@@ -165,14 +165,22 @@ class BatchedSim:
                   "so100_forward")
         return dict(qacc=qacc, ncon=ncon, con_geom=geom, con_data=data, sites=sites)
 
+    def debug_read(self, what: int) -> torch.Tensor:
+        """Raw per-env records (development aid): what=0 state record, what=1 phase workspace."""
+        words = C.c_int64(0)
+        ext.check(self.lib.so100_debug_read(self.h, int(what), None, C.byref(words), self._stream()), "so100_debug_read")
+        out = torch.empty((self.n, int(words.value)), dtype=torch.float32, device=self.device)
+        ext.check(self.lib.so100_debug_read(self.h, int(what), _ptr(out), None, self._stream()), "so100_debug_read")
+        return out
+
     def phase_timing(self, enable: bool, read: bool = False):
         """Toggle per-kernel CUDA-event timing of `step`; with read=True returns ({class: ms}, {class: launches})
         accumulated since the previous call (synchronises the stream)."""
-        ms = np.zeros(4, dtype=np.float32)
-        cnt = np.zeros(4, dtype=np.int32)
+        ms = np.zeros(6, dtype=np.float32)
+        cnt = np.zeros(6, dtype=np.int32)
         ext.check(self.lib.so100_phase_timing(self.h, int(enable), ms.ctypes.data_as(C.c_void_p) if read else None,
                                               cnt.ctypes.data_as(C.c_void_p) if read else None, self._stream()), "so100_phase_timing")
-        names = ["kin_dyn", "collide", "solve", "task"]
+        names = ["kin_dyn", "collide_box", "solve_light", "task", "collide_hull", "solve_heavy"]
         return dict(zip(names, ms.tolist())), dict(zip(names, cnt.tolist()))
 
     def diagnostics(self) -> Dict[str, int]:

@@ -15,7 +15,7 @@ _lib = None
 SYMBOLS = [
     "so100_create", "so100_destroy", "so100_num_envs", "so100_reset", "so100_step", "so100_step_host",
     "so100_compute_reward", "so100_get_state", "so100_set_state", "so100_get_aux", "so100_set_aux",
-    "so100_substeps", "so100_forward", "so100_diagnostics", "so100_phase_timing", "so100_last_error",
+    "so100_substeps", "so100_forward", "so100_diagnostics", "so100_phase_timing", "so100_debug_read", "so100_last_error",
 ]
 
 MAX_CONTACTS = 24
@@ -58,6 +58,7 @@ def load():
     lib.so100_forward.argtypes = [vp] * 7
     lib.so100_diagnostics.argtypes = [vp, vp, vp]
     lib.so100_phase_timing.argtypes = [vp, i32, vp, vp, vp]
+    lib.so100_debug_read.argtypes = [vp, i32, vp, vp, vp]
     lib.so100_last_error.restype = C.c_char_p
     for name in SYMBOLS:
         if name != "so100_last_error":

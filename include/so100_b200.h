@@ -109,10 +109,16 @@ int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom,
 int so100_diagnostics(so100_handle h, int64_t* out8, void* stream);
 
 /* Measurement aid (bench.py roofline): when enabled, every kernel launched by so100_step is bracketed by a CUDA
- * event pair on `stream`.  A call first reports (if ms4 / launches4 are non-NULL; synchronises the stream) the
+ * event pair on `stream`.  A call first reports (if ms6 / launches6 are non-NULL; synchronises the stream) the
  * accumulated device time and launch count per kernel class since the previous call -- [0] kinematics+dynamics,
- * [1] collision, [2] constraint solve + integration, [3] task layer -- then clears the record and sets the mode. */
-int so100_phase_timing(so100_handle h, int enable, float* ms4, int32_t* launches4, void* stream);
+ * [1] collision, box stage, [2] constraint solve + integration (<= 8 contacts), [3] task layer, [4] collision, GJK/EPA
+ * queue, [5] constraint solve, heavy queue -- then clears the record and sets the mode. */
+int so100_phase_timing(so100_handle h, int enable, float* ms6, int32_t* launches6, void* stream);
+
+/* Development aid: raw copy of the per-env records.  what = 0: state record, 1: phase workspace (link frames, mass
+ * matrix, contact list, collision statistics).  `words_per_env` (host, nullable) receives the record length in float
+ * words; `out` (device, nullable) receives [N, words_per_env] floats. */
+int so100_debug_read(so100_handle h, int what, float* out, int64_t* words_per_env, void* stream);
 
 const char* so100_last_error(void);
 
