@@ -22,10 +22,10 @@ static_assert(NC == SO100_MAX_CONTACTS, "contact capacity mismatch");
 #define SO100_LPE_K1 16
 #endif
 #ifndef SO100_LPE_K3L
-#define SO100_LPE_K3L 16
+#define SO100_LPE_K3L 32
 #endif
 constexpr unsigned LPE_K1 = SO100_LPE_K1, LPE_K2A = 32, LPE_K2B = 32, LPE_K3L = SO100_LPE_K3L, LPE_K3H = 32, LPE_K4 = 32;
-constexpr int BLOCK = 128;
+constexpr int BLOCK = 128, TPB_K3L = SO100_TPB_K3L;
 enum { CLS_KIN = 0, CLS_BOX = 1, CLS_SOLVE = 2, CLS_TASK = 3, CLS_HULL = 4, CLS_HEAVY = 5, CLS_N = 6 };
 
 static thread_local std::string g_err;
@@ -36,6 +36,17 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     if (e_ != cudaSuccess) return fail(SO100_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+// A contiguous range of envs that runs the step pipeline on its own stream.  Kernel durations are set by their slowest
+// env (a 25-iteration Newton solve or a GJK/EPA pair is ~10x the typical one), so one grid over all envs leaves the GPU
+// nearly idle during every kernel's tail; with several independent groups the tail of one group's kernel overlaps the
+// bulk of another's.  The heavy solve queue of each group drains on a second stream beside the light kernel.
+struct EnvGroup {
+  int off = 0, n = 0;
+  cudaStream_t st = nullptr, side = nullptr;            // st == nullptr: the caller's stream
+  cudaEvent_t fork = nullptr, join = nullptr, done = nullptr;
+  int* ctl = nullptr;                                   // this group's queue control words
+};
+
 struct so100_ctx {
   int n = 0, device = 0, task = 0, nsub = 10;
   uint64_t seed = 0;
@@ -44,17 +55,30 @@ struct so100_ctx {
   DevGeom* geom = nullptr;
   DevPair* pair = nullptr;
   float4* vert = nullptr;
+  uchar4* bpair = nullptr;
   unsigned long long* diag = nullptr;
   float* work = nullptr;      // [N, WORK_WORDS] phase-pipeline workspace (L2-resident)
-  int* qmem = nullptr;        // queue control words + hull queue [N] + heavy queue [N]
+  int* qmem = nullptr;        // queue control words + heavy queue [N] + hull-pair queue [N * NHP]
+  // so100_step replays a CUDA graph of its whole launch sequence (all groups, forks and joins): the host cost of a step
+  // drops from several hundred launch / event calls to one cudaGraphLaunch.  Actions are staged into a fixed buffer so
+  // that the graph's kernel arguments never change; one graph is cached per distinct set of output pointers.
+  struct StepGraph { const void* key[10]; cudaGraphExec_t exec; };
+  std::vector<StepGraph> graphs;
+  cudaStream_t cap = nullptr;
+  float* act_stage = nullptr;
+  bool use_graph = true;
+  EnvGroup whole;             // all envs on the caller's stream (small batches, forward / substeps, timing mode)
+  std::vector<EnvGroup> groups;
+  cudaEvent_t ev_start = nullptr;
   int sm_count = 148;
   bool timing = false;        // so100_phase_timing: CUDA-event pairs around every phase-kernel launch
   std::vector<std::pair<cudaEvent_t, int>> events;   // (event, kernel class) begin markers, class -1 = end marker
   // staging for the host-buffer entry point
   float *h_action = nullptr, *h_obs = nullptr, *h_ag = nullptr, *h_dg = nullptr, *h_rew = nullptr, *h_fin = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_succ = nullptr;
-  DevTables tables() const { return DevTables{geom, pair, vert}; }
-  Queues queues() const { return Queues{qmem, qmem + 32, qmem + 32 + n}; }
+  DevTables tables() const { return DevTables{geom, pair, vert, bpair}; }
+  static constexpr int CTL_WORDS = 8 * 40;
+  Queues queues(const EnvGroup& G) const { return Queues{G.ctl, qmem + CTL_WORDS + n + (size_t)G.off * NHP, qmem + CTL_WORDS + G.off}; }
 };
 
 // ------------------------------------------------------------------ small host math (double)
@@ -290,8 +314,8 @@ static int build_dev_model(const so100_model& m, DevModel& dm, std::vector<DevGe
 }
 
 // ------------------------------------------------------------------ launches
-template <class ST> static size_t smem_of(unsigned lpe) { return (size_t)(BLOCK / lpe) * sizeof(ST); }
-static int grid_of(int n, unsigned lpe) { const int epb = BLOCK / (int)lpe; return (n + epb - 1) / epb; }
+template <class ST> static size_t smem_of(unsigned lpe, int tpb = BLOCK) { return (size_t)(tpb / lpe) * sizeof(ST); }
+static int grid_of(int n, unsigned lpe, int tpb = BLOCK) { const int epb = tpb / (int)lpe; return (n + epb - 1) / epb; }
 
 static int configure_kernels() {
   static bool done = false;
@@ -299,7 +323,7 @@ static int configure_kernels() {
   CUDA_OK(cudaFuncSetAttribute(phase_kin_dyn<LPE_K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<KinS>(LPE_K1)));
   CUDA_OK(cudaFuncSetAttribute(phase_collide_box<LPE_K2A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<BoxS>(LPE_K2A)));
   CUDA_OK(cudaFuncSetAttribute(phase_collide_hull<LPE_K2B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<HullS>(LPE_K2B)));
-  CUDA_OK(cudaFuncSetAttribute(phase_solve_light<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L)));
+  CUDA_OK(cudaFuncSetAttribute(phase_solve_light<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NC>>(LPE_K3H)));
   done = true;
   return SO100_OK;
@@ -315,28 +339,68 @@ static void mark(so100_ctx* h, cudaStream_t st, int cls, bool begin) {
 }
 
 // K1: kinematics (+ dynamics), K2a/K2b: collision.  Leaves frames, M, qfrc_smooth and the contact list in the workspace.
-static void launch_position_stage(so100_ctx* h, cudaStream_t st, const float* action, int with_dyn) {
-  const int n = h->n;
+static void launch_position_stage(so100_ctx* h, const EnvGroup& G, cudaStream_t st, const float* action, int with_dyn) {
+  const int n = G.n;
   const DevTables T = h->tables();
-  const Queues Q = h->queues();
+  const Queues Q = h->queues(G);
+  float* state = h->state + (size_t)G.off * STATE_WORDS;
+  float* work = h->work + (size_t)G.off * WORK_WORDS;
   mark(h, st, CLS_KIN, true);
-  phase_kin_dyn<LPE_K1><<<grid_of(n, LPE_K1), BLOCK, smem_of<KinS>(LPE_K1), st>>>(h->state, h->work, action, n, with_dyn, Q);
+  phase_kin_dyn<LPE_K1><<<grid_of(n, LPE_K1), BLOCK, smem_of<KinS>(LPE_K1), st>>>(state, work, action ? action + (size_t)G.off * 6 : nullptr, n, with_dyn, Q);
   mark(h, st, CLS_KIN, false); mark(h, st, CLS_BOX, true);
-  phase_collide_box<LPE_K2A><<<grid_of(n, LPE_K2A), BLOCK, smem_of<BoxS>(LPE_K2A), st>>>(h->work, n, T, Q);
+  phase_collide_box<LPE_K2A><<<grid_of(n, LPE_K2A), BLOCK, smem_of<BoxS>(LPE_K2A), st>>>(work, n, T, Q);
   mark(h, st, CLS_BOX, false); mark(h, st, CLS_HULL, true);
-  phase_collide_hull<LPE_K2B><<<std::min(grid_of(n, LPE_K2B), h->sm_count * 8), BLOCK, smem_of<HullS>(LPE_K2B), st>>>(h->work, T, Q);
+  phase_collide_hull<LPE_K2B><<<std::min(grid_of(n, LPE_K2B), h->sm_count * 8), BLOCK, smem_of<HullS>(LPE_K2B), st>>>(work, T, Q);
   mark(h, st, CLS_HULL, false);
 }
 
-// K3l/K3h: constraint solve (+ Euler unless O.forward)
-static void launch_solve_stage(so100_ctx* h, cudaStream_t st, const SolveOut& O) {
-  const int n = h->n;
+// K3l/K3h: constraint solve (+ Euler unless O.forward).  The heavy queue (a handful of envs with long serial Newton
+// runs) is drained on a side stream beside the light kernel; both rejoin `st`.
+static void launch_solve_stage(so100_ctx* h, const EnvGroup& G, cudaStream_t st, const SolveOut& O) {
+  const int n = G.n;
   const DevTables T = h->tables();
+  float* state = h->state + (size_t)G.off * STATE_WORDS;
+  const float* work = h->work + (size_t)G.off * WORK_WORDS;
+  cudaEventRecord(G.fork, st);
+  cudaStreamWaitEvent(G.side, G.fork, 0);
+  mark(h, G.side, CLS_HEAVY, true);
+  phase_solve_heavy<LPE_K3H><<<std::min(grid_of(n, LPE_K3H), h->sm_count * 2), BLOCK, smem_of<SolS<NC>>(LPE_K3H), G.side>>>(state, work, T, h->queues(G), O);
+  mark(h, G.side, CLS_HEAVY, false);
+  cudaEventRecord(G.join, G.side);
   mark(h, st, CLS_SOLVE, true);
-  phase_solve_light<LPE_K3L><<<grid_of(n, LPE_K3L), BLOCK, smem_of<SolS<NCL>>(LPE_K3L), st>>>(h->state, h->work, n, T, O);
-  mark(h, st, CLS_SOLVE, false); mark(h, st, CLS_HEAVY, true);
-  phase_solve_heavy<LPE_K3H><<<std::min(grid_of(n, LPE_K3H), h->sm_count * 4), BLOCK, smem_of<SolS<NC>>(LPE_K3H), st>>>(h->state, h->work, T, h->queues(), O);
-  mark(h, st, CLS_HEAVY, false);
+  phase_solve_light<LPE_K3L><<<grid_of(n, LPE_K3L, TPB_K3L), TPB_K3L, smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L), st>>>(state, work, n, T, O);
+  mark(h, st, CLS_SOLVE, false);
+  cudaStreamWaitEvent(st, G.join, 0);
+}
+
+static int make_group(so100_ctx* h, EnvGroup& G, int off, int n, int index, bool own_stream) {
+  G.off = off; G.n = n; G.ctl = h->qmem + 8 * index;
+  if (own_stream) CUDA_OK(cudaStreamCreateWithFlags(&G.st, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&G.side, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&G.fork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&G.join, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
+  return SO100_OK;
+}
+static void free_group(EnvGroup& G) {
+  if (G.st) cudaStreamDestroy(G.st);
+  if (G.side) cudaStreamDestroy(G.side);
+  if (G.fork) cudaEventDestroy(G.fork);
+  if (G.join) cudaEventDestroy(G.join);
+  if (G.done) cudaEventDestroy(G.done);
+}
+
+// Runs `body(group, stream)` for every env group: on the groups' own streams, forked from and joined back into `st`,
+// or (one group / timing mode) directly on `st`.
+template <class F> static void for_each_group(so100_ctx* h, cudaStream_t st, bool allow_groups, F body) {
+  if (!allow_groups || h->timing || h->groups.size() < 2) { body(h->whole, st); return; }
+  cudaEventRecord(h->ev_start, st);
+  for (EnvGroup& G : h->groups) {
+    cudaStreamWaitEvent(G.st, h->ev_start, 0);
+    body(G, G.st);
+    cudaEventRecord(G.done, G.st);
+    cudaStreamWaitEvent(st, G.done, 0);
+  }
 }
 
 extern "C" {
@@ -376,12 +440,39 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   CUDA_OK(cudaMalloc(&h->diag, SO100_NDIAG * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&h->work, (size_t)num_envs * WORK_WORDS * sizeof(float)));
   CUDA_OK(cudaMemset(h->work, 0, (size_t)num_envs * WORK_WORDS * sizeof(float)));
-  CUDA_OK(cudaMalloc(&h->qmem, (32 + 2 * (size_t)num_envs) * sizeof(int)));
-  CUDA_OK(cudaMemset(h->qmem, 0, (32 + 2 * (size_t)num_envs) * sizeof(int)));
+  CUDA_OK(cudaMalloc(&h->qmem, (so100_ctx::CTL_WORDS + (1 + NHP) * (size_t)num_envs) * sizeof(int)));
+  CUDA_OK(cudaMemset(h->qmem, 0, (so100_ctx::CTL_WORDS + (1 + NHP) * (size_t)num_envs) * sizeof(int)));
+  CUDA_OK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+  CUDA_OK(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
+  CUDA_OK(cudaMalloc(&h->act_stage, (size_t)num_envs * 6 * sizeof(float)));
+  if (const char* e = getenv("SO100_GRAPH")) h->use_graph = atoi(e) != 0;
+  {
+    // env groups: SO100_GROUPS overrides; default one group per 2048 envs, at most 8
+    int ng = std::min(8, num_envs / 2048);
+    if (const char* e = getenv("SO100_GROUPS")) ng = atoi(e);
+    ng = std::max(1, std::min(ng, 32));
+    rc = make_group(h, h->whole, 0, num_envs, 32, false);
+    if (rc) return rc;
+    if (ng > 1) {
+      const int per = ((num_envs + ng - 1) / ng + 7) / 8 * 8;
+      for (int g = 0, off = 0; g < ng && off < num_envs; g++, off += per) {
+        h->groups.emplace_back();
+        rc = make_group(h, h->groups.back(), off, std::min(per, num_envs - off), g, true);
+        if (rc) return rc;
+      }
+    }
+  }
   CUDA_OK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
   CUDA_OK(cudaMemcpy(h->geom, geoms.data(), geoms.size() * sizeof(DevGeom), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(h->pair, pairs.data(), pairs.size() * sizeof(DevPair), cudaMemcpyHostToDevice));
   if (!verts.empty()) CUDA_OK(cudaMemcpy(h->vert, verts.data(), verts.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  {
+    std::vector<uchar4> bp(pairs.size());
+    for (size_t p = 0; p < pairs.size(); p++)
+      bp[p] = make_uchar4((unsigned char)pairs[p].g1, (unsigned char)pairs[p].g2, (unsigned char)pairs[p].mode, (unsigned char)pairs[p].dim);
+    CUDA_OK(cudaMalloc(&h->bpair, bp.size() * sizeof(uchar4)));
+    CUDA_OK(cudaMemcpy(h->bpair, bp.data(), bp.size() * sizeof(uchar4), cudaMemcpyHostToDevice));
+  }
   const int total = num_envs * STATE_WORDS;
   init_state_kernel<<<(total + 255) / 256, 256>>>(h->state, num_envs);
   CUDA_OK(cudaGetLastError());
@@ -393,7 +484,13 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
 int so100_destroy(so100_handle h) {
   if (!h) return SO100_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->state); cudaFree(h->geom); cudaFree(h->pair); cudaFree(h->vert); cudaFree(h->diag); cudaFree(h->work); cudaFree(h->qmem);
+  cudaFree(h->state); cudaFree(h->geom); cudaFree(h->pair); cudaFree(h->vert); cudaFree(h->bpair); cudaFree(h->diag); cudaFree(h->work); cudaFree(h->qmem);
+  free_group(h->whole);
+  for (EnvGroup& G : h->groups) free_group(G);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+  if (h->cap) cudaStreamDestroy(h->cap);
+  cudaFree(h->act_stage);
   cudaFree(h->h_action); cudaFree(h->h_obs); cudaFree(h->h_ag); cudaFree(h->h_dg); cudaFree(h->h_rew); cudaFree(h->h_fin);
   cudaFree(h->h_term); cudaFree(h->h_trunc); cudaFree(h->h_succ);
   delete h;
@@ -413,6 +510,34 @@ int so100_reset(so100_handle h, const uint8_t* mask, const float* box_pose, floa
   return SO100_OK;
 }
 
+// the launch sequence of one env step on `stream` (directly, or while `stream` is being captured into a graph)
+static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream) {
+  const float* action = A.action;
+  for_each_group(h, stream, true, [&](const EnvGroup& G, cudaStream_t st) {
+    const SolveOut O{nullptr, nullptr, 0};
+    for (int s = 0; s < h->nsub; s++) {
+      launch_position_stage(h, G, st, s == 0 ? action : nullptr, 1);
+      launch_solve_stage(h, G, st, O);
+    }
+    // trailing mj_step1 (dm_control's legacy step): positions + contacts of the new state, then the task layer
+    launch_position_stage(h, G, st, h->nsub == 0 ? action : nullptr, 0);
+    StepArgs B = A;
+    const size_t o = (size_t)G.off;
+    B.state += o * STATE_WORDS; B.n = G.n; B.env_offset += G.off;
+    if (B.obs) B.obs += o * 15;
+    if (B.achieved) B.achieved += o * 3;
+    if (B.desired) B.desired += o * 3;
+    if (B.reward) B.reward += o;
+    if (B.final_obs) B.final_obs += o * 15;
+    if (B.terminated) B.terminated += o;
+    if (B.truncated) B.truncated += o;
+    if (B.success) B.success += o;
+    mark(h, st, CLS_TASK, true);
+    phase_task<LPE_K4><<<grid_of(G.n, LPE_K4), BLOCK, smem_of<TaskS>(LPE_K4), st>>>(B, h->work + o * WORK_WORDS, h->tables());
+    mark(h, st, CLS_TASK, false);
+  });
+}
+
 int so100_step(so100_handle h, const float* action, int autoreset, float* obs, float* achieved, float* desired, float* reward,
                uint8_t* terminated, uint8_t* truncated, uint8_t* success, float* final_obs, void* stream) {
   if (!h || !action) return fail(SO100_ERR_ARG, "so100_step: null handle or action");
@@ -422,17 +547,32 @@ int so100_step(so100_handle h, const float* action, int autoreset, float* obs, f
   A.n = h->n; A.autoreset = autoreset; A.task = h->task;
   A.seed_lo = (uint32_t)h->seed; A.seed_hi = (uint32_t)(h->seed >> 32); A.env_offset = h->env_offset;
   cudaStream_t st = (cudaStream_t)stream;
-  const SolveOut O{nullptr, nullptr, 0};
-  for (int s = 0; s < h->nsub; s++) {
-    launch_position_stage(h, st, s == 0 ? action : nullptr, 1);
-    launch_solve_stage(h, st, O);
+  if (!h->use_graph || h->timing) {
+    enqueue_step(h, A, st);
+    CUDA_OK(cudaGetLastError());
+    return SO100_OK;
   }
-  // trailing mj_step1 (dm_control's legacy step): positions + contacts of the new state, then the task layer
-  launch_position_stage(h, st, h->nsub == 0 ? action : nullptr, 0);
-  mark(h, st, CLS_TASK, true);
-  phase_task<LPE_K4><<<grid_of(h->n, LPE_K4), BLOCK, smem_of<TaskS>(LPE_K4), st>>>(A, h->work, h->tables());
-  mark(h, st, CLS_TASK, false);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(h->act_stage, action, (size_t)h->n * 6 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  A.action = h->act_stage;
+  const void* key[10] = {obs, achieved, desired, reward, terminated, truncated, success, final_obs,
+                         reinterpret_cast<const void*>((size_t)(autoreset != 0)), nullptr};
+  cudaGraphExec_t exec = nullptr;
+  for (auto& g : h->graphs)
+    if (memcmp(g.key, key, sizeof(key)) == 0) exec = g.exec;
+  if (!exec) {
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal));
+    enqueue_step(h, A, h->cap);
+    CUDA_OK(cudaStreamEndCapture(h->cap, &graph));
+    CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    if (h->graphs.size() >= 8) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+    so100_ctx::StepGraph g;
+    memcpy(g.key, key, sizeof(key));
+    g.exec = exec;
+    h->graphs.push_back(g);
+  }
+  CUDA_OK(cudaGraphLaunch(exec, st));
   return SO100_OK;
 }
 
@@ -502,12 +642,13 @@ int so100_set_aux(so100_handle h, const float* goal, const int32_t* step_count, 
 
 int so100_substeps(so100_handle h, int nsub, void* stream) {
   if (!h || nsub < 0) return fail(SO100_ERR_ARG, "so100_substeps: bad argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  const SolveOut O{nullptr, nullptr, 0};
-  for (int s = 0; s < nsub; s++) {
-    launch_position_stage(h, st, nullptr, 1);
-    launch_solve_stage(h, st, O);
-  }
+  for_each_group(h, (cudaStream_t)stream, true, [&](const EnvGroup& G, cudaStream_t st) {
+    const SolveOut O{nullptr, nullptr, 0};
+    for (int s = 0; s < nsub; s++) {
+      launch_position_stage(h, G, st, nullptr, 1);
+      launch_solve_stage(h, G, st, O);
+    }
+  });
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
@@ -515,10 +656,10 @@ int so100_substeps(so100_handle h, int nsub, void* stream) {
 int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom, float* con_data, float* sites, void* stream) {
   if (!h) return fail(SO100_ERR_ARG, "so100_forward: null handle");
   cudaStream_t st = (cudaStream_t)stream;
-  launch_position_stage(h, st, nullptr, 1);
+  launch_position_stage(h, h->whole, st, nullptr, 1);
   const int threads = h->n * 32;
   export_forward_kernel<<<(threads + 255) / 256, 256, 0, st>>>(h->work, h->n, ncon, con_geom, con_data, sites, h->tables());
-  launch_solve_stage(h, st, SolveOut{qacc, con_data, 1});
+  launch_solve_stage(h, h->whole, st, SolveOut{qacc, con_data, 1});
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }

@@ -51,8 +51,8 @@ __device__ __forceinline__ void put_contact(float* con, int c, V3 p, V3 n, float
 
 // 15-axis separating-axis test.  Returns false when separated; otherwise `code` = 0..5 (face axis of
 // A / B) or 6 + 3 i + j (edge axis A_i x B_j) and `sep` < 0 the signed separation along it.
-// FULL = false: overlap test only (cull), with a 1e-6 slack on |R|.
-template <bool FULL> __device__ __forceinline__ bool box_sat(const Obb& A, const Obb& B, int& code, float& sep_out) {
+// cull = true (hull pairs): overlap test only, with a 1e-6 slack on |R|.
+__device__ __forceinline__ bool box_sat(const Obb& A, const Obb& B, bool cull, int& code, float& sep_out) {
   float R[3][3], aR[3][3], tA[3], tB[3];
   const V3 t = B.c - A.c;
 #pragma unroll
@@ -60,7 +60,7 @@ template <bool FULL> __device__ __forceinline__ bool box_sat(const Obb& A, const
     tA[i] = dot(t, A.ax[i]);
     tB[i] = dot(t, B.ax[i]);
 #pragma unroll
-    for (int j = 0; j < 3; j++) { R[i][j] = dot(A.ax[i], B.ax[j]); aR[i][j] = fabsf(R[i][j]) + (FULL ? 0.0f : 1e-6f); }
+    for (int j = 0; j < 3; j++) { R[i][j] = dot(A.ax[i], B.ax[j]); aR[i][j] = fabsf(R[i][j]) + (cull ? 1e-6f : 0.0f); }
   }
   float best_face = -1e30f;
   code = 0;
@@ -87,7 +87,7 @@ template <bool FULL> __device__ __forceinline__ bool box_sat(const Obb& A, const
       const float ra = A.h[i1] * aR[i2][j] + A.h[i2] * aR[i1][j];
       const float rb = B.h[j1] * aR[i][j2] + B.h[j2] * aR[i][j1];
       const float num = fabsf(tA[i2] * R[i1][j] - tA[i1] * R[i2][j]) - (ra + rb);
-      if (!FULL) {
+      if (cull) {
         if (num > 0) return false;
         continue;
       }
@@ -240,107 +240,92 @@ __device__ int box_contacts(const Tile<LPE>& t, float* con, int base, const Obb&
 
 // Stage A for one env.  Writes the contact list and the header of workspace record `w`; returns (on every lane)
 // the number of hull pairs that need GJK/EPA, with *ncon_out the contact count so far (NC + 1 = overflow).
+//   1. world bounds of the 25 collidable geoms (one lane each): centre + bounding radius, AABB half extents;
+//   2. broad phase over the static 191-pair table (one lane per pair): sphere-sphere and AABB-AABB; any
+//      conservative filter gives the same contacts, because every survivor goes through the exact test of 3;
+//   3. 15-axis separating-axis test on the oriented boxes, one lane per surviving pair (box pairs and hull
+//      pairs in the same rounds): penetrating box pairs -> q1 with their axis code, hull pairs whose boxes
+//      overlap -> the GJK/EPA list in the workspace header;
+//   4. contact points, whole tile per penetrating box pair.
 template <unsigned LPE> __device__ int collide_box_env(const Tile<LPE>& t, BoxS* S, float* w, const DevTables& T, int* ncon_out) {
   const int lane = t.thread_rank();
+  const unsigned lt = (1u << lane) - 1u;
   float* con = w + W_CON;
-  // world OBB centres
-  for (int g = lane; g < c_m.ngeom; g += LPE) st3(S->gcen[g], geom_center(S->f, T.geom[g]));
-  t.sync();
-  // stage 1: bounding sphere vs sphere, sphere vs oriented box (both ways); compact survivors by mode
-  int nbox = 0, nhull = 0;
-  for (int base = 0; base < c_m.npair; base += LPE) {
-    const int p = base + lane;
-    int pass = 0, mode = 0;
-    if (p < c_m.npair) {
-      const DevPair& P = T.pair[p];
-      const DevGeom& G1 = T.geom[P.g1];
-      const DevGeom& G2 = T.geom[P.g2];
-      const V3 c1 = ld3(S->gcen[P.g1]), c2 = ld3(S->gcen[P.g2]);
-      const V3 d = c2 - c1;
-      const float rr = G1.rbound + G2.rbound;
-      if (dot(d, d) <= rr * rr) {
-        Obb b1, b2;
-        load_obb(S->f, G1, c1, b1);
-        load_obb(S->f, G2, c2, b2);
-        if (point_obb_d2(c1, b2) <= G1.rbound * G1.rbound && point_obb_d2(c2, b1) <= G2.rbound * G2.rbound) {
-          pass = 1; mode = P.mode;
-        }
-      }
-    }
-    const unsigned mb = t.ballot(pass && mode != MODE_HULL), mh = t.ballot(pass && mode == MODE_HULL);
-    const unsigned lt = (1u << lane) - 1u;
-    if (pass) {
-      if (mode != MODE_HULL) S->qbox[nbox + __popc(mb & lt)] = (unsigned char)p;
-      else S->qhull[nhull + __popc(mh & lt)] = (unsigned char)p;
-    }
-    nbox += __popc(mb); nhull += __popc(mh);
+  for (int g = lane; g < c_m.ngeom; g += LPE) {
+    const DevGeom& G = T.geom[g];
+    const V3 c = geom_center(S->f, G);
+    const float* m = G.link >= 0 ? S->f.lmat[G.link] : G.wmat;
+    S->gbox[g] = make_float4(c.x, c.y, c.z, G.rbound);
+    S->gext[g] = make_float4(fabsf(m[0]) * G.half[0] + fabsf(m[1]) * G.half[1] + fabsf(m[2]) * G.half[2],
+                             fabsf(m[3]) * G.half[0] + fabsf(m[4]) * G.half[1] + fabsf(m[5]) * G.half[2],
+                             fabsf(m[6]) * G.half[0] + fabsf(m[7]) * G.half[1] + fabsf(m[8]) * G.half[2], 0.0f);
   }
   t.sync();
-  // stage 2a: separating-axis test, one lane per box-like pair; penetrating pairs are compacted into q1
-  int npen = 0;
-  for (int base = 0; base < nbox; base += LPE) {
+  int ncand = 0;
+  for (int base = 0; base < c_m.npair; base += LPE) {
+    const int p = base + lane;
+    bool pass = false;
+    if (p < c_m.npair) {
+      const uchar4 bp = T.bpair[p];
+      const float4 a = S->gbox[bp.x], b = S->gbox[bp.y], ea = S->gext[bp.x], eb = S->gext[bp.y];
+      const float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z, rr = a.w + b.w;
+      pass = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= rr * rr && fabsf(dx) <= ea.x + eb.x && fabsf(dy) <= ea.y + eb.y &&
+             fabsf(dz) <= ea.z + eb.z;
+    }
+    const unsigned m = t.ballot(pass);
+    if (pass) S->qc[ncand + __popc(m & lt)] = (unsigned char)p;
+    ncand += __popc(m);
+  }
+  t.sync();
+  int npen = 0, nsurv = 0, nbox = 0;
+  for (int base = 0; base < ncand; base += LPE) {
     const int k = base + lane;
-    bool hit = false;
+    bool hit = false, hull = false;
     int p = 0, code = 0;
     float sep = 0;
-    if (k < nbox) {
-      p = S->qbox[k];
-      const DevPair& P = T.pair[p];
+    if (k < ncand) {
+      p = S->qc[k];
+      const uchar4 bp = T.bpair[p];
+      hull = bp.z == MODE_HULL;
+      const float4 c1 = S->gbox[bp.x], c2 = S->gbox[bp.y];
       Obb A, B;
-      load_obb(S->f, T.geom[P.g1], ld3(S->gcen[P.g1]), A);
-      load_obb(S->f, T.geom[P.g2], ld3(S->gcen[P.g2]), B);
-      hit = box_sat<true>(A, B, code, sep);
+      load_obb(S->f, T.geom[bp.x], mk(c1.x, c1.y, c1.z), A);
+      load_obb(S->f, T.geom[bp.y], mk(c2.x, c2.y, c2.z), B);
+      hit = box_sat(A, B, hull, code, sep);
     }
-    const unsigned m = t.ballot(hit);
-    if (hit) {
-      const int slot = npen + __popc(m & ((1u << lane) - 1u));
-      if (slot < 64) {
+    const unsigned mb = t.ballot(hit && !hull), mh = t.ballot(hit && hull);
+    nbox += __popc(t.ballot(k < ncand && !hull));
+    if (hit && !hull) {
+      const int slot = npen + __popc(mb & lt);
+      if (slot < NPEN) {
         S->q1[slot] = (unsigned char)p;
         S->qcode[slot] = (unsigned char)code;
         S->qsep[slot] = sep;
       }
     }
-    npen = min(npen + __popc(m), 64);
-  }
-  t.sync();
-  // stage 2b: contact points, whole tile per penetrating pair
-  int ncon = 0;
-  for (int k = 0; k < npen; k++) {
-    const int p = S->q1[k];
-    const DevPair& P = T.pair[p];
-    Obb A, B;
-    load_obb(S->f, T.geom[P.g1], ld3(S->gcen[P.g1]), A);
-    load_obb(S->f, T.geom[P.g2], ld3(S->gcen[P.g2]), B);
-    const int nc = box_contacts(t, con, ncon, A, B, (int)S->qcode[k], S->qsep[k], P.mode == MODE_BOX_SINGLE, p);
-    ncon = min(ncon + nc, NC + 1);   // NC + 1 marks overflow
-  }
-  // stage 3: oriented-box cull of the hull pairs, one lane per pair; survivors go to the workspace header
-  int nsurv = 0;
-  for (int base = 0; base < nhull; base += LPE) {
-    const int k = base + lane;
-    bool pass = false;
-    int p = 0;
-    if (k < nhull) {
-      p = S->qhull[k];
-      const DevPair& P = T.pair[p];
-      Obb A, B;
-      load_obb(S->f, T.geom[P.g1], ld3(S->gcen[P.g1]), A);
-      load_obb(S->f, T.geom[P.g2], ld3(S->gcen[P.g2]), B);
-      int code; float sep;
-      pass = box_sat<false>(A, B, code, sep);
-    }
-    const unsigned m = t.ballot(pass);
-    if (pass) {
-      const int slot = nsurv + __popc(m & ((1u << lane) - 1u));
+    if (hit && hull) {
+      const int slot = nsurv + __popc(mh & lt);
       if (slot < NHP) reinterpret_cast<unsigned char*>(w + W_HULLP)[slot] = (unsigned char)p;
     }
-    nsurv += __popc(m);
+    npen += __popc(mb);
+    nsurv += __popc(mh);
   }
-  if (nsurv > NHP) { ncon = NC + 1; nsurv = NHP; }   // more hull pairs than the list holds: counted as a contact overflow
-  if (lane == 0) {
-    int4 hdr = make_int4(ncon, nsurv, min(nbox, 255) | (npen << 8) | (min(nhull, 255) << 16), 0);
-    *reinterpret_cast<int4*>(w + W_HDR) = hdr;
+  t.sync();
+  int ncon = 0;
+  for (int k = 0; k < min(npen, NPEN); k++) {
+    const int p = S->q1[k];
+    const uchar4 bp = T.bpair[p];
+    const float4 c1 = S->gbox[bp.x], c2 = S->gbox[bp.y];
+    Obb A, B;
+    load_obb(S->f, T.geom[bp.x], mk(c1.x, c1.y, c1.z), A);
+    load_obb(S->f, T.geom[bp.y], mk(c2.x, c2.y, c2.z), B);
+    const int nc = box_contacts(t, con, ncon, A, B, (int)S->qcode[k], S->qsep[k], bp.z == MODE_BOX_SINGLE, p);
+    ncon = min(ncon + nc, NC + 1);   // NC + 1 marks overflow
   }
+  // more penetrating box pairs / hull pairs than the lists hold: counted as a contact overflow
+  if (npen > NPEN || nsurv > NHP) { ncon = NC + 1; nsurv = min(nsurv, NHP); }
+  if (lane == 0)
+    *reinterpret_cast<int4*>(w + W_HDR) = make_int4(ncon, nsurv, min(nbox, 255) | (min(npen, 255) << 8) | (min(ncand - nbox, 255) << 16), nsurv);
   *ncon_out = ncon;
   return nsurv;
 }

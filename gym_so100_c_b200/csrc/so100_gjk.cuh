@@ -375,40 +375,53 @@ __device__ V3 deepest_feature_point(const Tile<LPE>& t, const Shape& A, const Sh
   return cB + n * (0.5f * depth);
 }
 
-// Stage B for one queued env: GJK/EPA with the whole tile per listed hull pair, in pair order (deterministic
-// contact order); contacts are appended to the workspace list after the box contacts.  Returns the final count.
-template <unsigned LPE> __device__ int collide_hull_env(const Tile<LPE>& t, HullS* S, float* w, const DevTables& T) {
+// Stage B, one queue item = one hull pair of one env: GJK/EPA with the whole tile; the result goes to the pair's
+// staging slot.  The tile that finishes an env's last pending pair merges the staged contacts into the contact list
+// in pair order (deterministic contact order, after the box contacts) and returns the final count; every other tile
+// returns -1.
+template <unsigned LPE> __device__ int collide_hull_item(const Tile<LPE>& t, HullS* S, float* w, int slot, const DevTables& T) {
   const int lane = t.thread_rank();
-  const int4 hdr = *reinterpret_cast<const int4*>(w + W_HDR);
-  int ncon = hdr.x;
-  const int nsurv = min(hdr.y, NHP);
-  const uint4 plist = *reinterpret_cast<const uint4*>(w + W_HULLP);
-  float* con = w + W_CON;
-  EpaScratch* E = reinterpret_cast<EpaScratch*>(S->epa);
-  for (int k = 0; k < nsurv; k++) {
-    const unsigned word = (k >> 2) == 0 ? plist.x : ((k >> 2) == 1 ? plist.y : ((k >> 2) == 2 ? plist.z : plist.w));
-    const int p = (int)((word >> (8 * (k & 3))) & 0xffu);
-    const DevPair& P = T.pair[p];
-    const DevGeom& G1 = T.geom[P.g1];
-    const DevGeom& G2 = T.geom[P.g2];
-    const V3 c1 = geom_center(S->f, G1), c2 = geom_center(S->f, G2);
-    Shape A, B;
-    load_shape(S->f, G1, c1, A);
-    load_shape(S->f, G2, c2, B);
-    V3 n, pos;
-    float depth;
-    if (gjk_epa(t, A, B, c1, c2, T.vert, E, n, depth, pos)) {
-      snap_normal(t, A, B, n, depth, T.vert);
-      pos = deepest_feature_point(t, A, B, n, depth, pos, T.vert);
-      if (lane == 0 && ncon < NC) put_contact(con, ncon, pos, n, -depth, p);
-      ncon = min(ncon + 1, NC + 1);
-    }
-    t.sync();
+  const int p = reinterpret_cast<const unsigned char*>(w + W_HULLP)[slot];
+  const DevPair& P = T.pair[p];
+  const DevGeom& G1 = T.geom[P.g1];
+  const DevGeom& G2 = T.geom[P.g2];
+  const V3 c1 = geom_center(S->f, G1), c2 = geom_center(S->f, G2);
+  Shape A, B;
+  load_shape(S->f, G1, c1, A);
+  load_shape(S->f, G2, c2, B);
+  V3 n = mk(0, 0, 1), pos = mk(0, 0, 0);
+  float depth = 0;
+  int pid = -1;
+  if (gjk_epa(t, A, B, c1, c2, T.vert, reinterpret_cast<EpaScratch*>(S->epa), n, depth, pos)) {
+    snap_normal(t, A, B, n, depth, T.vert);
+    pos = deepest_feature_point(t, A, B, n, depth, pos, T.vert);
+    pid = p;
   }
+  int* hdr = reinterpret_cast<int*>(w + W_HDR);
+  int last = 0;
   if (lane == 0) {
-    reinterpret_cast<int*>(w + W_HDR)[0] = ncon;
-    reinterpret_cast<int*>(w + W_HDR)[3] = nsurv;      // statistics: GJK runs
+    put_contact(w + W_HSTAGE, slot, pos, n, -depth, pid);
+    __threadfence();
+    last = atomicSub(&hdr[3], 1) == 1;
   }
+  last = t.shfl(last, 0);
+  if (!last) return -1;
+  __threadfence();
+  const int nbox = hdr[0], nsurv = min(hdr[1], NHP);
+  float4 q0 = make_float4(0, 0, 0, 0), q1 = make_float4(0, 0, 0, __int_as_float(-1));
+  if (lane < nsurv) {
+    q0 = __ldcg(reinterpret_cast<const float4*>(w + W_HSTAGE + lane * CON_WORDS));
+    q1 = __ldcg(reinterpret_cast<const float4*>(w + W_HSTAGE + lane * CON_WORDS) + 1);
+  }
+  const bool valid = lane < nsurv && __float_as_int(q1.w) >= 0;
+  const unsigned m = t.ballot(valid);
+  const int c = nbox + __popc(m & ((1u << lane) - 1u));
+  if (valid && c < NC) {
+    float4* dst = reinterpret_cast<float4*>(w + W_CON + c * CON_WORDS);
+    dst[0] = q0; dst[1] = q1;
+  }
+  const int ncon = min(nbox + __popc(m), NC + 1);
+  if (lane == 0) hdr[0] = ncon;
   return ncon;
 }
 

@@ -20,14 +20,17 @@
 
 namespace so100 {
 
-#ifndef SO100_MINB_K3L
-#define SO100_MINB_K3L 5
+#ifndef SO100_TPB_K3L
+#define SO100_TPB_K3L 32      // threads per block of the light solve kernel: one env per block, so a slow env never pins idle tiles
+#endif
+#ifndef SO100_WARPS_K3L
+#define SO100_WARPS_K3L 20    // resident warps per SM the register allocation of the light solve kernel must allow
 #endif
 
 // K1: state -> frames (+ mass matrix, smooth forces, unconstrained acceleration); also re-arms the queues
 template <unsigned LPE>
 __global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, const float* action, int n, int with_dyn, Queues Q) {
-  SO100_TILE_PROLOGUE(LPE, KinS);
+  SO100_TILE_PROLOGUE(LPE, 128, KinS);
   if (blockIdx.x == 0 && threadIdx.x < Q_WORDS) Q.ctl[threadIdx.x] = 0;
   const int env = blockIdx.x * EPB + t.meta_group_rank();
   if (env >= n) return;
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, 
 
 // K2a: frames -> box contacts + surviving hull pairs; classifies the env
 template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_box(float* work, int n, DevTables T, Queues Q) {
-  SO100_TILE_PROLOGUE(LPE, BoxS);
+  SO100_TILE_PROLOGUE(LPE, 128, BoxS);
   const int env = blockIdx.x * EPB + t.meta_group_rank();
   if (env >= n) return;
   float* w = work + (size_t)env * WORK_WORDS;
@@ -68,26 +71,30 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_box
   t.sync();
   int ncon;
   const int nsurv = collide_box_env(t, S, w, T, &ncon);
-  if (lane == 0) {
-    if (nsurv > 0) Q.hull[atomicAdd(&Q.ctl[Q_HULL_COUNT], 1)] = env;
-    else if (ncon > NCL) Q.heavy[atomicAdd(&Q.ctl[Q_HEAVY_COUNT], 1)] = env;
+  if (nsurv > 0) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&Q.ctl[Q_HULL_COUNT], nsurv);
+    base = t.shfl(base, 0);
+    if (lane < nsurv) Q.hull[base + lane] = env * NHP + lane;
+  } else if (lane == 0 && ncon > NCL) {
+    Q.heavy[atomicAdd(&Q.ctl[Q_HEAVY_COUNT], 1)] = env;
   }
 }
 
-// K2b: persistent tiles drain the hull queue
+// K2b: persistent tiles drain the hull-pair queue
 template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_hull(float* work, DevTables T, Queues Q) {
-  SO100_TILE_PROLOGUE(LPE, HullS);
+  SO100_TILE_PROLOGUE(LPE, 128, HullS);
   const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_HULL_COUNT]);
   for (;;) {
     int i = 0;
     if (lane == 0) i = atomicAdd(&Q.ctl[Q_HULL_NEXT], 1);
     i = t.shfl(i, 0);
     if (i >= count) break;
-    const int env = Q.hull[i];
+    const int item = Q.hull[i], env = item / NHP;
     float* w = work + (size_t)env * WORK_WORDS;
     copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
     t.sync();
-    const int ncon = collide_hull_env(t, S, w, T);
+    const int ncon = collide_hull_item(t, S, w, item % NHP, T);
     if (lane == 0 && ncon > NCL) Q.heavy[atomicAdd(&Q.ctl[Q_HEAVY_COUNT], 1)] = env;
     t.sync();
   }
@@ -127,8 +134,8 @@ __device__ void solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w,
 
 // K3l: regular grid, one tile per env; envs with more than NCL contacts are left to K3h
 template <unsigned LPE>
-__global__ void __launch_bounds__(128, SO100_MINB_K3L) phase_solve_light(float* state, const float* work, int n, DevTables T, SolveOut O) {
-  SO100_TILE_PROLOGUE(LPE, SolS<NCL>);
+__global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TPB_K3L) phase_solve_light(float* state, const float* work, int n, DevTables T, SolveOut O) {
+  SO100_TILE_PROLOGUE(LPE, SO100_TPB_K3L, SolS<NCL>);
   const int env = blockIdx.x * EPB + t.meta_group_rank();
   if (env >= n) return;
   const float* w = work + (size_t)env * WORK_WORDS;
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(128, SO100_MINB_K3L) phase_solve_light(float* 
 // K3h: persistent tiles drain the heavy queue
 template <unsigned LPE>
 __global__ void __launch_bounds__(128) phase_solve_heavy(float* state, const float* work, DevTables T, Queues Q, SolveOut O) {
-  SO100_TILE_PROLOGUE(LPE, SolS<NC>);
+  SO100_TILE_PROLOGUE(LPE, 128, SolS<NC>);
   const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_HEAVY_COUNT]);
   for (;;) {
     int i = 0;
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(128) phase_solve_heavy(float* state, const flo
 
 // K4: task layer on the post-step state
 template <unsigned LPE> __global__ void __launch_bounds__(128) phase_task(StepArgs A, const float* work, DevTables T) {
-  SO100_TILE_PROLOGUE(LPE, TaskS);
+  SO100_TILE_PROLOGUE(LPE, 128, TaskS);
   const int env = blockIdx.x * EPB + t.meta_group_rank();
   if (env >= A.n) return;
   const float* w = work + (size_t)env * WORK_WORDS;
@@ -173,7 +180,7 @@ template <unsigned LPE>
 __global__ void __launch_bounds__(128)
 reset_kernel(float* state, const uint8_t* mask, const float* box_pose, float* obs, float* achieved, float* desired, int n,
              int task, uint32_t seed_lo, uint32_t seed_hi, long long env_offset) {
-  SO100_TILE_PROLOGUE(LPE, TaskS);
+  SO100_TILE_PROLOGUE(LPE, 128, TaskS);
   const int env = blockIdx.x * EPB + t.meta_group_rank();
   if (env >= n) return;
   float* rec = state + (size_t)env * STATE_WORDS;

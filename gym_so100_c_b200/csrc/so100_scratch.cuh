@@ -20,6 +20,7 @@ struct DevTables {
   const DevGeom* geom;
   const DevPair* pair;
   const float4* vert;
+  const uchar4* bpair;   // broad-phase view of the pair table: (g1, g2, mode, condim)
 };
 
 template <unsigned LPE> using Tile = cg::thread_block_tile<LPE>;
@@ -33,11 +34,12 @@ constexpr int W_FRAMES = 0;        // lpos[7][3] lmat[7][9] axis[6][3] (+2 pad)
 constexpr int W_FRAMES_N = 104;
 constexpr int W_DYN = 104;         // Marm[21] qfs[12] qas[12] (+3 pad)
 constexpr int W_DYN_N = 48;
-constexpr int W_HDR = 152;         // ncon, nhullpairs, stats (nbox | npen << 8 | nhull << 16), spare
+constexpr int W_HDR = 152;         // ncon, nhullpairs, stats (nbox | npen << 8 | nhull << 16), hull pairs still pending
 constexpr int W_HULLP = 156;       // NHP pair ids, one byte each
 constexpr int W_CON = 160;         // contact c: pos[3] nrm[3] dist pair
 constexpr int CON_WORDS = 8;
-constexpr int WORK_WORDS = W_CON + CON_WORDS * NC;   // 352 words = 1408 B = 44 sectors
+constexpr int W_HSTAGE = W_CON + CON_WORDS * NC;     // GJK/EPA results by hull-pair slot (pair = -1: no contact), merged in pair order
+constexpr int WORK_WORDS = W_HSTAGE + CON_WORDS * NHP;   // 480 words = 1920 B = 60 sectors (the staging area is touched by hull envs only)
 static_assert(WORK_WORDS % 8 == 0, "workspace records must stay 32-byte aligned");
 static_assert(NHP <= 16, "hull pair list is 4 words");
 
@@ -46,7 +48,7 @@ enum { Q_HULL_COUNT = 0, Q_HULL_NEXT = 1, Q_HEAVY_COUNT = 2, Q_HEAVY_NEXT = 3, Q
 
 struct Queues {
   int* ctl;      // [Q_WORDS]
-  int* hull;     // [N] envs with at least one hull pair for GJK/EPA this substep
+  int* hull;     // [N * NHP] hull pairs for GJK/EPA this substep, one item = env * NHP + slot
   int* heavy;    // [N] envs with more than NCL contacts this substep
 };
 
@@ -76,12 +78,14 @@ struct __align__(16) KinS {
 };
 
 // K2a: broad phase + box-like pairs
+constexpr int NPEN = 32;           // penetrating box pairs per env that reach contact generation
 struct __align__(16) BoxS {
   FrameBlock f;
-  float gcen[NGEOM][3];            // world OBB centres of the collidable geoms
-  float gpad;
-  unsigned char qbox[NPAIR_MAX], qhull[NPAIR_MAX], q1[64], qcode[64];
-  float qsep[64];
+  float4 gbox[NGEOM];              // world OBB centre + bounding radius of the collidable geoms
+  float4 gext[NGEOM];              // world AABB half extents
+  unsigned char qc[NPAIR_MAX];     // broad-phase survivors (pair ids)
+  unsigned char q1[NPEN], qcode[NPEN];
+  float qsep[NPEN];
 };
 
 // K2b: GJK / EPA for hull pairs
@@ -154,10 +158,10 @@ template <unsigned LPE, int NW> __device__ __forceinline__ void copy_vec(const T
   }
 }
 
-// tile and env bookkeeping shared by all phase kernels (blockDim.x = 128)
-#define SO100_TILE_PROLOGUE(LPE_, STYPE_)                                      \
+// tile and env bookkeeping shared by all phase kernels (blockDim.x = TPB_)
+#define SO100_TILE_PROLOGUE(LPE_, TPB_, STYPE_)                                \
   extern __shared__ __align__(16) unsigned char smem_raw[];                    \
-  constexpr int EPB = 128 / LPE_;                                              \
+  constexpr int EPB = TPB_ / LPE_;                                             \
   cg::thread_block blk = cg::this_thread_block();                              \
   Tile<LPE_> t = cg::tiled_partition<LPE_>(blk);                               \
   STYPE_* S = reinterpret_cast<STYPE_*>(smem_raw) + t.meta_group_rank();       \

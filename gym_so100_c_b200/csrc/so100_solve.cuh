@@ -18,7 +18,10 @@
 namespace so100 {
 
 constexpr int S_DIAG = 49;         // per-env diagnostic counters inside the state record (uint32 words 49..56)
-constexpr int NEWTON_MAXIT = 50;   // MuJoCo: 100; warm-started solves need 1-3
+#ifndef SO100_NEWTON_MAXIT
+#define SO100_NEWTON_MAXIT 50
+#endif
+constexpr int NEWTON_MAXIT = SO100_NEWTON_MAXIT;   // MuJoCo: 100; warm-started solves need 1-3
 constexpr int LS_MAXIT = 10;
 #ifndef SO100_GTOL
 #define SO100_GTOL 2e-6f     // gradient tolerance relative to |qfrc_smooth| + |J^T f|

@@ -36,7 +36,7 @@ def main():
     st1 = sim.debug_read(0).view(torch.int32)[:, S_DIAG:S_DIAG + 8].cpu().numpy().astype(np.int64)
     w = sim.debug_read(1).view(torch.int32).cpu().numpy()
     words = w.shape[1]
-    stat = np.stack([w[:, 154] & 255, (w[:, 154] >> 8) & 255, (w[:, 154] >> 16) & 255, w[:, 155]], axis=1)
+    stat = np.stack([w[:, 154] & 255, (w[:, 154] >> 8) & 255, (w[:, 154] >> 16) & 255, w[:, 153]], axis=1)
     ncon = w[:, 152]
     d = st1 - st0
     it = d[:, 5] / np.maximum(d[:, 6], 1)
@@ -47,6 +47,14 @@ def main():
     hist("GJK runs", stat[:, 3], [0, 1, 2, 3, 5, 9])
     hist("newton it/solve", it, [0, 1, 1.05, 1.5, 2, 3, 5, 10])
     hist("contacts/solve", d[:, 7] / np.maximum(d[:, 6], 1), [0, 0.5, 1.5, 2.5, 4.5, 8.5, 16.5])
+    # per-solve Newton iterations over 10 single substeps
+    its = []
+    for _ in range(10):
+        a = sim.debug_read(0).view(torch.int32)[:, S_DIAG + 5].clone()
+        sim.substeps(1)
+        its.append((sim.debug_read(0).view(torch.int32)[:, S_DIAG + 5] - a).cpu().numpy())
+    its = np.concatenate(its)
+    hist("newton it (solve)", its, [0, 1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 50])
     print("diag", sim.diagnostics())
 
 
