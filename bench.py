@@ -39,7 +39,8 @@ METRIC = "env-steps/sec (bin-a-cube)"
 #   task          reads state64 + frames102 + contacts9, writes state64 + obs15 + final_obs15 + goals6 + reward + flags
 PHASE_ALG_BYTES = {"kin_dyn": (31 + 147) * 4, "collide_box": (102 + 12) * 4, "collide_hull": (110 + 9) * 4,
                    "solve_light": (199 + 47) * 4, "solve_heavy": (199 + 47) * 4, "task": (175 + 103) * 4}
-LAUNCHES_PER_STEP = 10 * 5 + 3 + 1    # 10 x (kin_dyn, collide_box, collide_hull, solve_light, solve_heavy) + 3 + task
+# kernel launches per step: per env group 10 x (kin_dyn, collide_box, collide_hull, solve_light, solve_heavy) + 3 + task,
+# replayed as ONE CUDA graph; the count comes from the library (so100_launches_per_step)
 
 
 def measured_peaks():
@@ -169,7 +170,7 @@ def run_gpu(args):
     for s in range(K):
         flush.fill_(float(s))                       # evict L2 between timed iterations (not timed)
         ev[s][0].record()
-        sim.step(acts[W + s], autoreset=True)       # one C-ABI call = LAUNCHES_PER_STEP kernel launches
+        sim.step(acts[W + s], autoreset=True)       # one C-ABI call = one CUDA-graph launch of the step's kernels
         ev[s][1].record()
     torch.cuda.synchronize()
     parallel.barrier()
@@ -180,7 +181,9 @@ def run_gpu(args):
     kernel_ms = float(np.mean(ms))
     diag = parallel.all_reduce_stats(sim.diagnostics(), device=dev)
 
-    # ---- per-kernel device time (CUDA events on the launching stream, inside the library) for the roofline
+    # ---- per-kernel device time (CUDA events on the launching stream, inside the library) for the roofline.
+    # In timing mode the library runs all envs as one group on one stream without graph replay, so that the kernels of
+    # different env groups do not overlap and each duration is that kernel alone over the whole batch.
     sim.phase_timing(True)
     for s in range(min(K, 10)):
         sim.step(acts[W + s], autoreset=True)
@@ -231,7 +234,8 @@ def run_gpu(args):
             "config": {"workload": "BASELINE config 3: full bin-a-cube (gripper/cube/table/bin contacts), random actions "
                                    "U(-1,1), same-step auto-reset",
                        "envs_per_gpu": n, "envs_total": n_total, "substeps_per_step": 10, "l2": "flushed between timed steps "
-                       "(256 MiB write, untimed)", "parallelism": f"env-shard x{world}, no data-path collective"},
+                       "(256 MiB write, untimed)", "parallelism": f"env-shard x{world}, no data-path collective",
+                       "launches_per_step": sim.launches_per_step(), "launch": "one CUDA graph per step; env groups on parallel streams"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": f"phase_{dom}",
                          "kernel_ms_per_launch": dom_ms, "algorithmic_bytes_per_env_per_launch": PHASE_ALG_BYTES[dom],
@@ -246,7 +250,7 @@ def run_gpu(args):
                              "sample": f"{cpu_n} envs x {cpu_steps} steps of the same workload, fp64 C restatement (oracle/), OpenMP over envs"},
             "e2e": {"value": n_total * Ke / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "steps": Ke},
-            "gpu_launches": K * LAUNCHES_PER_STEP,
+            "gpu_launches": K * sim.launches_per_step(),
             "clocks": clocks,
             "physics_substeps_per_s": value * 10,
             "wall_s_timed_region": t_wall,

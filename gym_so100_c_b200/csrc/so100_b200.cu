@@ -44,6 +44,7 @@ struct EnvGroup {
   int off = 0, n = 0;
   cudaStream_t st = nullptr, side = nullptr;            // st == nullptr: the caller's stream
   cudaEvent_t fork = nullptr, join = nullptr, done = nullptr;
+  cudaEvent_t t_done = nullptr;                         // timing-enabled twin of `done` (so100_group_times)
   int* ctl = nullptr;                                   // this group's queue control words
 };
 
@@ -69,7 +70,8 @@ struct so100_ctx {
   bool use_graph = true;
   EnvGroup whole;             // all envs on the caller's stream (small batches, forward / substeps, timing mode)
   std::vector<EnvGroup> groups;
-  cudaEvent_t ev_start = nullptr;
+  cudaEvent_t ev_start = nullptr, t_start = nullptr;
+  bool group_times = false, capturing = false;   // SO100_GROUP_TIMES=1: per-group completion times of the last step
   int sm_count = 148;
   bool timing = false;        // so100_phase_timing: CUDA-event pairs around every phase-kernel launch
   std::vector<std::pair<cudaEvent_t, int>> events;   // (event, kernel class) begin markers, class -1 = end marker
@@ -380,6 +382,7 @@ static int make_group(so100_ctx* h, EnvGroup& G, int off, int n, int index, bool
   CUDA_OK(cudaEventCreateWithFlags(&G.fork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.join, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreate(&G.t_done));
   return SO100_OK;
 }
 static void free_group(EnvGroup& G) {
@@ -388,6 +391,7 @@ static void free_group(EnvGroup& G) {
   if (G.fork) cudaEventDestroy(G.fork);
   if (G.join) cudaEventDestroy(G.join);
   if (G.done) cudaEventDestroy(G.done);
+  if (G.t_done) cudaEventDestroy(G.t_done);
 }
 
 // Runs `body(group, stream)` for every env group: on the groups' own streams, forked from and joined back into `st`,
@@ -395,9 +399,11 @@ static void free_group(EnvGroup& G) {
 template <class F> static void for_each_group(so100_ctx* h, cudaStream_t st, bool allow_groups, F body) {
   if (!allow_groups || h->timing || h->groups.size() < 2) { body(h->whole, st); return; }
   cudaEventRecord(h->ev_start, st);
+  if (h->group_times) cudaEventRecordWithFlags(h->t_start, st, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
   for (EnvGroup& G : h->groups) {
     cudaStreamWaitEvent(G.st, h->ev_start, 0);
     body(G, G.st);
+    if (h->group_times) cudaEventRecordWithFlags(G.t_done, G.st, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
     cudaEventRecord(G.done, G.st);
     cudaStreamWaitEvent(st, G.done, 0);
   }
@@ -443,6 +449,8 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   CUDA_OK(cudaMalloc(&h->qmem, (so100_ctx::CTL_WORDS + (1 + NHP) * (size_t)num_envs) * sizeof(int)));
   CUDA_OK(cudaMemset(h->qmem, 0, (so100_ctx::CTL_WORDS + (1 + NHP) * (size_t)num_envs) * sizeof(int)));
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreate(&h->t_start));
+  if (const char* e = getenv("SO100_GROUP_TIMES")) h->group_times = atoi(e) != 0;
   CUDA_OK(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
   CUDA_OK(cudaMalloc(&h->act_stage, (size_t)num_envs * 6 * sizeof(float)));
   if (const char* e = getenv("SO100_GRAPH")) h->use_graph = atoi(e) != 0;
@@ -498,6 +506,12 @@ int so100_destroy(so100_handle h) {
 }
 
 int so100_num_envs(so100_handle h) { return h ? h->n : SO100_ERR_ARG; }
+
+int so100_launches_per_step(so100_handle h) {
+  if (!h) return SO100_ERR_ARG;
+  const int per_group = h->nsub * 5 + 3 + 1;   // nsub x (K1, K2a, K2b, K3l, K3h) + trailing (K1, K2a, K2b) + K4
+  return per_group * (int)std::max<size_t>(h->groups.size(), 1);
+}
 
 int so100_reset(so100_handle h, const uint8_t* mask, const float* box_pose, float* obs, float* achieved, float* desired,
                 void* stream) {
@@ -562,7 +576,9 @@ int so100_step(so100_handle h, const float* action, int autoreset, float* obs, f
   if (!exec) {
     cudaGraph_t graph = nullptr;
     CUDA_OK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal));
+    h->capturing = true;
     enqueue_step(h, A, h->cap);
+    h->capturing = false;
     CUDA_OK(cudaStreamEndCapture(h->cap, &graph));
     CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
     cudaGraphDestroy(graph);
@@ -661,6 +677,19 @@ int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom,
   export_forward_kernel<<<(threads + 255) / 256, 256, 0, st>>>(h->work, h->n, ncon, con_geom, con_data, sites, h->tables());
   launch_solve_stage(h, h->whole, st, SolveOut{qacc, con_data, 1});
   CUDA_OK(cudaGetLastError());
+  return SO100_OK;
+}
+
+int so100_group_times(so100_handle h, float* ms, int32_t* ngroups, void* stream) {
+  if (!h || !ms || !ngroups) return fail(SO100_ERR_ARG, "so100_group_times: bad argument");
+  *ngroups = 0;
+  if (!h->group_times || h->groups.size() < 2) return SO100_OK;
+  CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  for (EnvGroup& G : h->groups) {
+    float e = 0;
+    if (cudaEventElapsedTime(&e, h->t_start, G.t_done) != cudaSuccess) { cudaGetLastError(); e = -1.0f; }
+    ms[(*ngroups)++] = e;
+  }
   return SO100_OK;
 }
 

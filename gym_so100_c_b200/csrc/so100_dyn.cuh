@@ -100,7 +100,8 @@ template <unsigned LPE> __device__ void mass_matrix(const Tile<LPE>& t, KinS* S)
     float s = (i == j) ? c_m.armature[i] : 0.0f;
     for (int l = i; l < NL; l++)
       s += c_m.link_mass[l] * dot(ld3(S->U[tri(l, i)]), ld3(S->U[tri(l, j)])) + dot(aj, ld3(S->Y[tri(l, i)]));
-    S->d.Marm[e] = s;
+    S->d.Mfull[i][j] = s;
+    S->d.Mfull[j][i] = s;
   }
   t.sync();
 }
@@ -155,11 +156,13 @@ template <unsigned LPE> __device__ void smooth_forces(const Tile<LPE>& t, KinS* 
   t.sync();
 }
 
-// In-register Cholesky solve of a packed 6x6 SPD block: x = sign * A^-1 b
-__device__ __forceinline__ void chol6_solve(const float* A21, const float* b6, float sign, float* x) {
+// In-register Cholesky solve of a 6x6 SPD block (FULL: row-major 6x6, else packed lower triangle): x = sign * A^-1 b
+template <bool FULL> __device__ __forceinline__ void chol6_solve(const float* A, const float* b6, float sign, float* x) {
   float L[21];
 #pragma unroll
-  for (int e = 0; e < 21; e++) L[e] = A21[e];
+  for (int i = 0; i < NL; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) L[tri(i, j)] = FULL ? A[i * NL + j] : A[tri(i, j)];
 #pragma unroll
   for (int i = 0; i < NL; i++) x[i] = sign * b6[i];
 #pragma unroll
@@ -198,7 +201,7 @@ template <unsigned LPE> __device__ void smooth_acc(const Tile<LPE>& t, KinS* S) 
   const int lane = t.thread_rank();
   if (lane == 0) {
     float x[NL];
-    chol6_solve(S->d.Marm, S->d.qfs, 1.0f, x);
+    chol6_solve<true>(&S->d.Mfull[0][0], S->d.qfs, 1.0f, x);
 #pragma unroll
     for (int i = 0; i < NL; i++) S->d.qas[i] = x[i];
   } else if (lane >= NL && lane < NV) {

@@ -32,15 +32,15 @@ constexpr int NHP = 16;            // hull pairs per env that may reach GJK/EPA 
 // 16-byte aligned sections so that tiles move them with 128-bit loads.
 constexpr int W_FRAMES = 0;        // lpos[7][3] lmat[7][9] axis[6][3] (+2 pad)
 constexpr int W_FRAMES_N = 104;
-constexpr int W_DYN = 104;         // Marm[21] qfs[12] qas[12] (+3 pad)
-constexpr int W_DYN_N = 48;
-constexpr int W_HDR = 152;         // ncon, nhullpairs, stats (nbox | npen << 8 | nhull << 16), hull pairs still pending
-constexpr int W_HULLP = 156;       // NHP pair ids, one byte each
-constexpr int W_CON = 160;         // contact c: pos[3] nrm[3] dist pair
+constexpr int W_DYN = 104;         // Mfull[6][6] qfs[12] qas[12]
+constexpr int W_DYN_N = 60;
+constexpr int W_HDR = 164;         // ncon, nhullpairs, stats (nbox | npen << 8 | nhull << 16), hull pairs still pending
+constexpr int W_HULLP = 168;       // NHP pair ids, one byte each
+constexpr int W_CON = 172;         // contact c: pos[3] nrm[3] dist pair
 constexpr int CON_WORDS = 8;
 constexpr int W_HSTAGE = W_CON + CON_WORDS * NC;     // GJK/EPA results by hull-pair slot (pair = -1: no contact), merged in pair order
-constexpr int WORK_WORDS = W_HSTAGE + CON_WORDS * NHP;   // 480 words = 1920 B = 60 sectors (the staging area is touched by hull envs only)
-static_assert(WORK_WORDS % 8 == 0, "workspace records must stay 32-byte aligned");
+constexpr int WORK_WORDS = W_HSTAGE + CON_WORDS * NHP + 4;   // 496 words = 1984 B = 62 sectors (the staging area is touched by hull envs only)
+static_assert(WORK_WORDS % 8 == 0 && W_HDR % 4 == 0 && W_CON % 4 == 0, "workspace records stay 32-byte aligned, sections 16-byte aligned");
 static_assert(NHP <= 16, "hull pair list is 4 words");
 
 // queue control words (device ints)
@@ -62,10 +62,9 @@ struct FrameBlock {                // image of W_FRAMES
 static_assert(sizeof(FrameBlock) == W_FRAMES_N * 4, "frame block layout");
 
 struct DynBlock {                  // image of W_DYN
-  float Marm[21];                  // arm mass matrix, packed lower triangle
+  float Mfull[NL][NL];             // arm mass matrix (symmetric, both triangles stored: row d feeds M a without index math)
   float qfs[NV];                   // qfrc_smooth
   float qas[NV];                   // unconstrained acceleration M^-1 qfrc_smooth
-  float dpad[3];
 };
 static_assert(sizeof(DynBlock) == W_DYN_N * 4, "dyn block layout");
 

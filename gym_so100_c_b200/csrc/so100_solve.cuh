@@ -75,7 +75,7 @@ template <class ES> __device__ __forceinline__ float mul_M(const ES* S, const fl
   if (d < NL) {
     float s = 0;
 #pragma unroll
-    for (int j = 0; j < NL; j++) s = fmaf(S->d.Marm[d >= j ? tri(d, j) : tri(j, d)], a[j], s);
+    for (int j = 0; j < NL; j++) s = fmaf(S->d.Mfull[d][j], a[j], s);
     return s;
   }
   return (d < 9 ? c_m.cube_mass : c_m.cube_I[d - 9]) * a[d];
@@ -212,35 +212,52 @@ __device__ __forceinline__ float cone_eval(bool hess, const float* x, const floa
   return 0.5f * Dm * NmT * NmT;
 }
 
-// first / second directional derivative of the cone cost along x + alpha v
-__device__ __forceinline__ void cone_ls(const float* x0, const float* v, float alpha, const float* D, float mu,
-                                        float f0, float f1, int dim, float& d1, float& d2) {
+// Line-search view of one contact: everything in the directional derivatives of the cone cost along x0 + alpha v
+// that does not depend on alpha, formed once per Newton iteration by the contact's quad leader.
+struct ConeLs {
+  float N0, Np;          // normal coordinate mu x0[0] and its slope
+  float U0[3], V[3];     // scaled tangential coordinates fr_j x0[j] and their slopes (zero beyond condim)
+  float VV;              // |V|^2
+  float A1, A2;          // bottom zone: sum D_j x0_j v_j, sum D_j v_j^2
+  float Dm, mu;
+};
+
+__device__ __forceinline__ void cone_ls_prepare(const float* x0, const float* v, const float* D, float mu, float f0, float f1, int dim,
+                                                ConeLs& q) {
   const float fr[3] = {f0, f0, f1};
-  float x[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) x[j] = fmaf(alpha, v[j], x0[j]);
-  float N = x[0] * mu, Np = v[0] * mu, TT = 0, UV = 0, VV = 0;
+  q.mu = mu;
+  q.N0 = x0[0] * mu; q.Np = v[0] * mu;
+  q.VV = 0;
+  q.A1 = D[0] * x0[0] * v[0]; q.A2 = D[0] * v[0] * v[0];
 #pragma unroll
   for (int j = 1; j < 4; j++) {
-    float f = (j < dim) ? fr[j - 1] : 0.0f;
-    float U = x[j] * f, V = v[j] * f;
-    TT = fmaf(U, U, TT); UV = fmaf(U, V, UV); VV = fmaf(V, V, VV);
+    const float f = (j < dim) ? fr[j - 1] : 0.0f, dj = (j < dim) ? D[j] : 0.0f;
+    q.U0[j - 1] = x0[j] * f; q.V[j - 1] = v[j] * f;
+    q.VV = fmaf(q.V[j - 1], q.V[j - 1], q.VV);
+    q.A1 = fmaf(dj * x0[j], v[j], q.A1); q.A2 = fmaf(dj * v[j], v[j], q.A2);
   }
-  const float Tn = sqrtf(TT);
+  q.Dm = D[0] / fmaxf(mu * mu * (1.0f + mu * mu), 1e-15f);
+}
+
+// first / second directional derivative of the cone cost at x0 + alpha v
+__device__ __forceinline__ void cone_ls(const ConeLs& q, float alpha, float& d1, float& d2) {
+  const float N = fmaf(alpha, q.Np, q.N0);
+  float TT = 0, UV = 0;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const float U = fmaf(alpha, q.V[j], q.U0[j]);
+    TT = fmaf(U, U, TT); UV = fmaf(U, q.V[j], UV);
+  }
+  const float Tn = sqrtf(TT), mu = q.mu;
   if (N >= mu * Tn || (Tn <= 0.0f && N >= 0.0f)) return;
   if (mu * N + Tn <= 0.0f || (Tn <= 0.0f && N < 0.0f)) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      float dj = (j < dim) ? D[j] : 0.0f;
-      d1 = fmaf(dj * x[j], v[j], d1);
-      d2 = fmaf(dj * v[j], v[j], d2);
-    }
+    d1 += fmaf(alpha, q.A2, q.A1);
+    d2 += q.A2;
     return;
   }
-  const float Dm = D[0] / fmaxf(mu * mu * (1.0f + mu * mu), 1e-15f);
-  const float Tp = UV / Tn, Tpp = (VV - Tp * Tp) / Tn, NmT = N - mu * Tn, dp = Np - mu * Tp;
-  d1 = fmaf(Dm * NmT, dp, d1);
-  d2 += Dm * (dp * dp - NmT * mu * Tpp);
+  const float Tp = UV / Tn, Tpp = (q.VV - Tp * Tp) / Tn, NmT = N - mu * Tn, dp = q.Np - mu * Tp;
+  d1 = fmaf(q.Dm * NmT, dp, d1);
+  d2 += q.Dm * (dp * dp - NmT * mu * Tpp);
 }
 
 // ------------------------------------------------------------------ Newton solver
@@ -248,7 +265,8 @@ template <unsigned LPE, int NCAP> struct SolveRegs {
   static constexpr int RPL = (NCAP * 4 + LPE - 1) / LPE;   // contact rows (and, on quad leaders, contacts) per lane
   float qfs, fr_aref, fr_R, fr_D, fr_fl;
   float lim_sgn, lim_D, lim_aref;
-  float jar[RPL][4], jv[RPL][4];
+  float jar[RPL][4];
+  ConeLs ls[RPL];
   int dim[RPL];
   float f0[RPL], f1[RPL];
 };
@@ -425,7 +443,7 @@ template <unsigned LPE, class ES> __device__ void solve(const Tile<LPE>& t, ES* 
         const int blk = e >= 21 ? 1 : 0, rr = e - 21 * blk;
         const int i = tri_row6(rr), j = rr - tri(i, 0);
         float h;
-        if (blk == 0) h = S->d.Marm[rr];
+        if (blk == 0) h = S->d.Mfull[i][j];
         else h = (i == j) ? (i < 3 ? c_m.cube_mass : c_m.cube_I[i - 3]) : 0.0f;
         const int gi = i + NL * blk, gj = j + NL * blk;
         if (i == j) h += S->hdiag[gi];
@@ -440,7 +458,7 @@ template <unsigned LPE, class ES> __device__ void solve(const Tile<LPE>& t, ES* 
       // both blocks factored + solved in registers; lower half-tile: arm, upper half-tile: cube
       const int hb = lane >= (int)(LPE / 2) ? 1 : 0;
       float x[NL];
-      chol6_solve(&S->H[21 * hb], &S->vec[NL * hb], -1.0f, x);
+      chol6_solve<false>(&S->H[21 * hb], &S->vec[NL * hb], -1.0f, x);
       t.sync();
       if (lane == 0 || lane == (int)(LPE / 2)) {
 #pragma unroll
@@ -454,7 +472,7 @@ template <unsigned LPE, class ES> __device__ void solve(const Tile<LPE>& t, ES* 
         int i, j;
         untri(e, i, j);
         float h = 0;
-        if (i < NL) h = S->d.Marm[e];
+        if (i < NL) h = S->d.Mfull[i][j];
         else if (i == j) h = (i < 9 ? c_m.cube_mass : c_m.cube_I[i - 9]);
         if (i == j) h += S->hdiag[i];
         for (int c = 0; c < ncon; c++) {
@@ -514,8 +532,10 @@ template <unsigned LPE, class ES> __device__ void solve(const Tile<LPE>& t, ES* 
         for (int d = d0; d < d1; d++) v = fmaf(S->J[row][d], S->vec[d], v);
       }
       const int qb = lane & ~3;
+      float jv[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) r.jv[s][k] = t.shfl(v, qb + k);
+      for (int k = 0; k < 4; k++) jv[k] = t.shfl(v, qb + k);
+      if ((lane & 3) == 0 && row < nrow) cone_ls_prepare(r.jar[s], jv, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], r.ls[s]);
     }
     const float a0 = S->a[lane < NV ? lane : 0];
     const float xf0 = a0 - r.fr_aref, xl0 = r.lim_sgn * a0 - r.lim_aref;
@@ -544,7 +564,7 @@ template <unsigned LPE, class ES> __device__ void solve(const Tile<LPE>& t, ES* 
 #pragma unroll
         for (int s = 0; s < Regs::RPL; s++) {
           const int c = (lane + s * LPE) >> 2;
-          if (c < ncon) cone_ls(r.jar[s], r.jv[s], alpha, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], e1, e2);
+          if (c < ncon) cone_ls(r.ls[s], alpha, e1, e2);
         }
       }
       tsum2(t, e1, e2);

@@ -93,10 +93,13 @@ class BatchedSim:
         if a.shape != (n, 6):
             raise ValueError(f"expected shape {(n, 6)}, got {a.shape}")
         if not hasattr(self, "_host"):
-            self._host = dict(obs=np.zeros((n, 15), np.float32), achieved=np.zeros((n, 3), np.float32),
-                              desired=np.zeros((n, 3), np.float32), reward=np.zeros(n, np.float32),
-                              terminated=np.zeros(n, np.uint8), truncated=np.zeros(n, np.uint8),
-                              success=np.zeros(n, np.uint8), final_obs=np.zeros((n, 15), np.float32))
+            # page-locked result buffers (numpy views of pinned torch tensors): the device -> host copies of so100_step_host
+            # then run as true async DMA instead of staged pageable copies
+            spec = dict(obs=((n, 15), torch.float32), achieved=((n, 3), torch.float32), desired=((n, 3), torch.float32),
+                        reward=((n,), torch.float32), terminated=((n,), torch.uint8), truncated=((n,), torch.uint8),
+                        success=((n,), torch.uint8), final_obs=((n, 15), torch.float32))
+            self._host_pinned = {k: torch.zeros(shape, dtype=dt).pin_memory() for k, (shape, dt) in spec.items()}
+            self._host = {k: v.numpy() for k, v in self._host_pinned.items()}
         o = self._host
         p = lambda x: x.ctypes.data_as(C.c_void_p)
         ext.check(self.lib.so100_step_host(self.h, p(a), int(autoreset), p(o["obs"]), p(o["achieved"]), p(o["desired"]),
@@ -164,6 +167,17 @@ class BatchedSim:
         ext.check(self.lib.so100_forward(self.h, _ptr(qacc), _ptr(ncon), _ptr(geom), _ptr(data), _ptr(sites), self._stream()),
                   "so100_forward")
         return dict(qacc=qacc, ncon=ncon, con_geom=geom, con_data=data, sites=sites)
+
+    def launches_per_step(self) -> int:
+        """Kernel launches (graph nodes) one `step` enqueues."""
+        return int(self.lib.so100_launches_per_step(self.h))
+
+    def group_times(self):
+        """Per-group completion times (ms) of the last step; empty unless SO100_GROUP_TIMES=1 was set at construction."""
+        ms = np.zeros(32, dtype=np.float32)
+        ng = C.c_int32(0)
+        ext.check(self.lib.so100_group_times(self.h, ms.ctypes.data_as(C.c_void_p), C.byref(ng), self._stream()), "so100_group_times")
+        return ms[:ng.value].tolist()
 
     def debug_read(self, what: int) -> torch.Tensor:
         """Raw per-env records (development aid): what=0 state record, what=1 phase workspace."""

@@ -13,9 +13,9 @@ from . import build as _build
 _lib = None
 
 SYMBOLS = [
-    "so100_create", "so100_destroy", "so100_num_envs", "so100_reset", "so100_step", "so100_step_host",
+    "so100_create", "so100_destroy", "so100_num_envs", "so100_launches_per_step", "so100_reset", "so100_step", "so100_step_host",
     "so100_compute_reward", "so100_get_state", "so100_set_state", "so100_get_aux", "so100_set_aux",
-    "so100_substeps", "so100_forward", "so100_diagnostics", "so100_phase_timing", "so100_debug_read", "so100_last_error",
+    "so100_substeps", "so100_forward", "so100_diagnostics", "so100_phase_timing", "so100_group_times", "so100_debug_read", "so100_last_error",
 ]
 
 MAX_CONTACTS = 24
@@ -46,6 +46,7 @@ def load():
     lib.so100_create.argtypes = [C.c_char_p, C.c_size_t, i32, i32, i32, u64, i64, C.POINTER(vp)]
     lib.so100_destroy.argtypes = [vp]
     lib.so100_num_envs.argtypes = [vp]
+    lib.so100_launches_per_step.argtypes = [vp]
     lib.so100_reset.argtypes = [vp] + [vp] * 5 + [vp]
     lib.so100_step.argtypes = [vp, vp, i32] + [vp] * 8 + [vp]
     lib.so100_step_host.argtypes = [vp, vp, i32] + [vp] * 8 + [vp]
@@ -58,6 +59,7 @@ def load():
     lib.so100_forward.argtypes = [vp] * 7
     lib.so100_diagnostics.argtypes = [vp, vp, vp]
     lib.so100_phase_timing.argtypes = [vp, i32, vp, vp, vp]
+    lib.so100_group_times.argtypes = [vp, vp, vp, vp]
     lib.so100_debug_read.argtypes = [vp, i32, vp, vp, vp]
     lib.so100_last_error.restype = C.c_char_p
     for name in SYMBOLS:

@@ -53,6 +53,8 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
                  uint64_t seed, int64_t env_offset, so100_handle* out);
 int so100_destroy(so100_handle h);
 int so100_num_envs(so100_handle h);
+/* Kernel launches (CUDA-graph kernel nodes) one so100_step enqueues: 54 per env group (so100_b200.cu: EnvGroup). */
+int so100_launches_per_step(so100_handle h);
 
 /* Replaces: SO100Env.reset / SO100GoalEnv.reset (env.py:148-170, 302-320) incl.
  * sample_so100_box_pose (utils.py:18-29) and initialize_episode (single_arm.py:299-309).
@@ -114,6 +116,10 @@ int so100_diagnostics(so100_handle h, int64_t* out8, void* stream);
  * [1] collision, box stage, [2] constraint solve + integration (<= 8 contacts), [3] task layer, [4] collision, GJK/EPA
  * queue, [5] constraint solve, heavy queue -- then clears the record and sets the mode. */
 int so100_phase_timing(so100_handle h, int enable, float* ms6, int32_t* launches6, void* stream);
+
+/* Development aid (SO100_GROUP_TIMES=1 in the environment at create): device time from the start of the last so100_step
+ * to the completion of each env group's pipeline.  ms: host float[32]; *ngroups receives the count (0 when disabled). */
+int so100_group_times(so100_handle h, float* ms, int32_t* ngroups, void* stream);
 
 /* Development aid: raw copy of the per-env records.  what = 0: state record, 1: phase workspace (link frames, mass
  * matrix, contact list, collision statistics).  `words_per_env` (host, nullable) receives the record length in float

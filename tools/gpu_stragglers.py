@@ -35,8 +35,8 @@ def main():
         w = sim.debug_read(1).view(torch.int32).cpu().numpy()
         qpos = sim.get_state()[0].cpu().numpy()
         for e in range(n):
-            nc = min(int(w[e, 152]), 24)
-            pairs = tuple(sorted((int(mjid[g1[w[e, 160 + 8 * c + 7]]]), int(mjid[g2[w[e, 160 + 8 * c + 7]]])) for c in range(nc)))
+            nc = min(int(w[e, 164]), 24)
+            pairs = tuple(sorted((int(mjid[g1[w[e, 172 + 8 * c + 7]]]), int(mjid[g2[w[e, 172 + 8 * c + 7]]])) for c in range(nc)))
             lim = tuple(int(x) for x in np.nonzero((qpos[e, :6] < m["dof_range"][:6, 0]) | (qpos[e, :6] > m["dof_range"][:6, 1]))[0])
             key = (pairs, lim)
             total[key] += 1

@@ -36,8 +36,8 @@ def main():
     st1 = sim.debug_read(0).view(torch.int32)[:, S_DIAG:S_DIAG + 8].cpu().numpy().astype(np.int64)
     w = sim.debug_read(1).view(torch.int32).cpu().numpy()
     words = w.shape[1]
-    stat = np.stack([w[:, 154] & 255, (w[:, 154] >> 8) & 255, (w[:, 154] >> 16) & 255, w[:, 153]], axis=1)
-    ncon = w[:, 152]
+    stat = np.stack([w[:, 166] & 255, (w[:, 166] >> 8) & 255, (w[:, 166] >> 16) & 255, w[:, 165]], axis=1)
+    ncon = w[:, 164]
     d = st1 - st0
     it = d[:, 5] / np.maximum(d[:, 6], 1)
     hist("ncon (last fwd)", ncon, [0, 1, 2, 3, 5, 9, 17, 25])
