@@ -417,7 +417,7 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
                  int64_t env_offset, so100_handle* out) {
   if (!model_blob || !out || num_envs <= 0) return fail(SO100_ERR_ARG, "so100_create: bad argument");
   if (nbytes != sizeof(so100_model)) return fail(SO100_ERR_ARG, "so100_create: model blob has the wrong size");
-  if (task != SO100_TASK_CUBE_TO_BIN && task != SO100_TASK_GOAL) return fail(SO100_ERR_ARG, "so100_create: unknown task");
+  if (task < SO100_TASK_CUBE_TO_BIN || task > SO100_TASK_TOUCH_CUBE_SPARSE) return fail(SO100_ERR_ARG, "so100_create: unknown task");
   so100_model m;
   memcpy(&m, model_blob, sizeof(m));
   if (m.magic != SO100_MODEL_MAGIC || m.version != SO100_MODEL_VERSION) return fail(SO100_ERR_ARG, "so100_create: model magic/version mismatch");
@@ -455,8 +455,9 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   CUDA_OK(cudaMalloc(&h->act_stage, (size_t)num_envs * 6 * sizeof(float)));
   if (const char* e = getenv("SO100_GRAPH")) h->use_graph = atoi(e) != 0;
   {
-    // env groups: SO100_GROUPS overrides; default one group per 2048 envs, at most 8
-    int ng = std::min(8, num_envs / 2048);
+    // env groups: SO100_GROUPS overrides; default one group per 1024 envs, at most 8 (measured on B200: 4096 envs
+    // 1.50 -> 1.73 M env-steps/s with 4 groups, 16384 envs 4.0 -> 5.0 M with 8, no gain beyond 8 at any batch size)
+    int ng = std::min(8, num_envs / 1024);
     if (const char* e = getenv("SO100_GROUPS")) ng = atoi(e);
     ng = std::max(1, std::min(ng, 32));
     rc = make_group(h, h->whole, 0, num_envs, 32, false);

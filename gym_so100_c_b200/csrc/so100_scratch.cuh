@@ -137,6 +137,12 @@ template <unsigned LPE> __device__ __forceinline__ void tsum2(const Tile<LPE>& t
   }
 }
 
+// true on every lane of the WARP when any lane's predicate holds (all tiles of the warp must call it together)
+template <unsigned LPE> __device__ __forceinline__ bool warp_any(const Tile<LPE>& t, bool p) {
+  if (LPE == 32) return t.any(p);
+  return __any_sync(0xffffffffu, p);
+}
+
 // Copy NW words (a multiple of 4, both sides 16-byte aligned) with one 128-bit load per lane and round;
 // all loads are issued before the first store so their latencies overlap.
 template <unsigned LPE, int NW> __device__ __forceinline__ void copy_vec(const Tile<LPE>& t, float* dst, const float* src) {

@@ -403,21 +403,10 @@ template <unsigned LPE, class ES> __device__ void solve(const Tile<LPE>& t, ES* 
   };
   set_a(qas_d);
   int stage = 0, it = 0;
-  bool need_eval = true, last = false, converged = false;
+  bool done = false, last = false, converged = false;
   float Ma = 0, dof_force = 0, cost = 0, cost_qas = 0;
-#pragma unroll 1
-  for (;;) {
-    if (need_eval) {
-      cost = eval_cost(t, S, r, stage != 0, Ma, dof_force);
-      t.sync();
-    }
-    need_eval = true;
-    if (stage == 0) { cost_qas = cost; stage = 1; set_a(warm_d); continue; }
-    if (stage == 1) {
-      stage = 2;
-      if (cost_qas < cost) { set_a(qas_d); continue; }
-    }
-    if (last || it >= NEWTON_MAXIT) break;
+  // one Newton iteration from the iterate / forces of the last evaluation; sets `done` when the solve is over
+  auto newton_step = [&]() {
     // ---- gradient: M a - qfrc_smooth - J^T f
     float g = 0, jtf = 0;
     if (lane < NV) {
@@ -435,7 +424,7 @@ template <unsigned LPE, class ES> __device__ void solve(const Tile<LPE>& t, ES* 
     // tolerance is 2e-6 relative to their magnitude (|qfrc_smooth| + |J^T f|), scaled like MuJoCo's.
     float gg = g * g, ss = r.qfs * r.qfs + jtf * jtf;
     tsum2(t, gg, ss);
-    if (sqrtf(gg) * c_m.inv_scale < SO100_GTOL * (1.0f + sqrtf(ss))) { converged = true; break; }
+    if (sqrtf(gg) * c_m.inv_scale < SO100_GTOL * (1.0f + sqrtf(ss))) { converged = true; done = true; return; }
     float pd;
     if (!coupled) {
       // ---- block-diagonal Hessian: entries 0..20 arm block, 21..41 cube block
@@ -578,7 +567,7 @@ template <unsigned LPE, class ES> __device__ void solve(const Tile<LPE>& t, ES* 
       if (fabsf(d1) <= 1e-4f * d10) break;
       if (d1 < 0) lo = alpha; else hi = alpha;
     }
-    if (!descent) { converged = true; break; }
+    if (!descent) { converged = true; done = true; return; }
     if (lane < NV) {
       const double na = fma((double)alpha, (double)pd, S->ad[lane]);
       S->ad[lane] = na; S->a[lane] = (float)na;
@@ -588,6 +577,25 @@ template <unsigned LPE, class ES> __device__ void solve(const Tile<LPE>& t, ES* 
     // predicted decrease 1/2 alpha |phi'(0)| below float32 resolution of the cost: stop after refreshing the forces
     // (MuJoCo's "improvement < tolerance" test, made relative because the arithmetic is float32)
     if (0.5f * alpha * d10 < SO100_ITOL * (1.0f + fabsf(cost))) last = true;
+  };
+  // Every trip = one evaluation, then (stage 2) one Newton iteration.  With two envs per warp (LPE = 16) both tiles
+  // vote at the top of every trip, so they run the trip in lock step and re-converge there; without the vote, tiles
+  // that took different branches once (e.g. the re-evaluation at the unconstrained start point) would never re-converge
+  // and the warp would execute both solves serially (ncu: 14.8 active threads per instruction).
+#pragma unroll 1
+  for (;;) {
+    if (!warp_any<LPE>(t, !done)) break;
+    if (!done) {
+      cost = eval_cost(t, S, r, stage != 0, Ma, dof_force);
+      t.sync();
+      if (stage == 0) { cost_qas = cost; stage = 1; set_a(warm_d); }
+      else if (stage == 1 && cost_qas < cost) { stage = 2; set_a(qas_d); }
+      else {
+        stage = 2;
+        if (last || it >= NEWTON_MAXIT) done = true;
+        else newton_step();
+      }
+    }
   }
   if (lane == 0 && diag) {
     diag[1] += (converged || last) ? 0u : 1u;

@@ -126,6 +126,23 @@ template <unsigned LPE> __device__ void task_env(const Tile<LPE>& t, TaskS* S, c
     if (released) reward = 4.0f;
     succ = reward == 4.0f;
     trunc = step_count >= c_m.max_episode_steps;
+  } else if (A.task >= 2) {
+    // SO100TouchCubeTask (2, single_arm.py:149-215) / SO100TouchCubeSparseTask (3, single_arm.py:246-285); the reference
+    // evaluates this in float64 on float64 sites, here float32 sites and arithmetic (reward within 1e-5)
+    const V3 d3 = so.ee - so.cube;
+    const float d = sqrtf(dot(d3, d3));
+    reward = 0.0f;
+    if (A.task == 2) {
+      if (d < 0.7f) reward = fmaxf(reward, 0.1f * (1.0f - d / 0.7f));
+      if (d < 0.5f) reward = fmaxf(reward, 0.2f * (1.0f - d / 0.5f));
+      if (d < 0.3f) reward = fmaxf(reward, 0.5f * (1.0f - d / 0.3f));
+      if (d < 0.1f) reward = fmaxf(reward, 1.0f * (1.0f - d / 0.1f));
+      if (d < 0.05f) reward = fmaxf(reward, 2.0f * (1.0f - d / 0.05f));
+      if (touch_gripper) reward += 1.0f;
+    }
+    succ = touch_gripper && d < 0.05f;
+    reward = succ ? 4.0f : reward - 0.2f;
+    trunc = step_count >= c_m.goal_max_steps;   // TimeLimit 300 (__init__.py:7,17)
   } else {
     // env.py:341-358, float32, ((dx^2 + dy^2) + dz^2)
     const float dx = __fsub_rn(so.cube.x, S->st[S_GOAL]), dy = __fsub_rn(so.cube.y, S->st[S_GOAL + 1]),

@@ -22,6 +22,8 @@ MAX_CONTACTS = 24
 NDIAG = 8
 TASK_CUBE_TO_BIN = 0
 TASK_GOAL = 1
+TASK_TOUCH_CUBE = 2
+TASK_TOUCH_CUBE_SPARSE = 3
 
 
 class So100Error(RuntimeError):

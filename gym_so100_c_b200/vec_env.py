@@ -89,19 +89,21 @@ class _VecBase:
 
 
 class SO100VecEnv(_VecBase):
-    """N copies of ``SO100Env(task="so100_cube_to_bin", obs_type="so100_state")`` under a 700-step TimeLimit."""
+    """N copies of ``SO100Env(task=..., obs_type="so100_state")`` under the TimeLimit of the registered id
+    (gym_so100/__init__.py:4-32): so100_cube_to_bin 700 steps, so100_touch_cube / so100_touch_cube_sparse 300 steps."""
 
-    _task = ext.TASK_CUBE_TO_BIN
+    TASKS = {"so100_cube_to_bin": (ext.TASK_CUBE_TO_BIN, 700), "so100_touch_cube": (ext.TASK_TOUCH_CUBE, 300),
+             "so100_touch_cube_sparse": (ext.TASK_TOUCH_CUBE_SPARSE, 300)}
 
     def __init__(self, num_envs: int, task: str = "so100_cube_to_bin", obs_type: str = "so100_state", **kw):
-        if task != "so100_cube_to_bin":
+        if task not in self.TASKS:
             raise NotImplementedError(task)           # env.py:117-118
         if obs_type != "so100_state":
             raise NotImplementedError(f"obs_type {obs_type!r}: the batched engine has no renderer (so100_state only)")
+        self._task, self.max_episode_steps = self.TASKS[task]     # __init__.py:7,17,27
         super().__init__(num_envs, **kw)
         self.task = task
         self.obs_type = obs_type
-        self.max_episode_steps = 700                  # __init__.py:27
         self.single_observation_space = Box(low=-100.0, high=100.0, shape=(15,), dtype=np.float32)   # env.py:67-73
         self.observation_space = batch_box(self.single_observation_space, self.num_envs)
 

@@ -39,7 +39,9 @@ enum so100_status {
 
 enum so100_task {
   SO100_TASK_CUBE_TO_BIN = 0,  /* SO100Env(task="so100_cube_to_bin"): staged reward, TimeLimit 700 */
-  SO100_TASK_GOAL = 1          /* SO100GoalEnv: sparse HER reward, truncation at 300 steps       */
+  SO100_TASK_GOAL = 1,         /* SO100GoalEnv: sparse HER reward, truncation at 300 steps       */
+  SO100_TASK_TOUCH_CUBE = 2,   /* SO100Env(task="so100_touch_cube"): shaped reward, TimeLimit 300 (single_arm.py:149-215) */
+  SO100_TASK_TOUCH_CUBE_SPARSE = 3 /* SO100Env(task="so100_touch_cube_sparse"): -0.2 / 4, TimeLimit 300 (single_arm.py:246-285) */
 };
 
 #define SO100_MAX_CONTACTS 24   /* per-env contact capacity; overflow is counted in diagnostics */

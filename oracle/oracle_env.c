@@ -13,7 +13,7 @@
 struct so100o {
   so100_model m;
   int n;
-  int task;            /* 0 cube_to_bin (SO100Env), 1 goal env (SO100GoalEnv) */
+  int task;            /* 0 cube_to_bin (SO100Env), 1 goal env (SO100GoalEnv), 2 touch_cube, 3 touch_cube_sparse (SO100Env) */
   uint64_t seed;
   int64_t env_offset;
   oenv* env;
@@ -94,6 +94,30 @@ static float cube_to_bin_reward(const so100o* h, const oenv* e) {
   if (inside) reward = 3.0f;
   if (released) reward = 4.0f;
   return reward;
+}
+
+/* single_arm.py:149-215 (dense = 1, SO100TouchCubeTask) and 246-285 (dense = 0, SO100TouchCubeSparseTask): float64
+ * throughout, like the reference (site_xpos is float64); success = pad contact and |ee - cube| < 0.05 -> max_reward 4 */
+static float touch_reward(const so100o* h, const oenv* e, int dense) {
+  const so100_model* m = &h->m;
+  int touch_gripper = 0;
+  for (int c = 0; c < e->ncon; c++) {
+    int g1 = e->con[c].g1, g2 = e->con[c].g2;
+    if ((g2 == m->cg_cube && ((m->pad_mask >> g1) & 1)) || (g1 == m->cg_cube && ((m->pad_mask >> g2) & 1))) touch_gripper = 1;
+  }
+  const double* ee = e->site[m->site_ee];
+  const double* cu = e->site[m->site_cube];
+  double d = sqrt((ee[0] - cu[0]) * (ee[0] - cu[0]) + (ee[1] - cu[1]) * (ee[1] - cu[1]) + (ee[2] - cu[2]) * (ee[2] - cu[2]));
+  double reward = 0.0;
+  if (dense) {
+    const double thr[5] = {0.7, 0.5, 0.3, 0.1, 0.05}, w[5] = {0.1, 0.2, 0.5, 1.0, 2.0};
+    for (int k = 0; k < 5; k++)
+      if (d < thr[k]) { double r = w[k] * (1 - d / thr[k]); if (r > reward) reward = r; }
+    if (touch_gripper) reward += 1.0;
+  }
+  if (touch_gripper && d < 0.05) return 4.0f;
+  reward -= 0.2;
+  return (float)reward;
 }
 
 /* env.py:341-358: float32 distance, threshold 0.01 */
@@ -221,6 +245,10 @@ int so100o_step(so100o* h, const float* action, int autoreset, int32_t* total_st
       r = cube_to_bin_reward(h, e);
       succ = r == 4.0f; term = succ;                       /* env.py:175 */
       trunc = e->step_count >= m->max_episode_steps;       /* TimeLimit wrapper, __init__.py:27 */
+    } else if (h->task >= 2) {
+      r = touch_reward(h, e, h->task == 2);
+      succ = r == 4.0f; term = succ;                       /* env.py:175 */
+      trunc = e->step_count >= 300;                        /* TimeLimit wrapper, __init__.py:7,17 */
     } else {
       float d = goal_distance(ag, dg);
       succ = d < (float)m->goal_threshold;
@@ -336,6 +364,26 @@ float so100o_test_reward(so100o* h, int ncon, const int32_t* geom_mjid_pairs, co
   }
   memcpy(e->site[m->site_cube], cube_site, 3 * sizeof(double));
   return cube_to_bin_reward(h, e);
+}
+
+/* the same for the touch tasks (task 2 = so100_touch_cube, 3 = so100_touch_cube_sparse) with an injected ee_site */
+float so100o_test_touch_reward(so100o* h, int task, int ncon, const int32_t* geom_mjid_pairs, const double* cube_site,
+                               const double* ee_site) {
+  oenv* e = &h->env[0];
+  const so100_model* m = &h->m;
+  e->ncon = 0;
+  for (int c = 0; c < ncon && c < MAXCON; c++) {
+    int g[2] = {-1, -1};
+    for (int s = 0; s < 2; s++)
+      for (int k = 0; k < m->ngeom; k++)
+        if (m->geom_mjid[k] == geom_mjid_pairs[2 * c + s]) g[s] = k;
+    if (g[0] < 0 || g[1] < 0) return -1000.0f;
+    e->con[e->ncon].g1 = g[0]; e->con[e->ncon].g2 = g[1];
+    e->ncon++;
+  }
+  memcpy(e->site[m->site_cube], cube_site, 3 * sizeof(double));
+  memcpy(e->site[m->site_ee], ee_site, 3 * sizeof(double));
+  return touch_reward(h, e, task == 2);
 }
 
 /* batched HER reward, env.py:346-349 */

@@ -153,6 +153,16 @@ def test_reward(oracle: Oracle, contacts, cube_site) -> float:
     return float(l.so100o_test_reward(C.c_void_p(oracle.h), len(pairs), _p(pairs), _p(site)))
 
 
+def test_touch_reward(oracle: Oracle, task: int, contacts, cube_site, ee_site) -> float:
+    """single_arm.py:149-215 (task 2) / 246-285 (task 3) on a synthetic contact list and cube_site / ee_site positions."""
+    l = lib()
+    l.so100o_test_touch_reward.restype = C.c_float
+    pairs = np.ascontiguousarray(np.asarray(contacts, dtype=np.int32).reshape(-1, 2))
+    cs = np.ascontiguousarray(cube_site, dtype=np.float64)
+    es = np.ascontiguousarray(ee_site, dtype=np.float64)
+    return float(l.so100o_test_touch_reward(C.c_void_p(oracle.h), int(task), len(pairs), _p(pairs), _p(cs), _p(es)))
+
+
 def test_box_pair(cA, RA, hA, cB, RB, hB):
     """(SAT normal, SAT depth, EPA normal, EPA depth, n_sat_points, epa_hit) for two boxes (row-major R)."""
     l = lib()
@@ -163,6 +173,7 @@ def test_box_pair(cA, RA, hA, cB, RB, hB):
 
 
 test_reward.__test__ = False
+test_touch_reward.__test__ = False
 test_box_pair.__test__ = False
 
 

@@ -11,6 +11,7 @@ What is pinned (reference file:line):
   * utils.sample_so100_box_pose(seed)                        gym_so100/utils.py:18-29
   * SO100GoalEnv.compute_reward / _is_success                gym_so100/env.py:341-358
   * SO100CubeToBinTask.get_reward on synthetic physics       gym_so100/tasks/single_arm.py:322-380
+  * SO100TouchCubeTask / SO100TouchCubeSparseTask.get_reward  gym_so100/tasks/single_arm.py:149-215, 246-285
 MuJoCo / dm_control / gymnasium are not installed, so they are replaced by inert stub modules that
 only let the reference modules import; the functions above never touch them.
 """
@@ -102,7 +103,7 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):
         from gym_so100 import constants, utils
         from gym_so100.env import SO100GoalEnv
-        from gym_so100.tasks.single_arm import SO100CubeToBinTask
+        from gym_so100.tasks.single_arm import SO100CubeToBinTask, SO100TouchCubeSparseTask, SO100TouchCubeTask
 
     out = {"numpy": np.__version__}
 
@@ -153,11 +154,29 @@ def main():
             cases.append(dict(site=sname, cube_site=list(site), contacts=[list(c) for c in cons], reward=float(r)))
     out["cube_to_bin_reward"] = cases
 
+    # single_arm.py:149-215 (shaped) and 246-285 (sparse): distance tiers x pad contact
+    tcases = []
+    cube = np.array([-0.2, 0.45, 0.03])
+    direction = np.array([0.6, -0.48, 0.64])
+    dists = [0.9, 0.7, 0.6999, 0.55, 0.5, 0.42, 0.3, 0.2999, 0.17, 0.1, 0.0999, 0.07, 0.05, 0.0499, 0.031, 0.004, 0.0]
+    tsets = {"none": [], "table": [(32, 0)], "pad": [(20, 32)], "pad_rev": [(32, 30)], "jaw_hull": [(32, 18)],
+             "pad+table": [(23, 32), (32, 0)]}
+    for tname, cls in (("so100_touch_cube", SO100TouchCubeTask), ("so100_touch_cube_sparse", SO100TouchCubeSparseTask)):
+        ttask = cls()
+        for d in dists:
+            ee = cube + direction * d
+            for cname, cons in tsets.items():
+                with contextlib.redirect_stdout(io.StringIO()):
+                    r = ttask.get_reward(FakePhysics(cons, tuple(cube), ee_site=tuple(ee)))
+                tcases.append(dict(task=tname, dist=d, cube_site=cube.tolist(), ee_site=ee.tolist(),
+                                   contacts=[list(c) for c in cons], reward=float(r)))
+    out["touch_reward"] = tcases
+
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_golden.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
     print(f"wrote {path}: {len(out['unnormalize_so100']['action'])} actions, {len(out['box_pose'])} poses, "
-          f"{len(ag)} goals, {len(cases)} reward cases (numpy {np.__version__})")
+          f"{len(ag)} goals, {len(cases)} + {len(tcases)} reward cases (numpy {np.__version__})")
 
 
 if __name__ == "__main__":

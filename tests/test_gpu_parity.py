@@ -156,6 +156,51 @@ def test_reward_levels_on_injected_states(model_blob):
     sim.close()
 
 
+@pytest.mark.parametrize("task", [2, 3])
+def test_touch_tasks_reward_parity(model_blob, task):
+    """SO100TouchCube (2) / SO100TouchCubeSparse (3): shaped distance tiers + pad-contact bonus, success = pad contact and
+    |ee - cube| < 0.05 (single_arm.py:149-215, 246-285), TimeLimit 300 (__init__.py:7,17).  States: the grasp scenario
+    (pads on the cube), arm-hull contacts and free space, so that every reward branch is visited; the reward must agree
+    with the float64 oracle within 1e-5 and the flags exactly."""
+    import torch
+    n = 64
+    rewards = []
+    for name in ("grasp_hull_contacts", "free_space", "cube_on_table"):
+        qpos, qvel, ctrl = scenarios.ALL[name](n)
+        sim, orc = make_pair(model_blob, n, task=task, seed=4)
+        orc.reset(); sim.reset()
+        inject(sim, orc, qpos, np.zeros_like(qvel), ctrl)
+        from oracle.so100_oracle import unnormalize  # noqa: F401
+        # hold the injected arm pose: action = normalised ctrl
+        m = orc_model_ranges(model_blob)
+        act = np.clip(2 * (ctrl - m[0]) / (m[1] - m[0]) - 1, -1, 1).astype(np.float32)
+        steps = torch.full((n,), 298, dtype=torch.int32)
+        sim.set_aux(step_count=steps); orc.set_counters(step_count=steps.numpy())
+        for k in range(2):
+            out_o = orc.step(act, autoreset=False)
+            obs, rew, term, trunc, succ = sim.step(torch.tensor(act), autoreset=False)
+            r_g, r_o = rew.cpu().numpy(), out_o["reward"]
+            flip = (r_g == 4.0) != (r_o == 4.0)          # knife-edge success threshold (0.05 m) on float32 vs float64 sites
+            assert flip.mean() <= 0.05
+            assert np.abs(r_g - r_o)[~flip].max() < 1e-5, (name, k)
+            assert np.array_equal(term.cpu().numpy().astype(bool)[~flip], out_o["terminated"][~flip])
+            assert np.array_equal(trunc.cpu().numpy().astype(bool), out_o["truncated"])
+            assert bool(trunc.cpu().numpy().all()) == (k == 1)     # 300-step TimeLimit
+            rewards.append(r_g.copy())
+        sim.close(); orc.close()
+    rewards = np.concatenate(rewards)
+    if task == 3:
+        assert set(np.unique(rewards)) <= {np.float32(-0.2), np.float32(4.0)}
+    else:
+        assert rewards.min() >= -0.2 - 1e-6 and len(np.unique(np.round(rewards, 3))) > 10    # many shaped values
+
+
+def orc_model_ranges(model_blob):
+    from gym_so100_c_b200 import model
+    m = model.unpack(model_blob)
+    return np.array(m["act_lo"][:6], dtype=np.float64), np.array(m["act_hi"][:6], dtype=np.float64)
+
+
 def test_autoreset_and_truncation(model_blob):
     """TimeLimit semantics: GoalEnv truncates at 300 steps (env.py:395-403); with autoreset the returned obs is the first
     observation of the next episode, final_obs the terminal one, and the episode counter advances."""

@@ -63,8 +63,12 @@ def test_create_fails_loudly_without_gpu(model_blob):
     from gym_so100_c_b200.vec_env import SO100VecEnv
     with pytest.raises(ext.So100Error):
         SO100VecEnv(4)
+    with pytest.raises(ext.So100Error):
+        SO100VecEnv(4, task="so100_touch_cube")          # a registered task: fails only because there is no GPU
     with pytest.raises(NotImplementedError):
-        SO100VecEnv(4, task="so100_touch_cube")
+        SO100VecEnv(4, task="so100_transfer_cube")       # env.py:117-118
+    rc = lib.so100_create(model_blob, len(model_blob), 4, 0, 7, C.c_uint64(0), C.c_int64(0), C.byref(h))
+    assert rc == -1 and b"unknown task" in lib.so100_last_error()
     with pytest.raises(NotImplementedError):
         SO100VecEnv(4, obs_type="so100_pixels_agent_pos")
 

@@ -58,3 +58,18 @@ def test_cube_to_bin_reward_truth_table(orc):
         assert r == case["reward"], case
         levels.add(r)
     assert levels == {0.0, 1.0, 2.0, 2.5, 3.0, 4.0}
+
+
+def test_touch_reward_tables(orc):
+    """SO100TouchCubeTask / SO100TouchCubeSparseTask.get_reward (single_arm.py:149-215, 246-285) over all distance tiers,
+    with and without pad contact: the oracle's float64 restatement equals the reference's float64 result, cast to float32."""
+    seen = set()
+    for case in GOLD["touch_reward"]:
+        task = 2 if case["task"] == "so100_touch_cube" else 3
+        r = O.test_touch_reward(orc, task, case["contacts"], case["cube_site"], case["ee_site"])
+        assert r == np.float32(case["reward"]), case
+        seen.add((case["task"], r == 4.0))
+    assert seen == {("so100_touch_cube", True), ("so100_touch_cube", False), ("so100_touch_cube_sparse", True),
+                    ("so100_touch_cube_sparse", False)}
+    sparse = {np.float32(c["reward"]) for c in GOLD["touch_reward"] if c["task"] == "so100_touch_cube_sparse"}
+    assert sparse == {np.float32(-0.2), np.float32(4.0)}
