@@ -99,10 +99,9 @@ def cpu_arm(n_envs: int, steps: int, warmup: int, seed: int = 1234):
     """The CPU implementation of the same step: the fp64 C restatement (oracle/) on all host cores.
     kind = "port": MuJoCo itself is not installable here, so this is NOT MuJoCo."""
     from gym_so100_c_b200 import model
-    from oracle.so100_oracle import Oracle, build
+    from oracle.so100_oracle import Oracle, build, set_threads
     build()
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
     orc = Oracle(model.pack(model.load_model()), n_envs, task=0, seed=seed)
     orc.reset()
     rng = np.random.default_rng(seed)
@@ -206,6 +205,32 @@ def run_gpu(args):
     h2d = nl * 6 * 4
     d2h = nl * (15 * 4 + 15 * 4 + 3 * 4 + 3 * 4 + 4 + 3)
 
+    # ---- BASELINE config 4 beside the headline (N=1 only, short): GoalEnv dict observations for 65536 envs plus the HER
+    # relabelling reward on a [65536 * 4, 3] batch every step (n_sampled_goal = 4, scripts/train_sac_her.py:242)
+    extra = None
+    if world == 1 and not args.no_extra:
+        sim.close()
+        n4 = 65536
+        sim4 = BatchedSim(n4, device=dev, task=1, seed=0x50100)
+        sim4.reset()
+        acts4 = torch.rand((8, n4, 6), device=dev, generator=gen) * 2 - 1
+        relabel = torch.rand((n4 * 4, 3), device=dev, generator=gen) * 0.1
+        for s in range(5):
+            sim4.step(acts4[s % 8], autoreset=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(10):
+            sim4.step(acts4[s % 8], autoreset=True)
+            sim4.compute_reward(sim4.achieved.repeat(4, 1), relabel)
+        e1.record()
+        torch.cuda.synchronize()
+        ms4 = e0.elapsed_time(e1) / 10
+        extra = {"config4_goal_env_her": {"envs": n4, "relabel_batch": n4 * 4, "ms_per_step": ms4, "value": n4 / ms4 * 1e3,
+                                          "unit": "env-steps/s", "steps": 10}}
+        sim4.close()
+        sim = BatchedSim(hi - lo, device=dev, task=0, seed=0x50100, env_offset=lo)   # only for launches_per_step below
+
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
         n_total = n * world
@@ -255,6 +280,7 @@ def run_gpu(args):
             "physics_substeps_per_s": value * 10,
             "wall_s_timed_region": t_wall,
             "diagnostics": diag,
+            "extra": extra,
         }
         print(json.dumps(line))
     sim.close()
@@ -271,6 +297,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--no-extra", action="store_true", help="skip the short BASELINE config 4 measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

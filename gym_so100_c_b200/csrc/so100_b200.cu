@@ -46,6 +46,8 @@ struct EnvGroup {
   cudaEvent_t fork = nullptr, join = nullptr, done = nullptr;
   cudaEvent_t t_done = nullptr;                         // timing-enabled twin of `done` (so100_group_times)
   int* ctl = nullptr;                                   // this group's queue control words
+  int* order = nullptr;                                 // two longest-first permutations of the group's envs, [2][n_total] apart
+  int parity = 0;                                       // which of the two the next solve stage reads
 };
 
 struct so100_ctx {
@@ -60,6 +62,7 @@ struct so100_ctx {
   unsigned long long* diag = nullptr;
   float* work = nullptr;      // [N, WORK_WORDS] phase-pipeline workspace (L2-resident)
   int* qmem = nullptr;        // queue control words + heavy queue [N] + hull-pair queue [N * NHP]
+  int* order = nullptr;       // solve order permutations: [2][N] for the env groups, [2][N] for the whole-batch group
   // so100_step replays a CUDA graph of its whole launch sequence (all groups, forks and joins): the host cost of a step
   // drops from several hundred launch / event calls to one cudaGraphLaunch.  Actions are staged into a fixed buffer so
   // that the graph's kernel arguments never change; one graph is cached per distinct set of output pointers.
@@ -80,7 +83,10 @@ struct so100_ctx {
   uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_succ = nullptr;
   DevTables tables() const { return DevTables{geom, pair, vert, bpair}; }
   static constexpr int CTL_WORDS = 8 * 40;
-  Queues queues(const EnvGroup& G) const { return Queues{G.ctl, qmem + CTL_WORDS + n + (size_t)G.off * NHP, qmem + CTL_WORDS + G.off}; }
+  Queues queues(const EnvGroup& G) const {
+    return Queues{G.ctl, qmem + CTL_WORDS + n + (size_t)G.off * NHP, qmem + CTL_WORDS + G.off, G.order + (size_t)G.parity * n,
+                  G.order + (size_t)(1 - G.parity) * n};
+  }
 };
 
 // ------------------------------------------------------------------ small host math (double)
@@ -341,7 +347,7 @@ static void mark(so100_ctx* h, cudaStream_t st, int cls, bool begin) {
 }
 
 // K1: kinematics (+ dynamics), K2a/K2b: collision.  Leaves frames, M, qfrc_smooth and the contact list in the workspace.
-static void launch_position_stage(so100_ctx* h, const EnvGroup& G, cudaStream_t st, const float* action, int with_dyn) {
+static void launch_position_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const float* action, int with_dyn) {
   const int n = G.n;
   const DevTables T = h->tables();
   const Queues Q = h->queues(G);
@@ -358,25 +364,34 @@ static void launch_position_stage(so100_ctx* h, const EnvGroup& G, cudaStream_t 
 
 // K3l/K3h: constraint solve (+ Euler unless O.forward).  The heavy queue (a handful of envs with long serial Newton
 // runs) is drained on a side stream beside the light kernel; both rejoin `st`.
-static void launch_solve_stage(so100_ctx* h, const EnvGroup& G, cudaStream_t st, const SolveOut& O) {
+static void launch_solve_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const SolveOut& O) {
   const int n = G.n;
   const DevTables T = h->tables();
+  const Queues Q = h->queues(G);
+  if (!O.forward) G.parity ^= 1;     // this launch writes the permutation the next one reads
   float* state = h->state + (size_t)G.off * STATE_WORDS;
   const float* work = h->work + (size_t)G.off * WORK_WORDS;
   cudaEventRecord(G.fork, st);
   cudaStreamWaitEvent(G.side, G.fork, 0);
   mark(h, G.side, CLS_HEAVY, true);
-  phase_solve_heavy<LPE_K3H><<<std::min(grid_of(n, LPE_K3H), h->sm_count * 2), BLOCK, smem_of<SolS<NC>>(LPE_K3H), G.side>>>(state, work, T, h->queues(G), O);
+  phase_solve_heavy<LPE_K3H><<<std::min(grid_of(n, LPE_K3H), h->sm_count * 2), BLOCK, smem_of<SolS<NC>>(LPE_K3H), G.side>>>(state, work, T, Q, O);
   mark(h, G.side, CLS_HEAVY, false);
   cudaEventRecord(G.join, G.side);
   mark(h, st, CLS_SOLVE, true);
-  phase_solve_light<LPE_K3L><<<grid_of(n, LPE_K3L, TPB_K3L), TPB_K3L, smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L), st>>>(state, work, n, T, O);
+  phase_solve_light<LPE_K3L><<<grid_of(n, LPE_K3L, TPB_K3L), TPB_K3L, smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L), st>>>(state, work, n, T, Q, O);
   mark(h, st, CLS_SOLVE, false);
   cudaStreamWaitEvent(st, G.join, 0);
 }
 
 static int make_group(so100_ctx* h, EnvGroup& G, int off, int n, int index, bool own_stream) {
   G.off = off; G.n = n; G.ctl = h->qmem + 8 * index;
+  G.order = h->order + (own_stream ? 0 : 2 * (size_t)h->n) + off;
+  {
+    std::vector<int> ident(n);
+    for (int i = 0; i < n; i++) ident[i] = i;
+    CUDA_OK(cudaMemcpy(G.order, ident.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(G.order + h->n, ident.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  }
   if (own_stream) CUDA_OK(cudaStreamCreateWithFlags(&G.st, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&G.side, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&G.fork, cudaEventDisableTiming));
@@ -448,6 +463,7 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   CUDA_OK(cudaMemset(h->work, 0, (size_t)num_envs * WORK_WORDS * sizeof(float)));
   CUDA_OK(cudaMalloc(&h->qmem, (so100_ctx::CTL_WORDS + (1 + NHP) * (size_t)num_envs) * sizeof(int)));
   CUDA_OK(cudaMemset(h->qmem, 0, (so100_ctx::CTL_WORDS + (1 + NHP) * (size_t)num_envs) * sizeof(int)));
+  CUDA_OK(cudaMalloc(&h->order, 4 * (size_t)num_envs * sizeof(int)));
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->t_start));
   if (const char* e = getenv("SO100_GROUP_TIMES")) h->group_times = atoi(e) != 0;
@@ -493,7 +509,7 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
 int so100_destroy(so100_handle h) {
   if (!h) return SO100_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->state); cudaFree(h->geom); cudaFree(h->pair); cudaFree(h->vert); cudaFree(h->bpair); cudaFree(h->diag); cudaFree(h->work); cudaFree(h->qmem);
+  cudaFree(h->state); cudaFree(h->geom); cudaFree(h->pair); cudaFree(h->vert); cudaFree(h->bpair); cudaFree(h->diag); cudaFree(h->work); cudaFree(h->qmem); cudaFree(h->order);
   free_group(h->whole);
   for (EnvGroup& G : h->groups) free_group(G);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
@@ -528,7 +544,7 @@ int so100_reset(so100_handle h, const uint8_t* mask, const float* box_pose, floa
 // the launch sequence of one env step on `stream` (directly, or while `stream` is being captured into a graph)
 static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream) {
   const float* action = A.action;
-  for_each_group(h, stream, true, [&](const EnvGroup& G, cudaStream_t st) {
+  for_each_group(h, stream, true, [&](EnvGroup& G, cudaStream_t st) {
     const SolveOut O{nullptr, nullptr, 0};
     for (int s = 0; s < h->nsub; s++) {
       launch_position_stage(h, G, st, s == 0 ? action : nullptr, 1);
@@ -659,7 +675,7 @@ int so100_set_aux(so100_handle h, const float* goal, const int32_t* step_count, 
 
 int so100_substeps(so100_handle h, int nsub, void* stream) {
   if (!h || nsub < 0) return fail(SO100_ERR_ARG, "so100_substeps: bad argument");
-  for_each_group(h, (cudaStream_t)stream, true, [&](const EnvGroup& G, cudaStream_t st) {
+  for_each_group(h, (cudaStream_t)stream, true, [&](EnvGroup& G, cudaStream_t st) {
     const SolveOut O{nullptr, nullptr, 0};
     for (int s = 0; s < nsub; s++) {
       launch_position_stage(h, G, st, nullptr, 1);

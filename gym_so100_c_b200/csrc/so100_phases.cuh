@@ -108,8 +108,8 @@ struct SolveOut {
 };
 
 template <unsigned LPE, class ES>
-__device__ void solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w, int env, int ncon_raw, const DevTables& T,
-                          const SolveOut& O) {
+__device__ int solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w, int env, int ncon_raw, const DevTables& T,
+                         const SolveOut& O) {
   const int lane = t.thread_rank();
   copy_vec<LPE, 48>(t, S->st, rec);
   copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
@@ -120,28 +120,34 @@ __device__ void solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w,
   if (lane == 0) S->ncon = ncon;
   t.sync();
   make_contact_rows(t, S, T);
-  solve(t, S, T, O.forward ? nullptr : reinterpret_cast<uint32_t*>(rec + S_DIAG));
+  const int iters = solve(t, S, T, O.forward ? nullptr : reinterpret_cast<uint32_t*>(rec + S_DIAG));
   if (O.forward) {
     t.sync();
     if (O.qacc && lane < NV) O.qacc[(size_t)env * NV + lane] = S->a[lane];
     if (O.con_data)
       for (int k = lane; k < ncon * 4; k += LPE) O.con_data[((size_t)env * NC + (k >> 2)) * 11 + 7 + (k & 3)] = S->cfrc[k >> 2][k & 3];
-    return;
+    return iters;
   }
   integrate(t, S);
   copy_vec<LPE, 48>(t, rec, S->st);   // qpos qvel (ctrl unchanged) warm (+ goal / counters unchanged)
+  return iters;
 }
 
 // K3l: regular grid, one tile per env; envs with more than NCL contacts are left to K3h
 template <unsigned LPE>
-__global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TPB_K3L) phase_solve_light(float* state, const float* work, int n, DevTables T, SolveOut O) {
+__global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TPB_K3L) phase_solve_light(float* state, const float* work, int n, DevTables T, Queues Q, SolveOut O) {
   SO100_TILE_PROLOGUE(LPE, SO100_TPB_K3L, SolS<NCL>);
-  const int env = blockIdx.x * EPB + t.meta_group_rank();
-  if (env >= n) return;
+  const int slot = blockIdx.x * EPB + t.meta_group_rank();
+  if (slot >= n) return;
+  const int env = Q.order_in[slot];
   const float* w = work + (size_t)env * WORK_WORDS;
   const int ncon_raw = __float_as_int(w[W_HDR]);
-  if (ncon_raw > NCL) return;
-  solve_env(t, S, state + (size_t)env * STATE_WORDS, w, env, ncon_raw, T, O);
+  int iters = 1000;                          // heavy envs count as slow
+  if (ncon_raw <= NCL) iters = solve_env(t, S, state + (size_t)env * STATE_WORDS, w, env, ncon_raw, T, O);
+  if (!O.forward && lane == 0) {
+    const int pos = iters >= 3 ? atomicAdd(&Q.ctl[Q_SLOW], 1) : n - 1 - atomicAdd(&Q.ctl[Q_FAST], 1);
+    Q.order_out[pos] = env;
+  }
 }
 
 // K3h: persistent tiles drain the heavy queue

@@ -44,12 +44,17 @@ static_assert(WORK_WORDS % 8 == 0 && W_HDR % 4 == 0 && W_CON % 4 == 0, "workspac
 static_assert(NHP <= 16, "hull pair list is 4 words");
 
 // queue control words (device ints)
-enum { Q_HULL_COUNT = 0, Q_HULL_NEXT = 1, Q_HEAVY_COUNT = 2, Q_HEAVY_NEXT = 3, Q_WORDS = 4 };
+enum { Q_HULL_COUNT = 0, Q_HULL_NEXT = 1, Q_HEAVY_COUNT = 2, Q_HEAVY_NEXT = 3, Q_SLOW = 4, Q_FAST = 5, Q_WORDS = 6 };
 
 struct Queues {
   int* ctl;      // [Q_WORDS]
   int* hull;     // [N * NHP] hull pairs for GJK/EPA this substep, one item = env * NHP + slot
   int* heavy;    // [N] envs with more than NCL contacts this substep
+  // Longest-first order of the light solve kernel: block b solves env order_in[b].  Envs that needed >= 3 Newton
+  // iterations (or went to the heavy kernel) are written to the front of order_out, the rest to the back, so that the
+  // next substep starts its likely stragglers first (the iteration count of an env is strongly correlated in time).
+  const int* order_in;
+  int* order_out;
 };
 
 // ---------------------------------------------------------------- scratch structs

@@ -357,7 +357,8 @@ template <class ES> __device__ __forceinline__ float hess_contact(const ES* S, i
 }
 
 // Solves for qacc (left in S->a / S->ad, contact forces in S->cfrc).  `diag` (nullable): the env's uint32 counters.
-template <unsigned LPE, class ES> __device__ void solve(const Tile<LPE>& t, ES* S, const DevTables& T, uint32_t* diag) {
+// Returns the number of Newton iterations.
+template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S, const DevTables& T, uint32_t* diag) {
   using Regs = SolveRegs<LPE, ES::NCAP>;
   const int lane = t.thread_rank();
   const int ncon = S->ncon;
@@ -603,6 +604,7 @@ template <unsigned LPE, class ES> __device__ void solve(const Tile<LPE>& t, ES* 
     diag[6] += 1u;
     diag[7] += (uint32_t)ncon;
   }
+  return it;
 }
 
 // ------------------------------------------------------------------ semi-implicit Euler

@@ -8,6 +8,9 @@
  *   GoalEnv step / compute_reward      gym_so100/env.py:341-358, 372-406
  */
 #include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "so100_oracle.h"
 
 struct so100o {
@@ -384,6 +387,17 @@ float so100o_test_touch_reward(so100o* h, int task, int ncon, const int32_t* geo
   memcpy(e->site[m->site_cube], cube_site, 3 * sizeof(double));
   memcpy(e->site[m->site_ee], ee_site, 3 * sizeof(double));
   return touch_reward(h, e, task == 2);
+}
+
+/* worker threads of the OpenMP loops over envs (torchrun exports OMP_NUM_THREADS=1; the CPU arm of bench.py uses all cores) */
+int so100o_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
 }
 
 /* batched HER reward, env.py:346-349 */

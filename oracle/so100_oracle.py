@@ -177,6 +177,11 @@ test_touch_reward.__test__ = False
 test_box_pair.__test__ = False
 
 
+def set_threads(n: int) -> int:
+    """Set the OpenMP team size of the oracle's loops over envs; returns the size in effect."""
+    return int(lib().so100o_set_threads(int(n)))
+
+
 def compute_reward(ag, dg, thr=0.01):
     ag = np.ascontiguousarray(ag, dtype=np.float32).reshape(-1, 3)
     dg = np.ascontiguousarray(dg, dtype=np.float32).reshape(-1, 3)
