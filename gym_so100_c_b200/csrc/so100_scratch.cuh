@@ -3,7 +3,7 @@
 //
 // Every phase kernel owns one cooperative tile of LPE lanes per env and a scratch struct that holds
 // only what that phase touches (1.7 KB for kinematics/dynamics, 1.2 KB for the box collision stage,
-// 4 KB for a hull (GJK/EPA) env, 4 KB for a solve with <= 8 contacts, 9.5 KB for the rare solve with
+// 4 KB for a hull (GJK/EPA) env, 5.7 KB for a solve with <= 8 contacts, 14.5 KB for the rare solve with
 // up to 24), so that shared memory never limits the number of resident warps.  The device functions
 // are templates over the scratch type and only name the members they use.
 #pragma once
@@ -117,6 +117,7 @@ template <int NCAP_> struct __align__(16) SolS {
   unsigned char ckind[NCAP_];      // bit 0: contact touches an arm link, bit 1: touches the cube
   int ncon, coupled;
   float J[NCAP_ * 4][JS];
+  float T[NCAP_ * 4][JS];          // H_c J_c rows of the current Newton iteration
 };
 
 // K4 / reset: task layer

@@ -334,25 +334,35 @@ __device__ __forceinline__ float eval_cost(const Tile<LPE>& t, ES* S, SolveRegs<
   return tsum(t, cost);
 }
 
-// contribution of contact c to Hessian entry (i, j)
-template <class ES> __device__ __forceinline__ float hess_contact(const ES* S, int c, int zone, int i, int j) {
-  const float* Hc = S->cH[c];
-  float h = 0;
-  if (zone == 1) {
+// T = H_c J_c for every active contact row (lane per (row, dof)): the Hessian J^T H J then costs 4 multiply-adds per
+// (entry, contact) instead of a 4x4 quadratic form per (entry, contact)
+template <unsigned LPE, class ES> __device__ __forceinline__ void cone_hess_rows(const Tile<LPE>& t, ES* S) {
+  // uncoupled: a contact touches the arm block or the cube block, 6 dofs (8 slots per row); coupled: all 12 (16 slots)
+  const int sh = S->coupled ? 4 : 3, W = S->coupled ? NV : NL;
+  const int n = (S->ncon * 4) << sh;
+  for (int it = t.thread_rank(); it < n; it += LPE) {
+    const int row = it >> sh, c = row >> 2, k = row & 3, slot = it & ((1 << sh) - 1);
+    if (slot >= W) continue;
+    const int d = slot + ((W == NL && !(S->ckind[c] & 1)) ? NL : 0);
+    const int zone = S->czone[c];
+    const float* Hc = S->cH[c];
+    float v = 0;
+    if (zone == 1) {
+      v = Hc[tri(k, k)] * S->J[row][d];          // bottom zone: H_c = diag(D)
+    } else if (zone == 2) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) h = fmaf(Hc[tri(k, k)] * S->J[c * 4 + k][i], S->J[c * 4 + k][j], h);
-  } else {
-    float ji[4], jj[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) { ji[k] = S->J[c * 4 + k][i]; jj[k] = S->J[c * 4 + k][j]; }
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      float tb = 0;
-#pragma unroll
-      for (int a2 = 0; a2 < 4; a2++) tb = fmaf(ji[a2], Hc[a2 >= b ? tri(a2, b) : tri(b, a2)], tb);
-      h = fmaf(tb, jj[b], h);
+      for (int l = 0; l < 4; l++) v = fmaf(Hc[l >= k ? tri(l, k) : tri(k, l)], S->J[c * 4 + l][d], v);
     }
+    S->T[row][d] = v;
   }
+  t.sync();
+}
+
+// contribution of contact c to Hessian entry (i, j)
+template <class ES> __device__ __forceinline__ float hess_contact(const ES* S, int c, int i, int j) {
+  float h = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) h = fmaf(S->J[c * 4 + k][i], S->T[c * 4 + k][j], h);
   return h;
 }
 
@@ -427,6 +437,7 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
     tsum2(t, gg, ss);
     if (sqrtf(gg) * c_m.inv_scale < SO100_GTOL * (1.0f + sqrtf(ss))) { converged = true; done = true; return; }
     float pd;
+    cone_hess_rows(t, S);
     if (!coupled) {
       // ---- block-diagonal Hessian: entries 0..20 arm block, 21..41 cube block
       for (int e = lane; e < 42; e += LPE) {
@@ -440,7 +451,7 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
         for (int c = 0; c < ncon; c++) {
           const int zone = S->czone[c];
           if (zone == 0 || !(S->ckind[c] & (1 << blk))) continue;
-          h += hess_contact(S, c, zone, gi, gj);
+          h += hess_contact(S, c, gi, gj);
         }
         S->H[e] = h;
       }
@@ -468,32 +479,42 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
         for (int c = 0; c < ncon; c++) {
           const int zone = S->czone[c];
           if (zone == 0) continue;
-          h += hess_contact(S, c, zone, i, j);
+          h += hess_contact(S, c, i, j);
         }
         S->H[e] = h;
       }
       t.sync();
+      // right-looking Cholesky with row i of the lower triangle in the registers of lane i: column k is scaled by
+      // 1 / L_kk (broadcast from lane k) and every lane fetches the L_jk it needs by shuffle -- no barriers, no
+      // shared-memory round trips (the barrier version cost ~3x the latency of this one per coupled Newton iteration)
+      float a[NV];
+#pragma unroll
+      for (int j = 0; j < NV; j++) a[j] = (lane < NV && j <= lane) ? S->H[tri(lane < NV ? lane : 0, j)] : 0.0f;
+#pragma unroll
       for (int k = 0; k < NV; k++) {
-        const float dk = rsqrtf(fmaxf(S->H[tri(k, k)], 1e-20f));
-        t.sync();
-        for (int i = k + lane; i < NV; i += LPE) {
-          if (i == k) S->H[tri(k, k)] = dk;      // stores 1 / L_kk
-          else S->H[tri(i, k)] *= dk;
+        const float dk = rsqrtf(fmaxf(t.shfl(a[k], k), 1e-20f));
+        const float lik = a[k] * dk;                 // L_ik on lanes i > k
+        a[k] = (lane == k) ? dk : lik;               // lane k keeps 1 / L_kk
+#pragma unroll
+        for (int j = k + 1; j < NV; j++) {
+          const float ljk = t.shfl(lik, j);
+          if (lane >= j) a[j] = fmaf(-lik, ljk, a[j]);
         }
-        t.sync();
-        for (int e = lane; e < 78; e += LPE) {
-          int i, j;
-          untri(e, i, j);
-          if (j > k) S->H[e] = fmaf(-S->H[tri(i, k)], S->H[tri(j, k)], S->H[e]);
-        }
-        t.sync();
       }
       float x = -g;
-      for (int k = 0; k < NV; k++) {
-        float xk = t.shfl(x, k) * S->H[tri(k, k)];
+#pragma unroll
+      for (int k = 0; k < NV; k++) {                 // L y = -g
+        const float xk = t.shfl(x * a[k], k);
         if (lane == k) x = xk;
-        else if (lane > k && lane < NV) x = fmaf(-S->H[tri(lane, k)], xk, x);
+        else if (lane > k && lane < NV) x = fmaf(-a[k], xk, x);
       }
+      // L^T z = y needs columns of L: hand the rows over through shared memory once
+      if (lane < NV) {
+#pragma unroll
+        for (int j = 0; j < NV; j++)
+          if (j <= lane) S->H[tri(lane, j)] = a[j];
+      }
+      t.sync();
       for (int k = NV - 1; k >= 0; k--) {
         float xk = t.shfl(x, k) * S->H[tri(k, k)];
         if (lane == k) x = xk;
