@@ -26,6 +26,29 @@ __device__ __forceinline__ void load_shape(const FrameBlock& f, const DevGeom& G
   else s.base = G.link >= 0 ? ld3(f.lpos[G.link]) : ld3(G.org);
 }
 
+// order-preserving map float -> uint (for integer warp reductions); -0 and +0 map to the same key
+__device__ __forceinline__ unsigned ordered_key(float f) {
+  const unsigned b = __float_as_uint(f + 0.0f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+// index of the largest value over the tile, ties to the lowest index (every lane passes its best value / index):
+// two redux.sync instructions on a full warp instead of a 5-round shuffle arg-max
+template <unsigned LPE> __device__ __forceinline__ int tile_argmax(const Tile<LPE>& t, float best, int bi) {
+  if constexpr (LPE == 32) {
+    const unsigned key = ordered_key(best);
+    const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+    return (int)__reduce_min_sync(0xffffffffu, key == kmax ? (unsigned)bi : 0x7fffffffu);
+  } else {
+#pragma unroll
+    for (int off = LPE / 2; off > 0; off >>= 1) {
+      const float ov = t.shfl_xor(best, off);
+      const int oi = t.shfl_xor(bi, off);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    return bi;
+  }
+}
+
 // support point in world direction d; identical on every lane of the tile
 template <unsigned LPE>
 __device__ __forceinline__ V3 support(const Tile<LPE>& t, const Shape& s, V3 d, const float4* __restrict__ vert) {
@@ -41,12 +64,7 @@ __device__ __forceinline__ V3 support(const Tile<LPE>& t, const Shape& s, V3 d, 
       const float val = fmaf(p.x, dl.x, fmaf(p.y, dl.y, p.z * dl.z));
       if (val > best) { best = val; bi = v; }
     }
-#pragma unroll
-    for (int off = LPE / 2; off > 0; off >>= 1) {
-      const float ov = t.shfl_xor(best, off);
-      const int oi = t.shfl_xor(bi, off);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
+    bi = tile_argmax(t, best, bi);
     const float4 p = __ldg(&vert[s.vadr + bi]);
     pl = mk(p.x, p.y, p.z);
   }
@@ -213,12 +231,7 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
     float bd = 3.0e38f; int bf = 0x7fffffff;
     for (int f = lane; f < nface; f += LPE)
       if (E->fv[f][3] && E->fdt[f] < bd) { bd = E->fdt[f]; bf = f; }
-#pragma unroll
-    for (int off = LPE / 2; off > 0; off >>= 1) {
-      const float ov = t.shfl_xor(bd, off);
-      const int of = t.shfl_xor(bf, off);
-      if (ov < bd || (ov == bd && of < bf)) { bd = ov; bf = of; }
-    }
+    bf = tile_argmax(t, -bd, bf);
     if (bf == 0x7fffffff) break;
     best = bf;
     const V3 nb = ld3(E->fn[best]);

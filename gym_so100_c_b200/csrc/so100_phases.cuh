@@ -143,7 +143,22 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
   const float* w = work + (size_t)env * WORK_WORDS;
   const int ncon_raw = __float_as_int(w[W_HDR]);
   int iters = 1000;                          // heavy envs count as slow
+#ifdef SO100_SOLVE_CLOCK
+  unsigned long long t0_;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0_));
+#endif
   if (ncon_raw <= NCL) iters = solve_env(t, S, state + (size_t)env * STATE_WORDS, w, env, ncon_raw, T, O);
+#ifdef SO100_SOLVE_CLOCK
+  // development build: duration (ns) and iteration count of this env's last solve in the spare words of its state record
+  unsigned long long t1_;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1_));
+  if (lane == 0) {
+    float* rec_ = state + (size_t)env * STATE_WORDS;
+    rec_[57] = __int_as_float((int)(t1_ - t0_));
+    rec_[58] = __int_as_float(iters);
+    rec_[59] = __int_as_float(ncon_raw | (S->coupled << 8));
+  }
+#endif
   if (!O.forward && lane == 0) {
     const int pos = iters >= 3 ? atomicAdd(&Q.ctl[Q_SLOW], 1) : n - 1 - atomicAdd(&Q.ctl[Q_FAST], 1);
     Q.order_out[pos] = env;

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Development aid (needs a -DSO100_SOLVE_CLOCK build, SO100_LIB=...): duration vs Newton iterations of the light solves."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from gym_so100_c_b200.engine import BatchedSim  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+sim = BatchedSim(n, seed=3)
+sim.reset()
+g = torch.Generator(device="cuda").manual_seed(1)
+for _ in range(60):
+    sim.step(torch.rand((n, 6), device="cuda", generator=g) * 2 - 1)
+rows = []
+for _ in range(20):
+    sim.substeps(1)
+    st = sim.debug_read(0).view(torch.int32)[:, 57:60].cpu().numpy()
+    rows.append(st.copy())
+    print("substep: max ns %d (its %d, ncon %d, coupled %d); mean ns %.0f; its>=8: %d" % (
+        st[:, 0].max(), st[st[:, 0].argmax(), 1], st[st[:, 0].argmax(), 2] & 255, st[st[:, 0].argmax(), 2] >> 8,
+        st[:, 0].mean(), (st[:, 1] >= 8).sum()))
+a = np.concatenate(rows)
+ok = a[:, 1] < 1000
+for it in sorted(set(a[ok, 1].tolist())):
+    m = ok & (a[:, 1] == it)
+    for cp in (0, 1):
+        mm = m & ((a[:, 2] >> 8) == cp)
+        if mm.sum():
+            print(f"its {it:3d} coupled {cp}: n {mm.sum():6d}  ns mean {a[mm, 0].mean():9.0f}  min {a[mm, 0].min():8d}  max {a[mm, 0].max():8d}")
