@@ -366,6 +366,72 @@ template <class ES> __device__ __forceinline__ float hess_contact(const ES* S, i
   return h;
 }
 
+// Newton direction -H^-1 g for a Hessian that couples the arm and the cube (a contact between them): dense 12x12.
+// Kept out of line: it is taken by < 1 % of the solves and its unrolled register Cholesky is ~1.5 k instructions that
+// would otherwise sit in the middle of the hot loop's instruction stream.
+template <unsigned LPE, class ES> __device__ __noinline__ float dense_newton_dir(const Tile<LPE>& t, ES* S, float g) {
+  const int lane = t.thread_rank();
+  const int ncon = S->ncon;
+  float pd;
+    // ---- dense 12x12: packed lower triangle in shared memory, tile-parallel Cholesky
+    for (int e = lane; e < 78; e += LPE) {
+      int i, j;
+      untri(e, i, j);
+      float h = 0;
+      if (i < NL) h = S->d.Mfull[i][j];
+      else if (i == j) h = (i < 9 ? c_m.cube_mass : c_m.cube_I[i - 9]);
+      if (i == j) h += S->hdiag[i];
+      for (int c = 0; c < ncon; c++) {
+        const int zone = S->czone[c];
+        if (zone == 0) continue;
+        h += hess_contact(S, c, i, j);
+      }
+      S->H[e] = h;
+    }
+    t.sync();
+    // right-looking Cholesky with row i of the lower triangle in the registers of lane i: column k is scaled by
+    // 1 / L_kk (broadcast from lane k) and every lane fetches the L_jk it needs by shuffle -- no barriers, no
+    // shared-memory round trips (the barrier version cost ~3x the latency of this one per coupled Newton iteration)
+    float a[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j++) a[j] = (lane < NV && j <= lane) ? S->H[tri(lane < NV ? lane : 0, j)] : 0.0f;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      const float dk = rsqrtf(fmaxf(t.shfl(a[k], k), 1e-20f));
+      const float lik = a[k] * dk;                 // L_ik on lanes i > k
+      a[k] = (lane == k) ? dk : lik;               // lane k keeps 1 / L_kk
+#pragma unroll
+      for (int j = k + 1; j < NV; j++) {
+        const float ljk = t.shfl(lik, j);
+        if (lane >= j) a[j] = fmaf(-lik, ljk, a[j]);
+      }
+    }
+    float x = -g;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {                 // L y = -g
+      const float xk = t.shfl(x * a[k], k);
+      if (lane == k) x = xk;
+      else if (lane > k && lane < NV) x = fmaf(-a[k], xk, x);
+    }
+    // L^T z = y needs columns of L: hand the rows over through shared memory once
+    if (lane < NV) {
+#pragma unroll
+      for (int j = 0; j < NV; j++)
+        if (j <= lane) S->H[tri(lane, j)] = a[j];
+    }
+    t.sync();
+    for (int k = NV - 1; k >= 0; k--) {
+      float xk = t.shfl(x, k) * S->H[tri(k, k)];
+      if (lane == k) x = xk;
+      else if (lane < k) x = fmaf(-S->H[tri(k, lane)], xk, x);
+    }
+    pd = (lane < NV) ? x : 0.0f;
+    t.sync();
+    if (lane < NV) S->vec[lane] = pd;
+    t.sync();
+  return pd;
+}
+
 // Solves for qacc (left in S->a / S->ad, contact forces in S->cfrc).  `diag` (nullable): the env's uint32 counters.
 // Returns the number of Newton iterations.
 template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S, const DevTables& T, uint32_t* diag) {
@@ -468,62 +534,7 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
       t.sync();
       pd = (lane < NV) ? S->vec[lane] : 0.0f;
     } else {
-      // ---- dense 12x12: packed lower triangle in shared memory, tile-parallel Cholesky
-      for (int e = lane; e < 78; e += LPE) {
-        int i, j;
-        untri(e, i, j);
-        float h = 0;
-        if (i < NL) h = S->d.Mfull[i][j];
-        else if (i == j) h = (i < 9 ? c_m.cube_mass : c_m.cube_I[i - 9]);
-        if (i == j) h += S->hdiag[i];
-        for (int c = 0; c < ncon; c++) {
-          const int zone = S->czone[c];
-          if (zone == 0) continue;
-          h += hess_contact(S, c, i, j);
-        }
-        S->H[e] = h;
-      }
-      t.sync();
-      // right-looking Cholesky with row i of the lower triangle in the registers of lane i: column k is scaled by
-      // 1 / L_kk (broadcast from lane k) and every lane fetches the L_jk it needs by shuffle -- no barriers, no
-      // shared-memory round trips (the barrier version cost ~3x the latency of this one per coupled Newton iteration)
-      float a[NV];
-#pragma unroll
-      for (int j = 0; j < NV; j++) a[j] = (lane < NV && j <= lane) ? S->H[tri(lane < NV ? lane : 0, j)] : 0.0f;
-#pragma unroll
-      for (int k = 0; k < NV; k++) {
-        const float dk = rsqrtf(fmaxf(t.shfl(a[k], k), 1e-20f));
-        const float lik = a[k] * dk;                 // L_ik on lanes i > k
-        a[k] = (lane == k) ? dk : lik;               // lane k keeps 1 / L_kk
-#pragma unroll
-        for (int j = k + 1; j < NV; j++) {
-          const float ljk = t.shfl(lik, j);
-          if (lane >= j) a[j] = fmaf(-lik, ljk, a[j]);
-        }
-      }
-      float x = -g;
-#pragma unroll
-      for (int k = 0; k < NV; k++) {                 // L y = -g
-        const float xk = t.shfl(x * a[k], k);
-        if (lane == k) x = xk;
-        else if (lane > k && lane < NV) x = fmaf(-a[k], xk, x);
-      }
-      // L^T z = y needs columns of L: hand the rows over through shared memory once
-      if (lane < NV) {
-#pragma unroll
-        for (int j = 0; j < NV; j++)
-          if (j <= lane) S->H[tri(lane, j)] = a[j];
-      }
-      t.sync();
-      for (int k = NV - 1; k >= 0; k--) {
-        float xk = t.shfl(x, k) * S->H[tri(k, k)];
-        if (lane == k) x = xk;
-        else if (lane < k) x = fmaf(-S->H[tri(k, lane)], xk, x);
-      }
-      pd = (lane < NV) ? x : 0.0f;
-      t.sync();
-      if (lane < NV) S->vec[lane] = pd;
-      t.sync();
+      pd = dense_newton_dir(t, S, g);
     }
     // ---- line-search set-up
     float Mp = 0;
