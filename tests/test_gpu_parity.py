@@ -294,6 +294,39 @@ def test_seeded_reset_matches_reference_golden(model_blob):
     env.close()
 
 
+def test_demonstration_replay_reproduces_recorded_episodes(model_blob, tmp_path):
+    """episodes recorded in the reference's pickle format (here: recorded from this env with scripted actions,
+    ragged lengths) replay to the same rewards, bit for bit, with every episode in its own env."""
+    import pickle
+    import torch
+    from gym_so100_c_b200 import replay
+    from gym_so100_c_b200.vec_env import SO100VecEnv
+    rng = np.random.default_rng(11)
+    E, lengths = 5, [12, 7, 12, 3, 9]
+    env = SO100VecEnv(E, seed=2, autoreset=False)
+    obs, _ = env.reset(seed=40)
+    eps = [dict(observations=[obs[i].cpu().numpy().copy()], actions=[], rewards=[], infos=[]) for i in range(E)]
+    a_start = np.array([0, 0.35089, -0.19493, 0, 0, -0.79585], dtype=np.float32)
+    for t in range(max(lengths)):
+        act = (a_start + rng.uniform(-0.3, 0.3, size=(E, 6))).astype(np.float32)
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(act))
+        for i in range(E):
+            if t < lengths[i]:
+                eps[i]["actions"].append(act[i]); eps[i]["rewards"].append(float(rew[i])); eps[i]["infos"].append({})
+                eps[i]["observations"].append(obs[i].cpu().numpy().copy())
+    env.close()
+    path = tmp_path / "demo.pkl"
+    with open(path, "wb") as f:
+        pickle.dump(eps, f)
+    out = replay.replay(replay.load_demonstrations(str(path)))
+    assert out["reward"].shape == (12, E) and list(out["lengths"]) == lengths
+    for i in range(E):
+        assert np.array_equal(out["reward"][:lengths[i], i], np.array(eps[i]["rewards"], dtype=np.float32))
+        assert np.abs(out["obs"][lengths[i] - 1, i] - eps[i]["observations"][-1]).max() < 1e-6
+    assert np.allclose(out["episode_return"], out["recorded_return"])
+    assert not out["valid"][3:, 3].any() and out["valid"][:3, 3].all()
+
+
 def test_compute_reward_batch_bit_exact(model_blob):
     import torch
     from oracle.so100_oracle import compute_reward

@@ -127,3 +127,27 @@ def test_two_rank_gloo_statistics(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_OK 2 1001" in out.stdout
+
+
+def test_demonstration_loading_and_start_poses(tmp_path):
+    """The reference's recording format (scripts/record_teleop.py:177-184, 277-282): a pickled list of episode dicts.
+    State observations give the cube's start pose (cube_site - 0.01), pixel observations fall back to the seeded pose."""
+    import pickle
+    import numpy as np
+    from gym_so100_c_b200 import replay
+    from gym_so100_c_b200.vec_env import sample_so100_box_pose
+    obs0 = np.zeros(15, np.float32); obs0[:3] = [-0.19, 0.46, 0.06]
+    eps = [dict(observations=[obs0, obs0], actions=[np.zeros(6), np.ones(6) * 0.5], rewards=[0.0, 1.0], infos=[{}, {}]),
+           dict(observations=[{"pixels": None, "agent_pos": np.zeros(6)}], actions=[np.zeros(6)], rewards=[0.0], infos=[{}])]
+    path = tmp_path / "expert_demonstrations.pkl"
+    with open(path, "wb") as f:
+        pickle.dump(eps, f)
+    loaded = replay.load_demonstrations(str(path))
+    assert len(loaded) == 2 and len(loaded[0]["actions"]) == 2
+    poses = replay.start_poses(loaded, seed=5)
+    assert np.allclose(poses[0], [-0.2, 0.45, 0.05, 1, 0, 0, 0], atol=1e-6)
+    assert np.array_equal(poses[1], sample_so100_box_pose(6).astype(np.float32))
+    with open(path, "wb") as f:
+        pickle.dump([dict(observations=[])], f)
+    with pytest.raises(ValueError):
+        replay.load_demonstrations(str(path))
