@@ -281,6 +281,7 @@ static int build_dev_model(const so100_model& m, DevModel& dm, std::vector<DevGe
     int b1 = m.geom_body[P.g1], b2 = m.geom_body[P.g2];
     P.dtran = (float)(m.body_invweight0[b1][0] + m.body_invweight0[b2][0]);
     P.drot = (float)(m.body_invweight0[b1][1] + m.body_invweight0[b2][1]);
+    P.l1 = (short)geoms[P.g1].link; P.l2 = (short)geoms[P.g2].link;
     P.omd0 = (float)(1.0 - si[0]);
     P.dd = (float)(si[1] - si[0]);
   }

@@ -50,7 +50,7 @@ struct DevPair {
   float dtran, drot;  // diagApprox: body_invweight0 sums
   float omd0, dd;     // 1 - solimp[0] and solimp[1] - solimp[0], formed in fp64 on the host: with the cube's
                       // solimp clamped to 0.9999, (1 - imp) in float32 would lose 3 digits (R = (1-imp)/imp * diag)
-  int pad;
+  short l1, l2;       // link of g1 / g2 (0..5 arm link, 6 cube, -1 static): saves a dependent table load in the solver
 };
 
 struct DevModel {

@@ -89,7 +89,7 @@ template <unsigned LPE, class ES> __device__ void make_contact_rows(const Tile<L
   int both = 0;
   for (int c = lane; c < ncon; c += LPE) {
     const DevPair& P = T.pair[__float_as_int(S->con[c][7])];
-    const int l1 = T.geom[P.g1].link, l2 = T.geom[P.g2].link;
+    const int l1 = P.l1, l2 = P.l2;
     const int kind = (((l1 >= 0 && l1 < NL) || (l2 >= 0 && l2 < NL)) ? 1 : 0) | ((l1 == NL || l2 == NL) ? 2 : 0);
     S->ckind[c] = (unsigned char)kind;
     both |= (kind == 3);
@@ -111,7 +111,7 @@ template <unsigned LPE, class ES> __device__ void make_contact_rows(const Tile<L
   for (int it = lane; it < ncon * NV; it += LPE) {
     const int c = it / NV, d = it - c * NV;
     const DevPair& P = T.pair[__float_as_int(S->con[c][7])];
-    const int l1 = T.geom[P.g1].link, l2 = T.geom[P.g2].link;
+    const int l1 = P.l1, l2 = P.l2;
     V3 n = ld3(&S->con[c][3]), t1, t2, pos = ld3(&S->con[c][0]);
     make_frame(n, t1, t2);
     V3 jp = mk(0, 0, 0), jr = mk(0, 0, 0);
