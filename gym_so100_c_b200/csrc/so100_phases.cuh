@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
     rec_[57] = __int_as_float((int)(t1_ - t0_));
     rec_[58] = __int_as_float(iters);
     rec_[59] = __int_as_float(ncon_raw | (S->coupled << 8));
+    for (int k_ = 0; k_ < 4; k_++) rec_[60 + k_] = __int_as_float(S->clk[k_]);
   }
 #endif
   if (!O.forward && lane == 0) {

@@ -26,6 +26,9 @@ constexpr int LS_MAXIT = 10;
 #ifndef SO100_GTOL
 #define SO100_GTOL 2e-6f     // gradient tolerance relative to |qfrc_smooth| + |J^T f|
 #endif
+#ifndef SO100_LS_TOL
+#define SO100_LS_TOL 1e-2f   // line search stops at |phi'| <= LS_TOL |phi'(0)|: MuJoCo's default ls_tolerance (0.01)
+#endif
 #ifndef SO100_ITOL
 #define SO100_ITOL 1e-9f     // predicted-improvement tolerance relative to the cost
 #endif
@@ -248,14 +251,16 @@ __device__ __forceinline__ void cone_ls(const ConeLs& q, float alpha, float& d1,
     const float U = fmaf(alpha, q.V[j], q.U0[j]);
     TT = fmaf(U, U, TT); UV = fmaf(U, q.V[j], UV);
   }
-  const float Tn = sqrtf(TT), mu = q.mu;
+  // 1 / |U| from one MUFU.RSQ (2 ulp): the line search only steers alpha, the residual is evaluated exactly elsewhere
+  const float rT = TT > 0.0f ? rsqrtf(TT) : 0.0f;
+  const float Tn = TT * rT, mu = q.mu;
   if (N >= mu * Tn || (Tn <= 0.0f && N >= 0.0f)) return;
   if (mu * N + Tn <= 0.0f || (Tn <= 0.0f && N < 0.0f)) {
     d1 += fmaf(alpha, q.A2, q.A1);
     d2 += q.A2;
     return;
   }
-  const float Tp = UV / Tn, Tpp = (q.VV - Tp * Tp) / Tn, NmT = N - mu * Tn, dp = q.Np - mu * Tp;
+  const float Tp = UV * rT, Tpp = (q.VV - Tp * Tp) * rT, NmT = N - mu * Tn, dp = q.Np - mu * Tp;
   d1 = fmaf(q.Dm * NmT, dp, d1);
   d2 += q.Dm * (dp * dp - NmT * mu * Tpp);
 }
@@ -432,6 +437,17 @@ template <unsigned LPE, class ES> __device__ __noinline__ float dense_newton_dir
   return pd;
 }
 
+#ifdef SO100_SOLVE_CLOCK
+// development build: SM-cycle split of the last solve (evaluation, gradient, Hessian + factorisation, line search)
+#define SOLVE_CLK_DECL long long clk_[4] = {0, 0, 0, 0}; long long clk_t_ = clock64()
+#define SOLVE_CLK(k) do { const long long now_ = clock64(); clk_[k] += now_ - clk_t_; clk_t_ = now_; } while (0)
+#define SOLVE_CLK_STORE(S) do { if (t.thread_rank() == 0) for (int k_ = 0; k_ < 4; k_++) (S)->clk[k_] = (int)clk_[k_]; } while (0)
+#else
+#define SOLVE_CLK_DECL do { } while (0)
+#define SOLVE_CLK(k) do { } while (0)
+#define SOLVE_CLK_STORE(S) do { } while (0)
+#endif
+
 // Solves for qacc (left in S->a / S->ad, contact forces in S->cfrc).  `diag` (nullable): the env's uint32 counters.
 // Returns the number of Newton iterations.
 template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S, const DevTables& T, uint32_t* diag) {
@@ -483,7 +499,9 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
   bool done = false, last = false, converged = false;
   float Ma = 0, dof_force = 0, cost = 0, cost_qas = 0;
   // one Newton iteration from the iterate / forces of the last evaluation; sets `done` when the solve is over
+  SOLVE_CLK_DECL;
   auto newton_step = [&]() {
+    SOLVE_CLK(0);
     // ---- gradient: M a - qfrc_smooth - J^T f
     float g = 0, jtf = 0;
     if (lane < NV) {
@@ -503,6 +521,7 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
     tsum2(t, gg, ss);
     if (sqrtf(gg) * c_m.inv_scale < SO100_GTOL * (1.0f + sqrtf(ss))) { converged = true; done = true; return; }
     float pd;
+    SOLVE_CLK(1);
     cone_hess_rows(t, S);
     if (!coupled) {
       // ---- block-diagonal Hessian: entries 0..20 arm block, 21..41 cube block
@@ -536,6 +555,7 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
     } else {
       pd = dense_newton_dir(t, S, g);
     }
+    SOLVE_CLK(2);
     // ---- line-search set-up
     float Mp = 0;
     if (lane < NV) Mp = mul_M(S, S->vec, lane);
@@ -567,7 +587,7 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
 #pragma unroll 1
     for (int ls = -1; ls < LS_MAXIT; ls++) {
       if (ls >= 0) {
-        float na = alpha - d1 / d2;
+        float na = alpha - __fdividef(d1, d2);     // approximate division: a safeguarded iterate, not a result
         if (hi >= 0 && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
         alpha = na;
       }
@@ -597,7 +617,7 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
         if (!(d1 < 0)) { descent = false; break; }   // no descent left at float32 resolution
         continue;
       }
-      if (fabsf(d1) <= 1e-4f * d10) break;
+      if (fabsf(d1) <= SO100_LS_TOL * d10) break;
       if (d1 < 0) lo = alpha; else hi = alpha;
     }
     if (!descent) { converged = true; done = true; return; }
@@ -607,6 +627,7 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
     }
     t.sync();
     it++;
+    SOLVE_CLK(3);
     // predicted decrease 1/2 alpha |phi'(0)| below float32 resolution of the cost: stop after refreshing the forces
     // (MuJoCo's "improvement < tolerance" test, made relative because the arithmetic is float32)
     if (0.5f * alpha * d10 < SO100_ITOL * (1.0f + fabsf(cost))) last = true;
@@ -630,6 +651,8 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
       }
     }
   }
+  SOLVE_CLK(0);
+  SOLVE_CLK_STORE(S);
   if (lane == 0 && diag) {
     diag[1] += (converged || last) ? 0u : 1u;
     diag[5] += (uint32_t)it;

@@ -19,7 +19,7 @@ for _ in range(60):
 rows = []
 for _ in range(20):
     sim.substeps(1)
-    st = sim.debug_read(0).view(torch.int32)[:, 57:60].cpu().numpy()
+    st = sim.debug_read(0).view(torch.int32)[:, 57:64].cpu().numpy()
     rows.append(st.copy())
     print("substep: max ns %d (its %d, ncon %d, coupled %d); mean ns %.0f; its>=8: %d" % (
         st[:, 0].max(), st[st[:, 0].argmax(), 1], st[st[:, 0].argmax(), 2] & 255, st[st[:, 0].argmax(), 2] >> 8,
@@ -32,3 +32,11 @@ for it in sorted(set(a[ok, 1].tolist())):
         mm = m & ((a[:, 2] >> 8) == cp)
         if mm.sum():
             print(f"its {it:3d} coupled {cp}: n {mm.sum():6d}  ns mean {a[mm, 0].mean():9.0f}  min {a[mm, 0].min():8d}  max {a[mm, 0].max():8d}")
+
+print("cycle split of multi-iteration solves (per Newton iteration): eval+driver, gradient, Hessian+factor, line search")
+for cp in (0, 1):
+    m = ok & ((a[:, 2] >> 8) == cp) & (a[:, 1] >= 6)
+    if m.sum():
+        per_it = a[m, 3:7] / a[m, 1:2]
+        print(f"coupled {cp}: n {m.sum()}  cycles/iteration", np.round(per_it.mean(axis=0)).astype(int).tolist(),
+              " ns/iteration %.0f" % (a[m, 0] / a[m, 1]).mean())
