@@ -147,6 +147,9 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
   unsigned long long t0_;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0_));
 #endif
+#ifdef SO100_SOLVE_CLOCK
+  if (lane < 4) S->clk2[lane] = 0;
+#endif
   if (ncon_raw <= NCL) iters = solve_env(t, S, state + (size_t)env * STATE_WORDS, w, env, ncon_raw, T, O);
 #ifdef SO100_SOLVE_CLOCK
   // development build: duration (ns) and iteration count of this env's last solve in the spare words of its state record
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
     rec_[58] = __int_as_float(iters);
     rec_[59] = __int_as_float(ncon_raw | (S->coupled << 8));
     for (int k_ = 0; k_ < 4; k_++) rec_[60 + k_] = __int_as_float(S->clk[k_]);
+    rec_[60] = __int_as_float(S->clk2[0]); rec_[61] = __int_as_float(S->clk2[1]); rec_[63] = __int_as_float(S->clk2[2]);   // dense split replaces eval/grad/ls
   }
 #endif
   if (!O.forward && lane == 0) {

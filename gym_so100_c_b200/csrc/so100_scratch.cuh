@@ -117,7 +117,7 @@ template <int NCAP_> struct __align__(16) SolS {
   unsigned char ckind[NCAP_];      // bit 0: contact touches an arm link, bit 1: touches the cube
   int ncon, coupled;
 #ifdef SO100_SOLVE_CLOCK
-  int clk[4];
+  int clk[4], clk2[4];
 #endif
   float J[NCAP_ * 4][JS];
   float T[NCAP_ * 4][JS];          // H_c J_c rows of the current Newton iteration

@@ -378,6 +378,9 @@ template <unsigned LPE, class ES> __device__ __noinline__ float dense_newton_dir
   const int lane = t.thread_rank();
   const int ncon = S->ncon;
   float pd;
+#ifdef SO100_SOLVE_CLOCK
+  long long dc_[5]; dc_[0] = clock64();
+#endif
     // ---- dense 12x12: packed lower triangle in shared memory, tile-parallel Cholesky
     for (int e = lane; e < 78; e += LPE) {
       int i, j;
@@ -397,6 +400,9 @@ template <unsigned LPE, class ES> __device__ __noinline__ float dense_newton_dir
     // right-looking Cholesky with row i of the lower triangle in the registers of lane i: column k is scaled by
     // 1 / L_kk (broadcast from lane k) and every lane fetches the L_jk it needs by shuffle -- no barriers, no
     // shared-memory round trips (the barrier version cost ~3x the latency of this one per coupled Newton iteration)
+#ifdef SO100_SOLVE_CLOCK
+    dc_[1] = clock64();
+#endif
     float a[NV];
 #pragma unroll
     for (int j = 0; j < NV; j++) a[j] = (lane < NV && j <= lane) ? S->H[tri(lane < NV ? lane : 0, j)] : 0.0f;
@@ -411,6 +417,9 @@ template <unsigned LPE, class ES> __device__ __noinline__ float dense_newton_dir
         if (lane >= j) a[j] = fmaf(-lik, ljk, a[j]);
       }
     }
+#ifdef SO100_SOLVE_CLOCK
+    dc_[2] = clock64();
+#endif
     float x = -g;
 #pragma unroll
     for (int k = 0; k < NV; k++) {                 // L y = -g
@@ -434,6 +443,10 @@ template <unsigned LPE, class ES> __device__ __noinline__ float dense_newton_dir
     t.sync();
     if (lane < NV) S->vec[lane] = pd;
     t.sync();
+#ifdef SO100_SOLVE_CLOCK
+  dc_[3] = clock64();
+  if (lane == 0) for (int k_ = 0; k_ < 3; k_++) S->clk2[k_] += (int)(dc_[k_ + 1] - dc_[k_]);
+#endif
   return pd;
 }
 
