@@ -110,7 +110,7 @@ template <int NCAP_> struct __align__(16) SolS {
   float vec[NV];                   // gradient -> search direction
   float H[80];                     // packed Hessian (block diagonal: 42 entries, dense: 78)
   float con[NCAP_][CON_WORDS];     // image of the workspace contact list
-  float cD[NCAP_][4], caref[NCAP_][4], cmu[NCAP_];
+  float cD[NCAP_][4], caref[NCAP_][4], cmu[NCAP_], cDm[NCAP_];
   float cfrc[NCAP_][4];
   float cH[NCAP_][10];
   unsigned char czone[NCAP_];

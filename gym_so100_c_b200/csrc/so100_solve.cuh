@@ -107,6 +107,10 @@ template <unsigned LPE, class ES> __device__ void make_contact_rows(const Tile<L
     S->cD[c][2] = 1.0f / R1;
     S->cD[c][3] = (P.f1 * P.f1) / (R1 * P.f0 * P.f0);
     S->cmu[c] = P.f0 * rs_imp;                 // friction[0] * sqrt(R1 / R0)
+    {
+      const float mu = P.f0 * rs_imp;
+      S->cDm[c] = (1.0f / R0) / fmaxf(mu * mu * (1.0f + mu * mu), 1e-15f);   // middle-zone stiffness
+    }
     S->caref[c][0] = -P.K * imp * dist;
     S->caref[c][1] = S->caref[c][2] = S->caref[c][3] = 0.0f;
   }
@@ -156,7 +160,7 @@ template <unsigned LPE, class ES> __device__ void make_contact_rows(const Tile<L
 }
 
 // elliptic cone: cost, force and (when hess) the 4x4 Hessian block, packed lower triangle
-__device__ __forceinline__ float cone_eval(bool hess, const float* x, const float* D, float mu, float f0, float f1, int dim,
+__device__ __forceinline__ float cone_eval(bool hess, const float* x, const float* D, float Dm, float mu, float f0, float f1, int dim,
                                            float* force, int& zone, float* Hc) {
   const float fr[3] = {f0, f0, f1};
   float U[4];
@@ -164,7 +168,8 @@ __device__ __forceinline__ float cone_eval(bool hess, const float* x, const floa
   float TT = 0;
 #pragma unroll
   for (int j = 1; j < 4; j++) { U[j] = (j < dim) ? x[j] * fr[j - 1] : 0.0f; TT = fmaf(U[j], U[j], TT); }
-  const float Tn = sqrtf(TT), N = U[0];
+  const float invT = TT > 0.0f ? rsqrtf(TT) : 0.0f;
+  const float Tn = TT * invT, N = U[0];
   if (N >= mu * Tn || (Tn <= 0.0f && N >= 0.0f)) {
     zone = 0;
 #pragma unroll
@@ -189,8 +194,7 @@ __device__ __forceinline__ float cone_eval(bool hess, const float* x, const floa
     return cost;
   }
   zone = 2;
-  const float Dm = D[0] / fmaxf(mu * mu * (1.0f + mu * mu), 1e-15f);
-  const float NmT = N - mu * Tn, invT = 1.0f / Tn;
+  const float NmT = N - mu * Tn;
   force[0] = -Dm * NmT * mu;
 #pragma unroll
   for (int j = 1; j < 4; j++) force[j] = (j < dim) ? -force[0] * invT * U[j] * fr[j - 1] : 0.0f;
@@ -225,8 +229,8 @@ struct ConeLs {
   float Dm, mu;
 };
 
-__device__ __forceinline__ void cone_ls_prepare(const float* x0, const float* v, const float* D, float mu, float f0, float f1, int dim,
-                                                ConeLs& q) {
+__device__ __forceinline__ void cone_ls_prepare(const float* x0, const float* v, const float* D, float Dm, float mu, float f0, float f1,
+                                                int dim, ConeLs& q) {
   const float fr[3] = {f0, f0, f1};
   q.mu = mu;
   q.N0 = x0[0] * mu; q.Np = v[0] * mu;
@@ -239,7 +243,7 @@ __device__ __forceinline__ void cone_ls_prepare(const float* x0, const float* v,
     q.VV = fmaf(q.V[j - 1], q.V[j - 1], q.VV);
     q.A1 = fmaf(dj * x0[j], v[j], q.A1); q.A2 = fmaf(dj * v[j], v[j], q.A2);
   }
-  q.Dm = D[0] / fmaxf(mu * mu * (1.0f + mu * mu), 1e-15f);
+  q.Dm = Dm;
 }
 
 // first / second directional derivative of the cone cost at x0 + alpha v
@@ -290,13 +294,18 @@ __device__ __forceinline__ float eval_cost(const Tile<LPE>& t, ES* S, SolveRegs<
     Ma = mul_M(S, S->a, lane);
     cost = 0.5f * ad * Ma - ad * r.qfs;
     // frictionloss row (Huber)
-    float x = ad - r.fr_aref, rf = r.fr_R * r.fr_fl, hd = 0;
-    if (x <= -rf) { cost += r.fr_fl * (-0.5f * rf - x); dof_force = r.fr_fl; }
-    else if (x >= rf) { cost += r.fr_fl * (-0.5f * rf + x); dof_force = -r.fr_fl; }
-    else { cost += 0.5f * r.fr_D * x * x; dof_force = -r.fr_D * x; hd = r.fr_D; }
-    if (r.lim_sgn != 0.0f) {
-      float xl = r.lim_sgn * ad - r.lim_aref;
-      if (xl < 0) { cost += 0.5f * r.lim_D * xl * xl; dof_force += -r.lim_sgn * r.lim_D * xl; hd += r.lim_D; }
+    // selects instead of branches: the 12 dof lanes sit in different Huber zones and would serialise three paths
+    const float x = ad - r.fr_aref, rf = r.fr_R * r.fr_fl, ax = fabsf(x);
+    const bool quad = ax < rf;
+    cost += quad ? 0.5f * r.fr_D * x * x : r.fr_fl * (ax - 0.5f * rf);
+    dof_force = quad ? -r.fr_D * x : copysignf(r.fr_fl, -x);
+    float hd = quad ? r.fr_D : 0.0f;
+    {
+      const float xl = r.lim_sgn * ad - r.lim_aref;       // lim_sgn = 0 (no active limit): lim_D = lim_aref = 0, xl = 0
+      const float dl = xl < 0.0f ? r.lim_D : 0.0f;
+      cost = fmaf(0.5f * dl * xl, xl, cost);
+      dof_force = fmaf(-r.lim_sgn * dl, xl, dof_force);
+      hd += dl;
     }
     if (hess) S->hdiag[lane] = hd;
   }
@@ -308,12 +317,25 @@ __device__ __forceinline__ float eval_cost(const Tile<LPE>& t, ES* S, SolveRegs<
     float xv = 0;
     if (row < nrow) {
       // jar = J a - aref cancels to ~1e-4 of its terms under stiff contacts: accumulate in fp64
+      // two fully unrolled 6-dof blocks (arm / cube), each with two accumulators: all loads in flight at once and
+      // half the dependent DFMA chain of a rolled loop
       const int kind = S->ckind[c];
-      const int d0 = (kind & 1) ? 0 : NL, d1 = (kind & 2) ? NV : NL;
-      double v = -(double)S->caref[c][row & 3];
-#pragma unroll 2
-      for (int d = d0; d < d1; d++) v = fma((double)S->J[row][d], S->ad[d], v);
-      xv = (float)v;
+      double v0 = -(double)S->caref[c][row & 3], v1 = 0.0;
+      if (kind & 1) {
+#pragma unroll
+        for (int d = 0; d < NL; d += 2) {
+          v0 = fma((double)S->J[row][d], S->ad[d], v0);
+          v1 = fma((double)S->J[row][d + 1], S->ad[d + 1], v1);
+        }
+      }
+      if (kind & 2) {
+#pragma unroll
+        for (int d = NL; d < NV; d += 2) {
+          v0 = fma((double)S->J[row][d], S->ad[d], v0);
+          v1 = fma((double)S->J[row][d + 1], S->ad[d + 1], v1);
+        }
+      }
+      xv = (float)(v0 + v1);
     }
     const int qb = lane & ~3;
     float x[4];
@@ -324,7 +346,7 @@ __device__ __forceinline__ float eval_cost(const Tile<LPE>& t, ES* S, SolveRegs<
       int zone;
 #pragma unroll
       for (int k = 0; k < 4; k++) r.jar[s][k] = x[k];
-      cost += cone_eval(hess, x, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], force, zone, Hc);
+      cost += cone_eval(hess, x, S->cD[c], S->cDm[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], force, zone, Hc);
       if (hess) {
 #pragma unroll
         for (int k = 0; k < 4; k++) S->cfrc[c][k] = force[k];
@@ -590,7 +612,7 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
       float jv[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) jv[k] = t.shfl(v, qb + k);
-      if ((lane & 3) == 0 && row < nrow) cone_ls_prepare(r.jar[s], jv, S->cD[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], r.ls[s]);
+      if ((lane & 3) == 0 && row < nrow) cone_ls_prepare(r.jar[s], jv, S->cD[c], S->cDm[c], S->cmu[c], r.f0[s], r.f1[s], r.dim[s], r.ls[s]);
     }
     const float a0 = S->a[lane < NV ? lane : 0];
     const float xf0 = a0 - r.fr_aref, xl0 = r.lim_sgn * a0 - r.lim_aref;
@@ -607,13 +629,13 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
       float e1 = 0, e2 = 0;
       if (lane < NV) {
         const float x = fmaf(alpha, pd, xf0), rf = r.fr_R * r.fr_fl;
-        if (x <= -rf) e1 = -r.fr_fl * pd;
-        else if (x >= rf) e1 = r.fr_fl * pd;
-        else { e1 = r.fr_D * x * pd; e2 = r.fr_D * pd * pd; }
-        if (r.lim_sgn != 0.0f) {
-          const float v = r.lim_sgn * pd, xl = fmaf(alpha, v, xl0);
-          if (xl < 0) { e1 = fmaf(r.lim_D * xl, v, e1); e2 = fmaf(r.lim_D * v, v, e2); }
-        }
+        const bool quad = fabsf(x) < rf;
+        e1 = (quad ? r.fr_D * x : copysignf(r.fr_fl, x)) * pd;
+        e2 = quad ? r.fr_D * pd * pd : 0.0f;
+        const float v = r.lim_sgn * pd, xl = fmaf(alpha, v, xl0);
+        const float dl = xl < 0.0f ? r.lim_D : 0.0f;      // lim_D = 0 without an active limit
+        e1 = fmaf(dl * xl, v, e1);
+        e2 = fmaf(dl * v, v, e2);
       }
       if ((lane & 3) == 0) {
 #pragma unroll
