@@ -576,17 +576,19 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
         S->H[e] = h;
       }
       t.sync();
-      // both blocks factored + solved in registers; lower half-tile: arm, upper half-tile: cube
-      const int hb = lane >= (int)(LPE / 2) ? 1 : 0;
+      // both blocks factored + solved in registers: lanes 0..5 (and 12..) the arm block, lanes 6..11 the cube block, so
+      // that dof lane d already holds its own component of the direction
+      const int hb = (lane >= NL && lane < NV) ? 1 : 0;
       float x[NL];
       chol6_solve<false>(&S->H[21 * hb], &S->vec[NL * hb], -1.0f, x);
-      t.sync();
-      if (lane == 0 || lane == (int)(LPE / 2)) {
+      const int kx = lane - NL * hb;
+      pd = 0.0f;
 #pragma unroll
-        for (int k = 0; k < NL; k++) S->vec[NL * hb + k] = x[k];
-      }
+      for (int k = 0; k < NL; k++) pd = (kx == k) ? x[k] : pd;
+      if (lane >= NV) pd = 0.0f;
+      t.sync();                                  // every lane has read the gradient in S->vec
+      if (lane < NV) S->vec[lane] = pd;
       t.sync();
-      pd = (lane < NV) ? S->vec[lane] : 0.0f;
     } else {
       pd = dense_newton_dir(t, S, g);
     }
@@ -604,9 +606,16 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
       float v = 0;
       if (row < nrow) {
         const int kind = S->ckind[c];
-        const int d0 = (kind & 1) ? 0 : NL, d1 = (kind & 2) ? NV : NL;
-#pragma unroll 2
-        for (int d = d0; d < d1; d++) v = fmaf(S->J[row][d], S->vec[d], v);
+        float v1 = 0;
+        if (kind & 1) {
+#pragma unroll
+          for (int d = 0; d < NL; d += 2) { v = fmaf(S->J[row][d], S->vec[d], v); v1 = fmaf(S->J[row][d + 1], S->vec[d + 1], v1); }
+        }
+        if (kind & 2) {
+#pragma unroll
+          for (int d = NL; d < NV; d += 2) { v = fmaf(S->J[row][d], S->vec[d], v); v1 = fmaf(S->J[row][d + 1], S->vec[d + 1], v1); }
+        }
+        v += v1;
       }
       const int qb = lane & ~3;
       float jv[4];
