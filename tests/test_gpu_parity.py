@@ -257,6 +257,77 @@ def test_groups_and_graph_replay_are_bit_invariant(model_blob, monkeypatch):
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("n", [1, 3, 37])
+def test_small_and_ragged_batches_match_the_oracle(model_blob, n):
+    """BASELINE config 1 (a single env) and batch sizes that do not fill a block / tile group: full env.step parity."""
+    import torch
+    rng = np.random.default_rng(100 + n)
+    sim, orc = make_pair(model_blob, n, task=0, seed=21)
+    orc.reset(); sim.reset()
+    a_start = np.array([0, 0.35089, -0.19493, 0, 0, -0.79585])
+    for k in range(4):
+        act = (a_start + rng.uniform(-0.08, 0.08, size=(n, 6))).astype(np.float32)
+        out_o = orc.step(act, autoreset=False)
+        obs, rew, term, trunc, succ = sim.step(torch.tensor(act), autoreset=False)
+        assert obs.shape == (n, 15)
+        assert np.abs(obs.cpu().numpy() - out_o["obs"]).max() < 1e-4, k
+        assert np.array_equal(rew.cpu().numpy(), out_o["reward"])
+    sim.close(); orc.close()
+
+
+def test_full_size_batch_invariants(model_blob):
+    """BASELINE config 3 at its full size (16384 envs, random actions, auto-reset): properties that do not need the oracle.
+    Finite state, unit cube quaternion, joints inside their limits up to the soft-constraint give, the cube never
+    tunnels through the table, rewards from the staged set, bounded contact-list overflow, and the same call repeated on
+    a second handle gives bit-identical results (determinism)."""
+    import torch
+    from gym_so100_c_b200 import model
+    from gym_so100_c_b200.engine import BatchedSim
+    n = 16384
+    m = model.unpack(model_blob)
+    lo, hi = np.array(m["dof_range"][:6, 0]), np.array(m["dof_range"][:6, 1])
+    g = torch.Generator(device="cuda").manual_seed(77)
+    acts = torch.rand((25, n, 6), device="cuda", generator=g) * 2 - 1
+    finals = []
+    for rep in range(2):
+        sim = BatchedSim(n, device="cuda:0", task=0, seed=1234, model_blob=model_blob)
+        sim.reset()
+        rewards = set()
+        for k in range(25):
+            obs, rew, term, trunc, succ = sim.step(acts[k], autoreset=True)
+            rewards |= set(np.unique(rew.cpu().numpy()).tolist())
+        qpos, qvel, ctrl, warm = [t.cpu().numpy() for t in sim.get_state()]
+        d = sim.diagnostics()
+        finals.append((qpos, qvel))
+        sim.close()
+        assert np.isfinite(qpos).all() and np.isfinite(qvel).all()
+        assert np.abs(np.linalg.norm(qpos[:, 9:13], axis=1) - 1).max() < 1e-5
+        assert (qpos[:, :6] > lo - 0.05).all() and (qpos[:, :6] < hi + 0.05).all()
+        assert qpos[:, 8].min() > 0.0                         # cube centre stays above the table top (z = 0)
+        assert rewards <= {0.0, 1.0, 2.0, 2.5, 3.0, 4.0}
+        assert d["nonfinite_resets"] == 0 and d["contact_overflow"] <= n * 25 // 1000 and d["solver_runs"] == n * 250
+        assert d["solver_cap_hits"] <= d["solver_runs"] // 100000
+    assert np.array_equal(finals[0][0], finals[1][0]) and np.array_equal(finals[0][1], finals[1][1])
+
+
+def test_goal_env_full_size_smoke(model_blob):
+    """BASELINE config 4 shape: 65536 GoalEnv envs, dict observation pieces and the HER reward on a 4x relabel batch."""
+    import torch
+    from gym_so100_c_b200.engine import BatchedSim
+    n = 65536
+    sim = BatchedSim(n, device="cuda:0", task=1, seed=5, model_blob=model_blob)
+    sim.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for k in range(3):
+        obs, rew, term, trunc, succ = sim.step(torch.rand((n, 6), device="cuda", generator=g) * 2 - 1, autoreset=True)
+    assert set(np.unique(rew.cpu().numpy()).tolist()) <= {0.0, -1.0}
+    r = sim.compute_reward(sim.achieved.repeat(4, 1), sim.desired.repeat(4, 1))
+    live = ~(term.bool() | trunc.bool())           # auto-reset envs already show the next episode's goals
+    assert r.shape == (4 * n,) and torch.equal(r[:n][live], rew[live])      # the true goal reproduces the step reward
+    assert torch.isfinite(sim.obs).all() and torch.isfinite(sim.achieved).all()
+    sim.close()
+
+
 def test_reset_sampling_bit_exact(model_blob):
     """On-device Philox cube placement == the oracle's, bit for bit, and independent of sharding."""
     import torch
