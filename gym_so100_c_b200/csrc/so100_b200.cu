@@ -26,6 +26,15 @@ static_assert(NC == SO100_MAX_CONTACTS, "contact capacity mismatch");
 #endif
 constexpr unsigned LPE_K1 = SO100_LPE_K1, LPE_K2A = 32, LPE_K2B = 32, LPE_K3L = SO100_LPE_K3L, LPE_K3H = 32, LPE_K4 = 32;
 constexpr int BLOCK = 128, TPB_K3L = SO100_TPB_K3L;
+// grids of the queue-driven persistent kernels (4 tiles per block): large enough for one item per tile in a 2048-env group,
+// small enough that the blocks that find the queue empty do not crowd the SMs (the heavy solve kernel holds 27 k registers
+// and 58 KB of shared memory per block)
+#ifndef SO100_K2B_BLOCKS_PER_SM
+#define SO100_K2B_BLOCKS_PER_SM 2     // and at least n / 8 blocks (one tile per ~2 envs; 0.18 GJK items per env)
+#endif
+#ifndef SO100_K3H_BLOCKS
+#define SO100_K3H_BLOCKS 37           // 148 tiles; a 2048-env group queues 0-10 heavy envs per substep
+#endif
 enum { CLS_KIN = 0, CLS_BOX = 1, CLS_SOLVE = 2, CLS_TASK = 3, CLS_HULL = 4, CLS_HEAVY = 5, CLS_N = 6 };
 
 static thread_local std::string g_err;
@@ -45,6 +54,7 @@ struct EnvGroup {
   cudaStream_t st = nullptr, side = nullptr;            // st == nullptr: the caller's stream
   cudaEvent_t fork = nullptr, join = nullptr, done = nullptr;
   cudaEvent_t t_done = nullptr;                         // timing-enabled twin of `done` (so100_group_times)
+  cudaEvent_t staged = nullptr;                         // recorded after the group's first position stage of a step (stagger)
   int* ctl = nullptr;                                   // this group's queue control words
   int* order = nullptr;                                 // two longest-first permutations of the group's envs, [2][n_total] apart
   int parity = 0;                                       // which of the two the next solve stage reads
@@ -75,6 +85,10 @@ struct so100_ctx {
   std::vector<EnvGroup> groups;
   cudaEvent_t ev_start = nullptr, t_start = nullptr;
   bool group_times = false, capturing = false;   // SO100_GROUP_TIMES=1: per-group completion times of the last step
+  // Groups that start a step together stay in phase (all in the solve bulk, then all in its tail) and overlap little;
+  // stagger = 1 starts every odd group only after its even neighbour has finished its first position stage, so that the
+  // two are about a third of a substep apart for the rest of the step; 2 chains all groups that way.
+  int stagger = 0;   // measured on B200: 1 and 2 are 1-9 % slower than 0 at 4096 / 16384 / 65536 envs (the groups drift apart on their own)
   int sm_count = 148;
   bool timing = false;        // so100_phase_timing: CUDA-event pairs around every phase-kernel launch
   std::vector<std::pair<cudaEvent_t, int>> events;   // (event, kernel class) begin markers, class -1 = end marker
@@ -359,7 +373,7 @@ static void launch_position_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, co
   mark(h, st, CLS_KIN, false); mark(h, st, CLS_BOX, true);
   phase_collide_box<LPE_K2A><<<grid_of(n, LPE_K2A), BLOCK, smem_of<BoxS>(LPE_K2A), st>>>(work, n, T, Q);
   mark(h, st, CLS_BOX, false); mark(h, st, CLS_HULL, true);
-  phase_collide_hull<LPE_K2B><<<std::min(grid_of(n, LPE_K2B), h->sm_count * 8), BLOCK, smem_of<HullS>(LPE_K2B), st>>>(work, T, Q);
+  phase_collide_hull<LPE_K2B><<<std::min(grid_of(n, LPE_K2B), std::max(h->sm_count * SO100_K2B_BLOCKS_PER_SM, n / 8)), BLOCK, smem_of<HullS>(LPE_K2B), st>>>(work, T, Q);
   mark(h, st, CLS_HULL, false);
 }
 
@@ -375,7 +389,7 @@ static void launch_solve_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const
   cudaEventRecord(G.fork, st);
   cudaStreamWaitEvent(G.side, G.fork, 0);
   mark(h, G.side, CLS_HEAVY, true);
-  phase_solve_heavy<LPE_K3H><<<std::min(grid_of(n, LPE_K3H), h->sm_count * 2), BLOCK, smem_of<SolS<NC>>(LPE_K3H), G.side>>>(state, work, T, Q, O);
+  phase_solve_heavy<LPE_K3H><<<std::min(grid_of(n, LPE_K3H), SO100_K3H_BLOCKS), BLOCK, smem_of<SolS<NC>>(LPE_K3H), G.side>>>(state, work, T, Q, O);
   mark(h, G.side, CLS_HEAVY, false);
   cudaEventRecord(G.join, G.side);
   mark(h, st, CLS_SOLVE, true);
@@ -399,6 +413,7 @@ static int make_group(so100_ctx* h, EnvGroup& G, int off, int n, int index, bool
   CUDA_OK(cudaEventCreateWithFlags(&G.join, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&G.t_done));
+  CUDA_OK(cudaEventCreateWithFlags(&G.staged, cudaEventDisableTiming));
   return SO100_OK;
 }
 static void free_group(EnvGroup& G) {
@@ -408,6 +423,7 @@ static void free_group(EnvGroup& G) {
   if (G.join) cudaEventDestroy(G.join);
   if (G.done) cudaEventDestroy(G.done);
   if (G.t_done) cudaEventDestroy(G.t_done);
+  if (G.staged) cudaEventDestroy(G.staged);
 }
 
 // Runs `body(group, stream)` for every env group: on the groups' own streams, forked from and joined back into `st`,
@@ -416,8 +432,10 @@ template <class F> static void for_each_group(so100_ctx* h, cudaStream_t st, boo
   if (!allow_groups || h->timing || h->groups.size() < 2) { body(h->whole, st); return; }
   cudaEventRecord(h->ev_start, st);
   if (h->group_times) cudaEventRecordWithFlags(h->t_start, st, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
-  for (EnvGroup& G : h->groups) {
+  for (size_t gi = 0; gi < h->groups.size(); gi++) {
+    EnvGroup& G = h->groups[gi];
     cudaStreamWaitEvent(G.st, h->ev_start, 0);
+    if (gi > 0 && (h->stagger == 2 || (h->stagger == 1 && (gi & 1)))) cudaStreamWaitEvent(G.st, h->groups[gi - 1].staged, 0);
     body(G, G.st);
     if (h->group_times) cudaEventRecordWithFlags(G.t_done, G.st, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
     cudaEventRecord(G.done, G.st);
@@ -468,6 +486,7 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->t_start));
   if (const char* e = getenv("SO100_GROUP_TIMES")) h->group_times = atoi(e) != 0;
+  if (const char* e = getenv("SO100_STAGGER")) h->stagger = atoi(e);
   CUDA_OK(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
   CUDA_OK(cudaMalloc(&h->act_stage, (size_t)num_envs * 6 * sizeof(float)));
   if (const char* e = getenv("SO100_GRAPH")) h->use_graph = atoi(e) != 0;
@@ -549,6 +568,7 @@ static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream) {
     const SolveOut O{nullptr, nullptr, 0};
     for (int s = 0; s < h->nsub; s++) {
       launch_position_stage(h, G, st, s == 0 ? action : nullptr, 1);
+      if (s == 0) cudaEventRecord(G.staged, st);
       launch_solve_stage(h, G, st, O);
     }
     // trailing mj_step1 (dm_control's legacy step): positions + contacts of the new state, then the task layer
@@ -680,6 +700,7 @@ int so100_substeps(so100_handle h, int nsub, void* stream) {
     const SolveOut O{nullptr, nullptr, 0};
     for (int s = 0; s < nsub; s++) {
       launch_position_stage(h, G, st, nullptr, 1);
+      if (s == 0) cudaEventRecord(G.staged, st);
       launch_solve_stage(h, G, st, O);
     }
   });
