@@ -719,6 +719,19 @@ int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom,
   return SO100_OK;
 }
 
+#ifdef SO100_HULL_CLOCK
+// development build: copy out and clear the GJK/EPA item statistics; returns the number of items recorded
+int so100_hull_stats(int32_t* out /* host [65536][4] */) {
+  int n = 0;
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpyFromSymbol(&n, g_hull_stat_n, sizeof(int)));
+  CUDA_OK(cudaMemcpyFromSymbol(out, g_hull_stat, sizeof(int) * 4 * 65536));
+  const int zero = 0;
+  CUDA_OK(cudaMemcpyToSymbol(g_hull_stat_n, &zero, sizeof(int)));
+  return n;
+}
+#endif
+
 int so100_group_times(so100_handle h, float* ms, int32_t* ngroups, void* stream) {
   if (!h || !ms || !ngroups) return fail(SO100_ERR_ARG, "so100_group_times: bad argument");
   *ngroups = 0;

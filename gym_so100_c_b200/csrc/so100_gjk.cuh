@@ -170,6 +170,9 @@ struct EpaScratch {
   unsigned char owner[EPA_MAXV][EPA_MAXV];  // face owning the directed edge a -> b
   unsigned char hedge[EPA_MAXF][2];
   unsigned char freed[EPA_MAXF];
+#ifdef SO100_HULL_CLOCK
+  int dbg[2];
+#endif
 };
 
 __device__ __forceinline__ void epa_make_face(EpaScratch* E, int slot, int i, int j, int k) {
@@ -187,6 +190,12 @@ __device__ __forceinline__ void epa_make_face(EpaScratch* E, int slot, int i, in
   E->fv[slot][3] = 1;
 }
 
+#ifdef SO100_HULL_CLOCK
+// development build: per GJK/EPA item (ns, GJK iterations, EPA iterations, hull vertices), ring buffer of 65536 items
+__device__ int g_hull_stat[65536][4];
+__device__ int g_hull_stat_n;
+#endif
+
 // Penetration of A into B.  On a hit: normal (A -> B), depth > 0, contact point (midpoint of the
 // witness points).  All lanes return the same values.
 template <unsigned LPE>
@@ -200,13 +209,18 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
   s[0] = msupport(t, A, B, dir, vert);
   dir = -s[0].w;
   bool hit = false;
+  int gjk_its_ = 0;
   for (int it = 0; it < 48; it++) {
-    if (dot(dir, dir) < 1e-24f) return false;
+    gjk_its_ = it + 1;
+    if (dot(dir, dir) < 1e-24f) break;
     const MV w = msupport(t, A, B, dir, vert);
-    if (dot(w.w, dir) <= 0) return false;
+    if (dot(w.w, dir) <= 0) break;
     s[n++] = w;
     if (do_simplex(s, n, dir)) { hit = true; break; }
   }
+#ifdef SO100_HULL_CLOCK
+  E->dbg[0] = gjk_its_; E->dbg[1] = 0;
+#endif
   if (!hit) return false;
   // ---- EPA
   t.sync();
@@ -227,6 +241,9 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
   for (int k = 0; k < 4; k++) degenerate |= (E->fv[k][3] == 0);
   if (degenerate) return false;   // flat tetrahedron: touching
   for (int it = 0; it < EPA_MAXV - 4; it++) {
+#ifdef SO100_HULL_CLOCK
+    if (lane == 0) E->dbg[1] = it + 1;
+#endif
     // closest face (ties -> lowest slot)
     float bd = 3.0e38f; int bf = 0x7fffffff;
     for (int f = lane; f < nface; f += LPE)
@@ -405,11 +422,31 @@ template <unsigned LPE> __device__ int collide_hull_item(const Tile<LPE>& t, Hul
   V3 n = mk(0, 0, 1), pos = mk(0, 0, 0);
   float depth = 0;
   int pid = -1;
+#ifdef SO100_HULL_CLOCK
+  unsigned long long hc0_, hc1_, hc2_;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(hc0_));
+  bool hit_ = gjk_epa(t, A, B, c1, c2, T.vert, reinterpret_cast<EpaScratch*>(S->epa), n, depth, pos);
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(hc1_));
+  if (hit_) {
+    snap_normal(t, A, B, n, depth, T.vert);
+    pos = deepest_feature_point(t, A, B, n, depth, pos, T.vert);
+    pid = p;
+  }
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(hc2_));
+  t.sync();
+  if (lane == 0) {
+    const int k_ = atomicAdd(&g_hull_stat_n, 1) & 65535;
+    const EpaScratch* E_ = reinterpret_cast<const EpaScratch*>(S->epa);
+    g_hull_stat[k_][0] = (int)(hc1_ - hc0_); g_hull_stat[k_][1] = (int)(hc2_ - hc1_);
+    g_hull_stat[k_][2] = E_->dbg[0] | (E_->dbg[1] << 8) | ((int)hit_ << 16); g_hull_stat[k_][3] = A.vnum + B.vnum;
+  }
+#else
   if (gjk_epa(t, A, B, c1, c2, T.vert, reinterpret_cast<EpaScratch*>(S->epa), n, depth, pos)) {
     snap_normal(t, A, B, n, depth, T.vert);
     pos = deepest_feature_point(t, A, B, n, depth, pos, T.vert);
     pid = p;
   }
+#endif
   int* hdr = reinterpret_cast<int*>(w + W_HDR);
   int last = 0;
   if (lane == 0) {
