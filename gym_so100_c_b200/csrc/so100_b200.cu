@@ -513,8 +513,13 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   if (!verts.empty()) CUDA_OK(cudaMemcpy(h->vert, verts.data(), verts.size() * sizeof(float4), cudaMemcpyHostToDevice));
   {
     std::vector<uchar4> bp(pairs.size());
-    for (size_t p = 0; p < pairs.size(); p++)
-      bp[p] = make_uchar4((unsigned char)pairs[p].g1, (unsigned char)pairs[p].g2, (unsigned char)pairs[p].mode, (unsigned char)pairs[p].dim);
+    for (size_t p = 0; p < pairs.size(); p++) {
+      // bit 7 of the mode byte: a contact of this pair couples an arm link with the cube (dense 12x12 Hessian)
+      const int l1 = pairs[p].l1, l2 = pairs[p].l2;
+      const bool couples = (l1 >= 0 && l1 < NL && l2 == NL) || (l2 >= 0 && l2 < NL && l1 == NL);
+      bp[p] = make_uchar4((unsigned char)pairs[p].g1, (unsigned char)pairs[p].g2, (unsigned char)(pairs[p].mode | (couples ? PAIR_COUPLES : 0)),
+                          (unsigned char)pairs[p].dim);
+    }
     CUDA_OK(cudaMalloc(&h->bpair, bp.size() * sizeof(uchar4)));
     CUDA_OK(cudaMemcpy(h->bpair, bp.data(), bp.size() * sizeof(uchar4), cudaMemcpyHostToDevice));
   }

@@ -239,7 +239,8 @@ __device__ int box_contacts(const Tile<LPE>& t, float* con, int base, const Obb&
 }
 
 // Stage A for one env.  Writes the contact list and the header of workspace record `w`; returns (on every lane)
-// the number of hull pairs that need GJK/EPA, with *ncon_out the contact count so far (NC + 1 = overflow).
+// the number of hull pairs that need GJK/EPA, with *ncon_out the contact count so far (NC + 1 = overflow, NC + 2 = an
+// arm-cube contact exists: the env belongs to the heavy solve kernel).
 //   1. world bounds of the 25 collidable geoms (one lane each): centre + bounding radius, AABB half extents;
 //   2. broad phase over the static 191-pair table (one lane per pair): sphere-sphere and AABB-AABB; any
 //      conservative filter gives the same contacts, because every survivor goes through the exact test of 3;
@@ -286,7 +287,7 @@ template <unsigned LPE> __device__ int collide_box_env(const Tile<LPE>& t, BoxS*
     if (k < ncand) {
       p = S->qc[k];
       const uchar4 bp = T.bpair[p];
-      hull = bp.z == MODE_HULL;
+      hull = (bp.z & 0x7f) == MODE_HULL;
       const float4 c1 = S->gbox[bp.x], c2 = S->gbox[bp.y];
       Obb A, B;
       load_obb(S->f, T.geom[bp.x], mk(c1.x, c1.y, c1.z), A);
@@ -311,7 +312,7 @@ template <unsigned LPE> __device__ int collide_box_env(const Tile<LPE>& t, BoxS*
     nsurv += __popc(mh);
   }
   t.sync();
-  int ncon = 0;
+  int ncon = 0, coupled = 0;
   for (int k = 0; k < min(npen, NPEN); k++) {
     const int p = S->q1[k];
     const uchar4 bp = T.bpair[p];
@@ -319,14 +320,15 @@ template <unsigned LPE> __device__ int collide_box_env(const Tile<LPE>& t, BoxS*
     Obb A, B;
     load_obb(S->f, T.geom[bp.x], mk(c1.x, c1.y, c1.z), A);
     load_obb(S->f, T.geom[bp.y], mk(c2.x, c2.y, c2.z), B);
-    const int nc = box_contacts(t, con, ncon, A, B, (int)S->qcode[k], S->qsep[k], bp.z == MODE_BOX_SINGLE, p);
+    const int nc = box_contacts(t, con, ncon, A, B, (int)S->qcode[k], S->qsep[k], (bp.z & 0x7f) == MODE_BOX_SINGLE, p);
+    if (nc > 0 && (bp.z & PAIR_COUPLES)) coupled = HDR_COUPLED;
     ncon = min(ncon + nc, NC + 1);   // NC + 1 marks overflow
   }
   // more penetrating box pairs / hull pairs than the lists hold: counted as a contact overflow
   if (npen > NPEN || nsurv > NHP) { ncon = NC + 1; nsurv = min(nsurv, NHP); }
   if (lane == 0)
-    *reinterpret_cast<int4*>(w + W_HDR) = make_int4(ncon, nsurv, min(nbox, 255) | (min(npen, 255) << 8) | (min(ncand - nbox, 255) << 16), nsurv);
-  *ncon_out = ncon;
+    *reinterpret_cast<int4*>(w + W_HDR) = make_int4(ncon, nsurv, min(nbox, 255) | (min(npen, 255) << 8) | (min(ncand - nbox, 255) << 16) | coupled, nsurv);
+  *ncon_out = coupled ? NC + 2 : ncon;    // a coupling contact sends the env to the heavy solve kernel whatever its count
   return nsurv;
 }
 

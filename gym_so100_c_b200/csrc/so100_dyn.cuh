@@ -156,15 +156,13 @@ template <unsigned LPE> __device__ void smooth_forces(const Tile<LPE>& t, KinS* 
   t.sync();
 }
 
-// In-register Cholesky solve of a 6x6 SPD block (FULL: row-major 6x6, else packed lower triangle): x = sign * A^-1 b
-template <bool FULL> __device__ __forceinline__ void chol6_solve(const float* A, const float* b6, float sign, float* x) {
-  float L[21];
+// In-register Cholesky of a 6x6 SPD block (FULL: row-major 6x6, else packed lower triangle): L[tri(i, j)] for i > j and
+// 1 / L_jj on the diagonal
+template <bool FULL> __device__ __forceinline__ void chol6_factor(const float* A, float* L) {
 #pragma unroll
   for (int i = 0; i < NL; i++)
 #pragma unroll
     for (int j = 0; j <= i; j++) L[tri(i, j)] = FULL ? A[i * NL + j] : A[tri(i, j)];
-#pragma unroll
-  for (int i = 0; i < NL; i++) x[i] = sign * b6[i];
 #pragma unroll
   for (int j = 0; j < NL; j++) {
     float d = L[tri(j, j)];
@@ -180,6 +178,9 @@ template <bool FULL> __device__ __forceinline__ void chol6_solve(const float* A,
       L[tri(i, j)] = s * d;
     }
   }
+}
+// x <- L^-1 x
+__device__ __forceinline__ void chol6_fwd(const float* L, float* x) {
 #pragma unroll
   for (int i = 0; i < NL; i++) {
     float s = x[i];
@@ -187,6 +188,9 @@ template <bool FULL> __device__ __forceinline__ void chol6_solve(const float* A,
     for (int k = 0; k < i; k++) s = fmaf(-L[tri(i, k)], x[k], s);
     x[i] = s * L[tri(i, i)];
   }
+}
+// x <- L^-T x
+__device__ __forceinline__ void chol6_bwd(const float* L, float* x) {
 #pragma unroll
   for (int i = NL - 1; i >= 0; i--) {
     float s = x[i];
@@ -194,6 +198,15 @@ template <bool FULL> __device__ __forceinline__ void chol6_solve(const float* A,
     for (int k = i + 1; k < NL; k++) s = fmaf(-L[tri(k, i)], x[k], s);
     x[i] = s * L[tri(i, i)];
   }
+}
+// x = sign * A^-1 b
+template <bool FULL> __device__ __forceinline__ void chol6_solve(const float* A, const float* b6, float sign, float* x) {
+  float L[21];
+  chol6_factor<FULL>(A, L);
+#pragma unroll
+  for (int i = 0; i < NL; i++) x[i] = sign * b6[i];
+  chol6_fwd(L, x);
+  chol6_bwd(L, x);
 }
 
 // qacc_smooth = M^-1 qfrc_smooth into S->d.qas: lane 0 factors the 6x6 arm block in registers, the cube block is diagonal

@@ -407,8 +407,8 @@ __device__ V3 deepest_feature_point(const Tile<LPE>& t, const Shape& A, const Sh
 
 // Stage B, one queue item = one hull pair of one env: GJK/EPA with the whole tile; the result goes to the pair's
 // staging slot.  The tile that finishes an env's last pending pair merges the staged contacts into the contact list
-// in pair order (deterministic contact order, after the box contacts) and returns the final count; every other tile
-// returns -1.
+// in pair order (deterministic contact order, after the box contacts) and returns the final count (NC + 2 when an arm-cube
+// contact exists); every other tile returns -1.
 template <unsigned LPE> __device__ int collide_hull_item(const Tile<LPE>& t, HullS* S, float* w, int slot, const DevTables& T) {
   const int lane = t.thread_rank();
   const int p = reinterpret_cast<const unsigned char*>(w + W_HULLP)[slot];
@@ -471,8 +471,12 @@ template <unsigned LPE> __device__ int collide_hull_item(const Tile<LPE>& t, Hul
     dst[0] = q0; dst[1] = q1;
   }
   const int ncon = min(nbox + __popc(m), NC + 1);
-  if (lane == 0) hdr[0] = ncon;
-  return ncon;
+  const bool couples = t.any(valid && (T.bpair[valid ? __float_as_int(q1.w) : 0].z & PAIR_COUPLES)) || (hdr[2] & HDR_COUPLED);
+  if (lane == 0) {
+    hdr[0] = ncon;
+    if (couples) hdr[2] |= HDR_COUPLED;
+  }
+  return couples ? NC + 2 : ncon;
 }
 
 }  // namespace so100

@@ -6,7 +6,7 @@
 //                 K2a phase_collide_box   broad phase, box SAT + clipping, hull-pair cull   work  -> work (+ hull queue)
 //                 K2b phase_collide_hull  GJK/EPA for queued envs (~14 % of envs)           work  -> work (+ heavy queue)
 //                 K3l phase_solve_light   contact rows, Newton, Euler; envs <= 8 contacts   state, work -> state
-//                 K3h phase_solve_heavy   the same for queued envs with 9..24 contacts
+//                 K3h phase_solve_heavy   the same for queued envs with 9..24 contacts or an arm-cube contact (dense Hessian)
 //   per step:     K1 (kinematics only) + K2a + K2b + K4 phase_task (reward / flags / obs / auto-reset)
 //
 // Why not one fused kernel: ncu on the fused step (profiles/r01_fused_step_ncu.txt) showed it to be instruction-fetch
@@ -107,7 +107,7 @@ struct SolveOut {
   int forward;       // 0: integrate and store the state (the step path)
 };
 
-template <unsigned LPE, class ES>
+template <bool DENSE, unsigned LPE, class ES>
 __device__ int solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w, int env, int ncon_raw, const DevTables& T,
                          const SolveOut& O) {
   const int lane = t.thread_rank();
@@ -120,7 +120,7 @@ __device__ int solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w, 
   if (lane == 0) S->ncon = ncon;
   t.sync();
   make_contact_rows(t, S, T);
-  const int iters = solve(t, S, T, O.forward ? nullptr : reinterpret_cast<uint32_t*>(rec + S_DIAG));
+  const int iters = solve<DENSE>(t, S, T, O.forward ? nullptr : reinterpret_cast<uint32_t*>(rec + S_DIAG));
   if (O.forward) {
     t.sync();
     if (O.qacc && lane < NV) O.qacc[(size_t)env * NV + lane] = S->a[lane];
@@ -133,7 +133,7 @@ __device__ int solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w, 
   return iters;
 }
 
-// K3l: regular grid, one tile per env; envs with more than NCL contacts are left to K3h
+// K3l: regular grid, one tile per env; envs with more than NCL contacts or an arm-cube contact are left to K3h
 template <unsigned LPE>
 __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TPB_K3L) phase_solve_light(float* state, const float* work, int n, DevTables T, Queues Q, SolveOut O) {
   SO100_TILE_PROLOGUE(LPE, SO100_TPB_K3L, SolS<NCL>);
@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
   if (slot >= n) return;
   const int env = Q.order_in[slot];
   const float* w = work + (size_t)env * WORK_WORDS;
-  const int ncon_raw = __float_as_int(w[W_HDR]);
+  const int4 hdr = *reinterpret_cast<const int4*>(w + W_HDR);
+  const int ncon_raw = (hdr.z & HDR_COUPLED) ? NC + 2 : hdr.x;      // arm-cube contacts: heavy kernel (dense Hessian)
   int iters = 1000;                          // heavy envs count as slow
 #ifdef SO100_SOLVE_CLOCK
   unsigned long long t0_;
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
 #ifdef SO100_SOLVE_CLOCK
   if (lane < 4) S->clk2[lane] = 0;
 #endif
-  if (ncon_raw <= NCL) iters = solve_env(t, S, state + (size_t)env * STATE_WORDS, w, env, ncon_raw, T, O);
+  if (ncon_raw <= NCL) iters = solve_env<false>(t, S, state + (size_t)env * STATE_WORDS, w, env, ncon_raw, T, O);
 #ifdef SO100_SOLVE_CLOCK
   // development build: duration (ns) and iteration count of this env's last solve in the spare words of its state record
   unsigned long long t1_;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(128) phase_solve_heavy(float* state, const flo
     if (i >= count) break;
     const int env = Q.heavy[i];
     const float* w = work + (size_t)env * WORK_WORDS;
-    solve_env(t, S, state + (size_t)env * STATE_WORDS, w, env, __float_as_int(w[W_HDR]), T, O);
+    solve_env<true>(t, S, state + (size_t)env * STATE_WORDS, w, env, __float_as_int(w[W_HDR]), T, O);
     t.sync();
   }
 }

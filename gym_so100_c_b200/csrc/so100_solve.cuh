@@ -394,16 +394,16 @@ template <class ES> __device__ __forceinline__ float hess_contact(const ES* S, i
 }
 
 // Newton direction -H^-1 g for a Hessian that couples the arm and the cube (a contact between them): dense 12x12.
-// Kept out of line: it is taken by < 1 % of the solves and its unrolled register Cholesky is ~1.5 k instructions that
-// would otherwise sit in the middle of the hot loop's instruction stream.
-template <unsigned LPE, class ES> __device__ __noinline__ float dense_newton_dir(const Tile<LPE>& t, ES* S, float g) {
+// Only the heavy solve kernel is compiled with it (solve<DENSE = true>): envs with an arm-cube contact are routed there, so the
+// light kernel's hot loop carries neither this code nor its registers.
+template <unsigned LPE, class ES> __device__ __forceinline__ float dense_newton_dir(const Tile<LPE>& t, ES* S, float g) {
   const int lane = t.thread_rank();
   const int ncon = S->ncon;
   float pd;
 #ifdef SO100_SOLVE_CLOCK
   long long dc_[5]; dc_[0] = clock64();
 #endif
-    // ---- dense 12x12: packed lower triangle in shared memory, tile-parallel Cholesky
+    // ---- dense 12x12 Hessian, packed lower triangle in shared memory
     for (int e = lane; e < 78; e += LPE) {
       int i, j;
       untri(e, i, j);
@@ -411,58 +411,78 @@ template <unsigned LPE, class ES> __device__ __noinline__ float dense_newton_dir
       if (i < NL) h = S->d.Mfull[i][j];
       else if (i == j) h = (i < 9 ? c_m.cube_mass : c_m.cube_I[i - 9]);
       if (i == j) h += S->hdiag[i];
+      // entry (i, j) only sees contacts that touch both its blocks: bit 0 arm, bit 1 cube
+      const int need = (i < NL ? 1 : 2) | (j < NL ? 1 : 2);
+      float h2 = 0;
       for (int c = 0; c < ncon; c++) {
-        const int zone = S->czone[c];
-        if (zone == 0) continue;
-        h += hess_contact(S, c, i, j);
+        if (S->czone[c] == 0 || (S->ckind[c] & need) != need) continue;
+        h += S->J[c * 4 + 0][i] * S->T[c * 4 + 0][j] + S->J[c * 4 + 1][i] * S->T[c * 4 + 1][j];
+        h2 += S->J[c * 4 + 2][i] * S->T[c * 4 + 2][j] + S->J[c * 4 + 3][i] * S->T[c * 4 + 3][j];
       }
-      S->H[e] = h;
+      S->H[e] = h + h2;
     }
     t.sync();
-    // right-looking Cholesky with row i of the lower triangle in the registers of lane i: column k is scaled by
-    // 1 / L_kk (broadcast from lane k) and every lane fetches the L_jk it needs by shuffle -- no barriers, no
-    // shared-memory round trips (the barrier version cost ~3x the latency of this one per coupled Newton iteration)
+    // Block elimination H = [[A, B^T], [B, C]] (A arm 6x6, C cube 6x6, B their coupling): factor A in registers,
+    // W = L_A^-1 B^T with one column per lane, the Schur complement S = C - W^T W with one entry per lane, factor S in
+    // registers.  Two 6-column register factorisations and two barriers instead of a 12-column chain of dependent
+    // shuffles (measured: 4.5 k cycles per coupled Newton iteration for the 12-column version).
+    float* const Wm = &S->T[0][0];          // scratch in the H_c J_c rows (dead until the next iteration): W[k][r] at 6 k + r
+    float* const y1 = Wm + 36;              // L_A^-1 (-g_arm)
+    float* const Sm = Wm + 48;              // packed Schur complement
+    float* const r2 = Wm + 72;              // its right-hand side
 #ifdef SO100_SOLVE_CLOCK
     dc_[1] = clock64();
 #endif
-    float a[NV];
+    float LA[21];
+    chol6_factor<false>(S->H, LA);          // entries 0..20 of the packed 12x12 are the arm block
+    {
+      float w[NL];
 #pragma unroll
-    for (int j = 0; j < NV; j++) a[j] = (lane < NV && j <= lane) ? S->H[tri(lane < NV ? lane : 0, j)] : 0.0f;
+      for (int c = 0; c < NL; c++) w[c] = lane < NL ? S->H[tri(NL + (lane < NL ? lane : 0), c)] : -S->vec[c];
+      chol6_fwd(LA, w);                     // lanes 0..5: column `lane` of W; every other lane: y1
+      if (lane <= NL) {
 #pragma unroll
-    for (int k = 0; k < NV; k++) {
-      const float dk = rsqrtf(fmaxf(t.shfl(a[k], k), 1e-20f));
-      const float lik = a[k] * dk;                 // L_ik on lanes i > k
-      a[k] = (lane == k) ? dk : lik;               // lane k keeps 1 / L_kk
-#pragma unroll
-      for (int j = k + 1; j < NV; j++) {
-        const float ljk = t.shfl(lik, j);
-        if (lane >= j) a[j] = fmaf(-lik, ljk, a[j]);
+        for (int k = 0; k < NL; k++) {
+          if (lane < NL) Wm[NL * k + lane] = w[k];
+          else y1[k] = w[k];
+        }
       }
     }
+    t.sync();
 #ifdef SO100_SOLVE_CLOCK
     dc_[2] = clock64();
 #endif
-    float x = -g;
+    if (lane < 21) {
+      const int r = tri_row6(lane), c = lane - tri(r, 0);
+      float sacc = S->H[tri(NL + r, NL + c)];
 #pragma unroll
-    for (int k = 0; k < NV; k++) {                 // L y = -g
-      const float xk = t.shfl(x * a[k], k);
-      if (lane == k) x = xk;
-      else if (lane > k && lane < NV) x = fmaf(-a[k], xk, x);
-    }
-    // L^T z = y needs columns of L: hand the rows over through shared memory once
-    if (lane < NV) {
+      for (int k = 0; k < NL; k++) sacc = fmaf(-Wm[NL * k + r], Wm[NL * k + c], sacc);
+      Sm[lane] = sacc;
+    } else if (lane < 21 + NL) {
+      const int r = lane - 21;
+      float racc = -S->vec[NL + r];
 #pragma unroll
-      for (int j = 0; j < NV; j++)
-        if (j <= lane) S->H[tri(lane, j)] = a[j];
+      for (int k = 0; k < NL; k++) racc = fmaf(-Wm[NL * k + r], y1[k], racc);
+      r2[r] = racc;
     }
     t.sync();
-    for (int k = NV - 1; k >= 0; k--) {
-      float xk = t.shfl(x, k) * S->H[tri(k, k)];
-      if (lane == k) x = xk;
-      else if (lane < k) x = fmaf(-S->H[tri(k, lane)], xk, x);
+    float x2[NL], x1[NL];
+    chol6_solve<false>(Sm, r2, 1.0f, x2);
+#pragma unroll
+    for (int k = 0; k < NL; k++) {
+      float acc = y1[k];
+#pragma unroll
+      for (int r = 0; r < NL; r++) acc = fmaf(-Wm[NL * k + r], x2[r], acc);
+      x1[k] = acc;
     }
-    pd = (lane < NV) ? x : 0.0f;
-    t.sync();
+    chol6_bwd(LA, x1);
+    pd = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NL; k++) {
+      pd = (lane == k) ? x1[k] : pd;
+      pd = (lane == NL + k) ? x2[k] : pd;
+    }
+    t.sync();                                // every lane has read the gradient in S->vec
     if (lane < NV) S->vec[lane] = pd;
     t.sync();
 #ifdef SO100_SOLVE_CLOCK
@@ -485,11 +505,11 @@ template <unsigned LPE, class ES> __device__ __noinline__ float dense_newton_dir
 
 // Solves for qacc (left in S->a / S->ad, contact forces in S->cfrc).  `diag` (nullable): the env's uint32 counters.
 // Returns the number of Newton iterations.
-template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S, const DevTables& T, uint32_t* diag) {
+template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S, const DevTables& T, uint32_t* diag) {
   using Regs = SolveRegs<LPE, ES::NCAP>;
   const int lane = t.thread_rank();
   const int ncon = S->ncon;
-  const bool coupled = S->coupled != 0;
+  const bool coupled = DENSE && S->coupled != 0;
   Regs r;
   // ---- dof rows
   r.qfs = 0; r.fr_aref = 0; r.fr_R = 1; r.fr_D = 0; r.fr_fl = 0; r.lim_sgn = 0; r.lim_D = 0; r.lim_aref = 0;
@@ -590,7 +610,8 @@ template <unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S
       if (lane < NV) S->vec[lane] = pd;
       t.sync();
     } else {
-      pd = dense_newton_dir(t, S, g);
+      if constexpr (DENSE) pd = dense_newton_dir(t, S, g);
+      else pd = 0.0f;
     }
     SOLVE_CLK(2);
     // ---- line-search set-up
