@@ -617,8 +617,9 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
     // ---- line-search set-up
     float Mp = 0;
     if (lane < NV) Mp = mul_M(S, S->vec, lane);
-    float pMp = pd * Mp, pg = pd * (Ma - r.qfs);
+    float pMp = pd * Mp, pg = pd * (Ma - r.qfs), gp = pd * g;    // gp: phi'(0) = g . p
     tsum2(t, pMp, pg);
+    gp = tsum(t, gp);
     const int nrow = ncon * 4;
 #pragma unroll
     for (int s = 0; s < Regs::RPL; s++) {
@@ -646,12 +647,15 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
     }
     const float a0 = S->a[lane < NV ? lane : 0];
     const float xf0 = a0 - r.fr_aref, xl0 = r.lim_sgn * a0 - r.lim_aref;
-    // ---- exact line search: safeguarded 1-D Newton on phi' (first trip: alpha = 0)
-    float alpha = 0, d1 = 0, d2 = 1, lo = 0, hi = -1, d10 = 0;
-    bool descent = true;
+    // ---- exact line search: safeguarded 1-D Newton on phi'.  phi'(0) = g . p is known from the gradient, and with the exact
+    // Hessian phi''(0) = p . H p = -g . p, so the first Newton iterate from alpha = 0 is alpha = 1: the search starts there
+    // instead of spending an evaluation on alpha = 0.
+    const float d10 = fabsf(gp);
+    const bool descent = gp < 0;                 // no descent left at float32 resolution otherwise
+    float alpha = 1.0f, d1 = 0, d2 = 1, lo = 0, hi = -1;
 #pragma unroll 1
-    for (int ls = -1; ls < LS_MAXIT; ls++) {
-      if (ls >= 0) {
+    for (int ls = 0; descent && ls < LS_MAXIT; ls++) {
+      if (ls > 0) {
         float na = alpha - __fdividef(d1, d2);     // approximate division: a safeguarded iterate, not a result
         if (hi >= 0 && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
         alpha = na;
@@ -677,11 +681,6 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
       tsum2(t, e1, e2);
       d1 = e1 + pg + alpha * pMp;
       d2 = e2 + pMp;
-      if (ls < 0) {
-        d10 = fabsf(d1);
-        if (!(d1 < 0)) { descent = false; break; }   // no descent left at float32 resolution
-        continue;
-      }
       if (fabsf(d1) <= SO100_LS_TOL * d10) break;
       if (d1 < 0) lo = alpha; else hi = alpha;
     }
