@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -38,6 +39,9 @@ constexpr int BLOCK = 128, TPB_K3L = SO100_TPB_K3L;
 enum { CLS_KIN = 0, CLS_BOX = 1, CLS_SOLVE = 2, CLS_TASK = 3, CLS_HULL = 4, CLS_HEAVY = 5, CLS_N = 6 };
 
 static thread_local std::string g_err;
+static std::mutex g_model_mutex;
+static int g_live_handles = 0;
+static so100::DevModel g_live_model;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CUDA_OK(expr)                                                                              \
   do {                                                                                             \
@@ -469,6 +473,15 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   if (rc) return rc;
   rc = configure_kernels();
   if (rc) return rc;
+  // the uniform model constants live in __constant__ memory shared by every handle of this process on a device:
+  // live handles must agree on the model
+  {
+    std::lock_guard<std::mutex> lock(g_model_mutex);
+    if (g_live_handles > 0 && memcmp(&g_live_model, &dm, sizeof(dm)) != 0)
+      return fail(SO100_ERR_MODEL, "so100_create: a live handle of this process uses a different model (one model per process)");
+    g_live_model = dm;
+    g_live_handles++;
+  }
   so100_ctx* h = new so100_ctx();
   h->n = num_envs; h->device = device; h->task = task; h->seed = seed; h->env_offset = env_offset;
   h->nsub = m.nsubstep;
@@ -533,6 +546,10 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
 
 int so100_destroy(so100_handle h) {
   if (!h) return SO100_OK;
+  {
+    std::lock_guard<std::mutex> lock(g_model_mutex);
+    if (g_live_handles > 0) g_live_handles--;
+  }
   cudaSetDevice(h->device);
   cudaFree(h->state); cudaFree(h->geom); cudaFree(h->pair); cudaFree(h->vert); cudaFree(h->bpair); cudaFree(h->diag); cudaFree(h->work); cudaFree(h->qmem); cudaFree(h->order);
   free_group(h->whole);

@@ -50,7 +50,8 @@ enum so100_task {
 /* Replaces: SO100Env.__init__/_make_env_task -> mujoco.Physics.from_xml_path + control.Environment
  * (gym_so100/env.py:29-77, 92-128).  `model_blob` (host) is the packed so100_model
  * (include/so100_model.h) produced by gym_so100_c_b200.model.pack(); `env_offset` is the global
- * index of this handle's env 0 (multi-GPU sharding: RNG streams depend on the global index only). */
+ * index of this handle's env 0 (multi-GPU sharding: RNG streams depend on the global index only).  All live handles of a
+ * process must use the same model (its constants sit in __constant__ memory); a different one fails with SO100_ERR_MODEL. */
 int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device, int task,
                  uint64_t seed, int64_t env_offset, so100_handle* out);
 int so100_destroy(so100_handle h);

@@ -328,6 +328,27 @@ def test_goal_env_full_size_smoke(model_blob):
     sim.close()
 
 
+def test_one_model_per_process_is_enforced(model_blob):
+    """The uniform model constants live in __constant__ memory shared by all handles: a second live handle with a different
+    model must be refused (loudly), the same model is fine, and after the first handle is gone a new model is accepted."""
+    from gym_so100_c_b200 import ext, model
+    from gym_so100_c_b200.engine import BatchedSim
+    m = model.unpack(model_blob).copy()
+    m["timestep"] = 0.001
+    other = model.pack(m)
+    a = BatchedSim(8, model_blob=model_blob)
+    b = BatchedSim(8, model_blob=model_blob)
+    with pytest.raises(ext.So100Error, match="one model per process"):
+        BatchedSim(8, model_blob=other)
+    a.close(); b.close()
+    c = BatchedSim(8, model_blob=other)
+    c.reset()
+    c.close()
+    d = BatchedSim(8, model_blob=model_blob)       # leave the process on the stock model for the tests that follow
+    d.reset()
+    d.close()
+
+
 def test_reset_sampling_bit_exact(model_blob):
     """On-device Philox cube placement == the oracle's, bit for bit, and independent of sharding."""
     import torch
