@@ -193,7 +193,9 @@ class SB3VecEnvAdapter:
 
     def reset(self):
         obs, _ = self.venv.reset()
-        return self._np(obs)
+        out = self._np(obs)
+        self._desired = out["desired_goal"] if isinstance(out, dict) else None
+        return out
 
     def seed(self, seed=None):
         self._seed = seed
@@ -208,17 +210,21 @@ class SB3VecEnvAdapter:
         succ = infos["is_success"].cpu().numpy()
         tl = infos["TimeLimit.truncated"].cpu().numpy()
         final = infos["final_obs"].cpu().numpy()
+        obs_np = self._np(obs)
+        prev_desired = getattr(self, "_desired", None)       # the goal of the episode that just ended (a reset draws a new one)
         out = []
         for i in range(self.num_envs):
             d = {"is_success": bool(succ[i]), "TimeLimit.truncated": bool(tl[i])}
             if done[i]:
                 if isinstance(obs, dict):
                     d["terminal_observation"] = {"observation": final[i].copy(), "achieved_goal": final[i, :3].copy(),
-                                                 "desired_goal": None}
+                                                 "desired_goal": None if prev_desired is None else prev_desired[i].copy()}
                 else:
                     d["terminal_observation"] = final[i].copy()
             out.append(d)
-        return self._np(obs), rew.cpu().numpy().copy(), done, out
+        if isinstance(obs_np, dict):
+            self._desired = obs_np["desired_goal"]
+        return obs_np, rew.cpu().numpy().copy(), done, out
 
     def step(self, actions):
         self.step_async(actions)
@@ -247,8 +253,11 @@ class SB3VecEnvAdapter:
 
 def make(env_id: str, num_envs: int, **kw):
     """Batched counterpart of ``gym.make`` for the registered ids (gym_so100/__init__.py:4-32)."""
-    if env_id in ("gym_so100/SO100CubeToBin-v0", "SO100CubeToBin-v0"):
-        return SO100VecEnv(num_envs, task="so100_cube_to_bin", **kw)
-    if env_id in ("gym_so100/SO100Goal-v0", "SO100GoalEnv"):
+    ids = {"SO100CubeToBin-v0": "so100_cube_to_bin", "SO100TouchCube-v0": "so100_touch_cube",
+           "SO100TouchCubeSparse-v0": "so100_touch_cube_sparse"}
+    name = env_id.split("/")[-1]
+    if name in ids:
+        return SO100VecEnv(num_envs, task=ids[name], **kw)
+    if name in ("SO100Goal-v0", "SO100GoalEnv"):
         return SO100GoalVecEnv(num_envs, **kw)
-    raise NotImplementedError(f"{env_id}: only the bin-a-cube envs are built (TouchCube variants: SURVEY 8f 'next')")
+    raise NotImplementedError(f"{env_id}: not one of the registered ids (gym_so100/__init__.py:4-32) or the GoalEnv")

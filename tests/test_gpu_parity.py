@@ -419,6 +419,32 @@ def test_demonstration_replay_reproduces_recorded_episodes(model_blob, tmp_path)
     assert not out["valid"][3:, 3].any() and out["valid"][:3, 3].all()
 
 
+def test_make_ids_and_sb3_terminal_observation(model_blob):
+    """`make` covers the three registered ids (gym_so100/__init__.py:4-32) with their TimeLimits, and the SB3 adapter's
+    terminal_observation of a GoalEnv carries the goal of the episode that ended (HerReplayBuffer stores it as next_obs)."""
+    import torch
+    from gym_so100_c_b200 import vec_env
+    for env_id, limit in (("gym_so100/SO100CubeToBin-v0", 700), ("gym_so100/SO100TouchCube-v0", 300),
+                          ("gym_so100/SO100TouchCubeSparse-v0", 300)):
+        env = vec_env.make(env_id, 4)
+        assert env.max_episode_steps == limit
+        env.close()
+    with pytest.raises(NotImplementedError):
+        vec_env.make("gym_so100/SO100Nope-v0", 4)
+    env = vec_env.SO100GoalVecEnv(6, seed=3)
+    ad = vec_env.SB3VecEnvAdapter(env)
+    first = ad.reset()
+    env.sim.set_aux(step_count=torch.full((6,), 299, dtype=torch.int32))
+    obs, rew, done, infos = ad.step(np.zeros((6, 6), np.float32))
+    assert done.all() and all(i["TimeLimit.truncated"] for i in infos)
+    for i in range(6):
+        term = infos[i]["terminal_observation"]
+        assert np.array_equal(term["desired_goal"], first["desired_goal"][i])          # the old episode's goal
+        assert not np.array_equal(obs["desired_goal"][i], first["desired_goal"][i])    # the new episode drew another one
+        assert term["observation"].shape == (15,) and np.array_equal(term["achieved_goal"], term["observation"][:3])
+    env.close()
+
+
 def test_compute_reward_batch_bit_exact(model_blob):
     import torch
     from oracle.so100_oracle import compute_reward
