@@ -1,4 +1,4 @@
-// Collision, stage A (App. A step 3): static candidate-pair list -> sphere / sphere-vs-box cull ->
+// Collision, stage A (App. A step 3): static candidate-pair list -> sphere + AABB cull ->
 //   box-like pairs: separating-axis test with one lane per pair, then contact generation with the
 //                   whole tile per penetrating pair (24 candidate points, one per lane: incident-face
 //                   corners, incident-edge x reference-edge intersections, reference corners under the
@@ -28,19 +28,6 @@ __device__ __forceinline__ void load_obb(const FrameBlock& f, const DevGeom& g, 
   b.h[0] = g.half[0]; b.h[1] = g.half[1]; b.h[2] = g.half[2];
   const float* m = g.link >= 0 ? f.lmat[g.link] : g.wmat;
   b.ax[0] = mcol(m, 0); b.ax[1] = mcol(m, 1); b.ax[2] = mcol(m, 2);
-}
-
-// distance^2 from point p to an oriented box
-__device__ __forceinline__ float point_obb_d2(V3 p, const Obb& b) {
-  V3 d = p - b.c;
-  float s = 0;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    float x = dot(d, b.ax[k]);
-    float e = fmaxf(fabsf(x) - b.h[k], 0.0f);
-    s = fmaf(e, e, s);
-  }
-  return s;
 }
 
 __device__ __forceinline__ void put_contact(float* con, int c, V3 p, V3 n, float dist, int pair) {

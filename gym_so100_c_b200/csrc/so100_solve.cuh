@@ -5,8 +5,8 @@
 //                     gathers the 4 rows of contact c and owns its cone state / jar / jv
 //   lane e (strided)  packed Hessian entry e
 // The Hessian is block diagonal (arm 6x6 | cube 6x6) unless a contact joins an arm link and the
-// cube; the common uncoupled case factors both blocks redundantly in registers (no barriers), the
-// coupled case falls back to a tile-parallel 12x12 Cholesky in shared memory.
+// cube; the common uncoupled case factors both blocks in registers (no barriers); the coupled case
+// (solve<DENSE = true>, heavy kernel only) eliminates the arm block and factors the 6x6 Schur complement.
 //
 // The cost/force evaluation and the line-search derivative each have exactly ONE call site (the start-point
 // selection, the Newton loop and the final force refresh all run through the same loop body): the kernel is
