@@ -30,6 +30,11 @@ ALG_BYTES_PER_ENV_STEP = 432          # 188 B read + 244 B written
 FLOP_PER_ENV_STEP = 1.0e6             # SURVEY.md Appendix C convention F_contact (fp32 FLOPs, FMA = 2)
 FP32_PEAK_NOMINAL_TFLOPS = 74.4       # 148 SM x 128 lanes x 2 x 1.965 GHz
 METRIC = "env-steps/sec (bin-a-cube)"
+# warp-instructions per env-step of the steady-state workload, from the ncu launch list in profiles/r01_phase_launches.txt
+# (per 2048-env launch: solve_light 5.70 M, collide_box 3.18 M, kin_dyn 1.72 M, collide_hull 0.15 M, solve_heavy 0.02 M per
+# substep, plus the trailing position stage and the task kernel): 10 x 5259 + 2944
+WARP_INSTR_PER_ENV_STEP = 55.5e3
+ISSUE_SLOTS_PER_S = 148 * 4 * 1.965e9        # SMs x schedulers x max SM clock: one warp-instruction per scheduler and cycle
 # Algorithmic bytes one env moves per launch of each phase kernel (4-byte words):
 #   kin_dyn       reads qpos13+qvel12+ctrl6, writes frames102 + Marm/qfs/qas45
 #   collide_box   reads frames102, writes header4 + 8 words per contact (1 contact typical)
@@ -271,6 +276,11 @@ def run_gpu(args):
                          "phase_share_of_step": {k: phase_ms[k] / max(sum(phase_ms.values()), 1e-9) for k in phase_ms},
                          "phase_ms_per_launch": {k: phase_ms[k] / max(phase_cnt[k], 1) for k in phase_ms},
                          "note": "HBM is not the binding roof for this path (SURVEY 8d): the step is FP32-issue bound",
+                         "issue_convention": {"warp_instr_per_env_step": WARP_INSTR_PER_ENV_STEP,
+                                              "achieved_warp_instr_per_s": value / world * WARP_INSTR_PER_ENV_STEP,
+                                              "peak_issue_slots_per_s": ISSUE_SLOTS_PER_S,
+                                              "frac": value / world * WARP_INSTR_PER_ENV_STEP / ISSUE_SLOTS_PER_S,
+                                              "note": "the binding resource (DESIGN.md section 5): per-GPU share of all issue slots"},
                          "fp32_convention": {"flop_per_env_step": FLOP_PER_ENV_STEP, "achieved_tflops": fp32_tflops,
                                              "peak_tflops_nominal": FP32_PEAK_NOMINAL_TFLOPS,
                                              "frac": fp32_tflops / FP32_PEAK_NOMINAL_TFLOPS}},
