@@ -94,6 +94,10 @@ struct so100_ctx {
   // two are about a third of a substep apart for the rest of the step; 2 chains all groups that way.
   int stagger = 0;   // measured on B200: 1 and 2 are 1-9 % slower than 0 at 4096 / 16384 / 65536 envs (the groups drift apart on their own)
   int sm_count = 148;
+  // so100_step ends with a collision stage on the post-step state (mj_step1), and the next so100_step starts with one on the
+  // same state: while nothing else has touched the state in between, the first substep reuses those contact lists
+  // (bit-identical by construction; envs auto-reset by the task kernel are marked stale and recomputed).  SO100_REUSE=0 disables.
+  bool work_fresh = false, reuse_enabled = true;
   bool timing = false;        // so100_phase_timing: CUDA-event pairs around every phase-kernel launch
   std::vector<std::pair<cudaEvent_t, int>> events;   // (event, kernel class) begin markers, class -1 = end marker
   // staging for the host-buffer entry point
@@ -366,7 +370,7 @@ static void mark(so100_ctx* h, cudaStream_t st, int cls, bool begin) {
 }
 
 // K1: kinematics (+ dynamics), K2a/K2b: collision.  Leaves frames, M, qfrc_smooth and the contact list in the workspace.
-static void launch_position_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const float* action, int with_dyn) {
+static void launch_position_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const float* action, int with_dyn, int reuse = 0) {
   const int n = G.n;
   const DevTables T = h->tables();
   const Queues Q = h->queues(G);
@@ -375,7 +379,7 @@ static void launch_position_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, co
   mark(h, st, CLS_KIN, true);
   phase_kin_dyn<LPE_K1><<<grid_of(n, LPE_K1), BLOCK, smem_of<KinS>(LPE_K1), st>>>(state, work, action ? action + (size_t)G.off * 6 : nullptr, n, with_dyn, Q);
   mark(h, st, CLS_KIN, false); mark(h, st, CLS_BOX, true);
-  phase_collide_box<LPE_K2A><<<grid_of(n, LPE_K2A), BLOCK, smem_of<BoxS>(LPE_K2A), st>>>(work, n, T, Q);
+  phase_collide_box<LPE_K2A><<<grid_of(n, LPE_K2A), BLOCK, smem_of<BoxS>(LPE_K2A), st>>>(work, n, T, Q, reuse);
   mark(h, st, CLS_BOX, false); mark(h, st, CLS_HULL, true);
   phase_collide_hull<LPE_K2B><<<std::min(grid_of(n, LPE_K2B), std::max(h->sm_count * SO100_K2B_BLOCKS_PER_SM, n / 8)), BLOCK, smem_of<HullS>(LPE_K2B), st>>>(work, T, Q);
   mark(h, st, CLS_HULL, false);
@@ -503,6 +507,7 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   CUDA_OK(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
   CUDA_OK(cudaMalloc(&h->act_stage, (size_t)num_envs * 6 * sizeof(float)));
   if (const char* e = getenv("SO100_GRAPH")) h->use_graph = atoi(e) != 0;
+  if (const char* e = getenv("SO100_REUSE")) h->reuse_enabled = atoi(e) != 0;
   {
     // env groups: SO100_GROUPS overrides; default one group per 1024 envs, at most 8 (measured on B200: 4096 envs
     // 1.50 -> 1.73 M env-steps/s with 4 groups, 16384 envs 4.0 -> 5.0 M with 8, no gain beyond 8 at any batch size)
@@ -575,6 +580,7 @@ int so100_launches_per_step(so100_handle h) {
 int so100_reset(so100_handle h, const uint8_t* mask, const float* box_pose, float* obs, float* achieved, float* desired,
                 void* stream) {
   if (!h) return fail(SO100_ERR_ARG, "so100_reset: null handle");
+  h->work_fresh = false;
   cudaStream_t st = (cudaStream_t)stream;
   reset_kernel<LPE_K4><<<grid_of(h->n, LPE_K4), BLOCK, smem_of<TaskS>(LPE_K4), st>>>(h->state, mask, box_pose, obs, achieved, desired, h->n,
                                                                                       h->task, (uint32_t)h->seed, (uint32_t)(h->seed >> 32),
@@ -584,12 +590,12 @@ int so100_reset(so100_handle h, const uint8_t* mask, const float* box_pose, floa
 }
 
 // the launch sequence of one env step on `stream` (directly, or while `stream` is being captured into a graph)
-static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream) {
+static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream, int reuse) {
   const float* action = A.action;
   for_each_group(h, stream, true, [&](EnvGroup& G, cudaStream_t st) {
     const SolveOut O{nullptr, nullptr, 0};
     for (int s = 0; s < h->nsub; s++) {
-      launch_position_stage(h, G, st, s == 0 ? action : nullptr, 1);
+      launch_position_stage(h, G, st, s == 0 ? action : nullptr, 1, s == 0 ? reuse : 0);
       if (s == 0) cudaEventRecord(G.staged, st);
       launch_solve_stage(h, G, st, O);
     }
@@ -621,15 +627,17 @@ int so100_step(so100_handle h, const float* action, int autoreset, float* obs, f
   A.n = h->n; A.autoreset = autoreset; A.task = h->task;
   A.seed_lo = (uint32_t)h->seed; A.seed_hi = (uint32_t)(h->seed >> 32); A.env_offset = h->env_offset;
   cudaStream_t st = (cudaStream_t)stream;
+  const int reuse = (h->reuse_enabled && h->work_fresh && h->nsub > 0) ? 1 : 0;
+  h->work_fresh = true;
   if (!h->use_graph || h->timing) {
-    enqueue_step(h, A, st);
+    enqueue_step(h, A, st, reuse);
     CUDA_OK(cudaGetLastError());
     return SO100_OK;
   }
   CUDA_OK(cudaMemcpyAsync(h->act_stage, action, (size_t)h->n * 6 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   A.action = h->act_stage;
   const void* key[10] = {obs, achieved, desired, reward, terminated, truncated, success, final_obs,
-                         reinterpret_cast<const void*>((size_t)(autoreset != 0)), nullptr};
+                         reinterpret_cast<const void*>((size_t)(autoreset != 0)), reinterpret_cast<const void*>((size_t)reuse)};
   cudaGraphExec_t exec = nullptr;
   for (auto& g : h->graphs)
     if (memcmp(g.key, key, sizeof(key)) == 0) exec = g.exec;
@@ -637,7 +645,7 @@ int so100_step(so100_handle h, const float* action, int autoreset, float* obs, f
     cudaGraph_t graph = nullptr;
     CUDA_OK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal));
     h->capturing = true;
-    enqueue_step(h, A, h->cap);
+    enqueue_step(h, A, h->cap, reuse);
     h->capturing = false;
     CUDA_OK(cudaStreamEndCapture(h->cap, &graph));
     CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
@@ -696,6 +704,7 @@ int so100_compute_reward(const float* achieved, const float* desired, int64_t n,
 static int state_io(so100_handle h, int dir, float* qpos, float* qvel, float* ctrl, float* warm, float* goal, int32_t* sc,
                     int32_t* ts, uint32_t* ep, void* stream) {
   if (!h) return fail(SO100_ERR_ARG, "state io: null handle");
+  if (dir == 1) h->work_fresh = false;
   const int total = h->n * STATE_WORDS;
   state_io_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, h->n, dir, qpos, qvel, ctrl, warm, goal, sc, ts, ep);
   CUDA_OK(cudaGetLastError());
@@ -718,6 +727,7 @@ int so100_set_aux(so100_handle h, const float* goal, const int32_t* step_count, 
 
 int so100_substeps(so100_handle h, int nsub, void* stream) {
   if (!h || nsub < 0) return fail(SO100_ERR_ARG, "so100_substeps: bad argument");
+  h->work_fresh = false;
   for_each_group(h, (cudaStream_t)stream, true, [&](EnvGroup& G, cudaStream_t st) {
     const SolveOut O{nullptr, nullptr, 0};
     for (int s = 0; s < nsub; s++) {
@@ -732,6 +742,7 @@ int so100_substeps(so100_handle h, int nsub, void* stream) {
 
 int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom, float* con_data, float* sites, void* stream) {
   if (!h) return fail(SO100_ERR_ARG, "so100_forward: null handle");
+  h->work_fresh = false;
   cudaStream_t st = (cudaStream_t)stream;
   launch_position_stage(h, h->whole, st, nullptr, 1);
   const int threads = h->n * 32;

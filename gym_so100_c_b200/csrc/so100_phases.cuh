@@ -62,11 +62,21 @@ __global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, 
 }
 
 // K2a: frames -> box contacts + surviving hull pairs; classifies the env
-template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_box(float* work, int n, DevTables T, Queues Q) {
+// `reuse`: the workspace already holds the complete contact lists of exactly this state (the trailing collision stage of
+// the previous so100_step), except for envs whose header says HDR_STALE (reset since): everyone else only re-enters the
+// heavy queue, which K1 has just re-armed
+template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_box(float* work, int n, DevTables T, Queues Q, int reuse) {
   SO100_TILE_PROLOGUE(LPE, 128, BoxS);
   const int env = blockIdx.x * EPB + t.meta_group_rank();
   if (env >= n) return;
   float* w = work + (size_t)env * WORK_WORDS;
+  if (reuse) {
+    const int4 hdr = *reinterpret_cast<const int4*>(w + W_HDR);
+    if (hdr.w == 0) {
+      if (lane == 0 && ((hdr.z & HDR_COUPLED) || hdr.x > NCL)) Q.heavy[atomicAdd(&Q.ctl[Q_HEAVY_COUNT], 1)] = env;
+      return;
+    }
+  }
   copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
   t.sync();
   int ncon;
@@ -189,11 +199,11 @@ __global__ void __launch_bounds__(128) phase_solve_heavy(float* state, const flo
 }
 
 // K4: task layer on the post-step state
-template <unsigned LPE> __global__ void __launch_bounds__(128) phase_task(StepArgs A, const float* work, DevTables T) {
+template <unsigned LPE> __global__ void __launch_bounds__(128) phase_task(StepArgs A, float* work, DevTables T) {
   SO100_TILE_PROLOGUE(LPE, 128, TaskS);
   const int env = blockIdx.x * EPB + t.meta_group_rank();
   if (env >= A.n) return;
-  const float* w = work + (size_t)env * WORK_WORDS;
+  float* w = work + (size_t)env * WORK_WORDS;
   float* rec = A.state + (size_t)env * STATE_WORDS;
   copy_vec<LPE, STATE_WORDS>(t, S->st, rec);
   copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);

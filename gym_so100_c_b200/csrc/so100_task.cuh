@@ -88,7 +88,7 @@ __device__ __forceinline__ void write_obs(const Tile<LPE>& t, const TaskS* S, in
 
 // reward / success / termination / observation / same-call auto-reset on the post-step state whose frames and
 // contact list are in workspace record `w`
-template <unsigned LPE> __device__ void task_env(const Tile<LPE>& t, TaskS* S, const StepArgs& A, const float* w, int env, const DevTables& T) {
+template <unsigned LPE> __device__ void task_env(const Tile<LPE>& t, TaskS* S, const StepArgs& A, float* w, int env, const DevTables& T) {
   const int lane = t.thread_rank();
   uint32_t* diag = reinterpret_cast<uint32_t*>(&S->st[S_DIAG]);
   const int ncon_raw = __float_as_int(w[W_HDR]), ncon = min(ncon_raw, NC);
@@ -171,6 +171,8 @@ template <unsigned LPE> __device__ void task_env(const Tile<LPE>& t, TaskS* S, c
   if ((A.autoreset && (term || trunc)) || bad) {
     reset_env(t, S, A.env_offset + env, nullptr, A.task, A.seed_lo, A.seed_hi);
     kinematics<false>(t, S);
+    // the contact list in the workspace belongs to the finished episode: the next step's first substep must not reuse it
+    if (lane == 0) reinterpret_cast<int*>(w + W_HDR)[3] = HDR_STALE;
   }
   write_obs(t, S, env, A.obs, A.achieved, A.desired);
 }

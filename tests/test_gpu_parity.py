@@ -230,17 +230,19 @@ def test_autoreset_and_truncation(model_blob):
 
 def test_groups_and_graph_replay_are_bit_invariant(model_blob, monkeypatch):
     """The execution schedule (env groups on parallel streams, CUDA-graph replay, longest-first solve order, work queues
-    filled through atomics) must not change any env's result: 4096 envs stepped as 4 groups under graph replay equal the same
-    envs stepped as one group with plain launches, bit for bit, including after auto-resets."""
+    filled through atomics, reuse of the trailing collision stage by the next step's first
+    substep) must not change any env's result: 4096 envs stepped as 4 groups under graph replay equal the same envs stepped
+    as one group with plain launches and every shortcut off, bit for bit, including after auto-resets."""
     import torch
     from gym_so100_c_b200.engine import BatchedSim
     n = 4096
     g = torch.Generator(device="cuda").manual_seed(5)
     acts = torch.rand((6, n, 6), device="cuda", generator=g) * 2 - 1
     results = []
-    for groups, graph in (("4", "1"), ("1", "0"), ("8", "0")):
+    for groups, graph, reuse in (("4", "1", "1"), ("1", "0", "0"), ("8", "0", "1"), ("4", "1", "0")):
         monkeypatch.setenv("SO100_GROUPS", groups)
         monkeypatch.setenv("SO100_GRAPH", graph)
+        monkeypatch.setenv("SO100_REUSE", reuse)
         sim = BatchedSim(n, device="cuda:0", task=0, seed=9, model_blob=model_blob)
         sim.reset()
         sim.set_aux(step_count=torch.full((n,), 697, dtype=torch.int32))     # everyone truncates (and auto-resets) at step 3
