@@ -234,6 +234,37 @@ def run_gpu(args):
         extra = {"config4_goal_env_her": {"envs": n4, "relabel_batch": n4 * 4, "ms_per_step": ms4, "value": n4 / ms4 * 1e3,
                                           "unit": "env-steps/s", "steps": 10}}
         sim4.close()
+        # BASELINE config 3 with SURVEY 8d's input mix: half the envs take random actions, half run the scripted
+        # pick-and-place (gym_so100_c_b200/scripted.py: reach, grasp, carry, release over the bin; episodes restart on success
+        # or after 300 steps).  One whole scripted episode is timed so that every phase of it is in the figure.
+        from gym_so100_c_b200 import model as _model
+        from gym_so100_c_b200.scripted import CUBE_SITE_OFFSET, ScriptedPolicy
+        simm = BatchedSim(hi - lo, device=dev, task=0, seed=0x50100, env_offset=lo)
+        obs_m = simm.reset()[0]
+        pol = ScriptedPolicy(_model.pack(_model.load_model()), hi - lo, device=dev, period=300)
+        pol.reset(obs_m[:, 0:2].double() - CUBE_SITE_OFFSET)
+        half = (hi - lo) // 2
+        Wm, Km = 20, 300
+        evm = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Km)]
+        for s in range(Wm + Km):
+            a = pol.step()
+            a[:half] = torch.rand((half, 6), device=dev, generator=gen) * 2 - 1
+            if s >= Wm:
+                flush.fill_(float(s))
+                evm[s - Wm][0].record()
+            obs_m, _, term_m, trunc_m, _ = simm.step(a, autoreset=True)
+            if s >= Wm:
+                evm[s - Wm][1].record()
+            pol.observe(obs_m, (term_m | trunc_m).bool())
+        torch.cuda.synchronize()
+        msm = float(np.mean([a.elapsed_time(b) for a, b in evm]))
+        dm = simm.diagnostics()
+        extra["config3_mix_random_scripted"] = {
+            "envs": hi - lo, "scripted_envs": hi - lo - half, "steps": Km, "ms_per_step": msm, "value": (hi - lo) / msm * 1e3,
+            "unit": "env-steps/s", "l2": "flushed between timed steps", "scripted_episodes_finished": dm["episodes"],
+            "scripted_successes": dm["successes"], "contacts_per_solve": dm["contacts_seen"] / max(dm["solver_runs"], 1),
+            "newton_iters_per_solve": dm["newton_iters"] / max(dm["solver_runs"], 1)}
+        simm.close()
         sim = BatchedSim(hi - lo, device=dev, task=0, seed=0x50100, env_offset=lo)   # only for launches_per_step below
 
     if rank == 0:
