@@ -34,7 +34,8 @@ constexpr int BLOCK = 128, TPB_K3L = SO100_TPB_K3L;
 #define SO100_K2B_BLOCKS_PER_SM 2     // and at least n / 8 blocks (one tile per ~2 envs; 0.18 GJK items per env)
 #endif
 #ifndef SO100_K3H_BLOCKS
-#define SO100_K3H_BLOCKS 37           // 148 tiles; a 2048-env group queues 0-10 heavy envs per substep
+#define SO100_K3H_BLOCKS 296          // 2 per SM: random actions queue 0-10 heavy envs per 2048-env group and substep (any grid
+                                      // >= 37 blocks measures the same), synchronized grasps (scripted / trained policies) queue half the group
 #endif
 enum { CLS_KIN = 0, CLS_BOX = 1, CLS_SOLVE = 2, CLS_TASK = 3, CLS_HULL = 4, CLS_HEAVY = 5, CLS_N = 6 };
 
@@ -94,6 +95,7 @@ struct so100_ctx {
   // two are about a third of a substep apart for the rest of the step; 2 chains all groups that way.
   int stagger = 0;   // measured on B200: 1 and 2 are 1-9 % slower than 0 at 4096 / 16384 / 65536 envs (the groups drift apart on their own)
   int sm_count = 148;
+  int k3h_blocks = SO100_K3H_BLOCKS;   // SO100_K3H_BLOCKS (environment) overrides
   // so100_step ends with a collision stage on the post-step state (mj_step1), and the next so100_step starts with one on the
   // same state: while nothing else has touched the state in between, the first substep reuses those contact lists
   // (bit-identical by construction; envs auto-reset by the task kernel are marked stale and recomputed).  SO100_REUSE=0 disables.
@@ -397,7 +399,7 @@ static void launch_solve_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const
   cudaEventRecord(G.fork, st);
   cudaStreamWaitEvent(G.side, G.fork, 0);
   mark(h, G.side, CLS_HEAVY, true);
-  phase_solve_heavy<LPE_K3H><<<std::min(grid_of(n, LPE_K3H), SO100_K3H_BLOCKS), BLOCK, smem_of<SolS<NC>>(LPE_K3H), G.side>>>(state, work, T, Q, O);
+  phase_solve_heavy<LPE_K3H><<<std::min(grid_of(n, LPE_K3H), h->k3h_blocks), BLOCK, smem_of<SolS<NC>>(LPE_K3H), G.side>>>(state, work, T, Q, O);
   mark(h, G.side, CLS_HEAVY, false);
   cudaEventRecord(G.join, G.side);
   mark(h, st, CLS_SOLVE, true);
@@ -508,6 +510,7 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   CUDA_OK(cudaMalloc(&h->act_stage, (size_t)num_envs * 6 * sizeof(float)));
   if (const char* e = getenv("SO100_GRAPH")) h->use_graph = atoi(e) != 0;
   if (const char* e = getenv("SO100_REUSE")) h->reuse_enabled = atoi(e) != 0;
+  if (const char* e = getenv("SO100_K3H_BLOCKS")) h->k3h_blocks = std::max(1, atoi(e));
   {
     // env groups: SO100_GROUPS overrides; default one group per 1024 envs, at most 8 (measured on B200: 4096 envs
     // 1.50 -> 1.73 M env-steps/s with 4 groups, 16384 envs 4.0 -> 5.0 M with 8, no gain beyond 8 at any batch size)

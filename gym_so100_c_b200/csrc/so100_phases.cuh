@@ -182,8 +182,12 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
 }
 
 // K3h: persistent tiles drain the heavy queue
+#ifndef SO100_K3H_MINB
+#define SO100_K3H_MINB 1      // resident blocks per SM the heavy solve kernel's register allocation must allow (168 registers, 3
+                              // blocks; measured on B200: 4 (128 registers, spills) -8 %, 5 (96 registers) -14 % env-steps/s)
+#endif
 template <unsigned LPE>
-__global__ void __launch_bounds__(128) phase_solve_heavy(float* state, const float* work, DevTables T, Queues Q, SolveOut O) {
+__global__ void __launch_bounds__(128, SO100_K3H_MINB) phase_solve_heavy(float* state, const float* work, DevTables T, Queues Q, SolveOut O) {
   SO100_TILE_PROLOGUE(LPE, 128, SolS<NC>);
   const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_HEAVY_COUNT]);
   for (;;) {

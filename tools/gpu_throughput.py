@@ -17,6 +17,8 @@ def main():
     sim.reset()
     g = torch.Generator(device="cuda").manual_seed(1)
     acts = torch.rand((steps + 20, n, 6), device="cuda", generator=g) * 2 - 1
+    if len(sys.argv) > 3 and sys.argv[3] == "mix":
+        return mix(sim, n, steps, acts)
     for s in range(20):
         sim.step(acts[s])
     torch.cuda.synchronize()
@@ -31,6 +33,29 @@ def main():
     print(f"{os.path.basename(os.environ.get('SO100_LIB', 'libso100_b200.so'))} N={n}: {ms:.3f} ms/step {n / ms * 1e3:,.0f} env-steps/s "
           f"iters/solve {d['newton_iters'] / max(d['solver_runs'], 1):.2f} contacts/solve {d['contacts_seen'] / max(d['solver_runs'], 1):.2f} "
           f"overflow {d['contact_overflow']} cap {d['solver_cap_hits']} nonfinite {d['nonfinite_resets']}")
+
+
+def mix(sim, n, steps, acts):
+    """Half the envs random, half the pick-and-place script (bench.py's config3_mix_random_scripted)."""
+    from gym_so100_c_b200 import model
+    from gym_so100_c_b200.scripted import CUBE_SITE_OFFSET, ScriptedPolicy
+    pol = ScriptedPolicy(model.pack(model.load_model()), n, device="cuda", period=300)
+    obs = sim.obs
+    pol.reset(obs[:, 0:2].double() - CUBE_SITE_OFFSET)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s in range(steps):
+        a = pol.step()
+        a[:n // 2] = acts[s % acts.shape[0], :n // 2]
+        ev[s][0].record()
+        obs, _, term, trunc, _ = sim.step(a)
+        ev[s][1].record()
+        pol.observe(obs, (term | trunc).bool())
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    d = sim.diagnostics()
+    seg = [sum(ms[k:k + 50]) / 50 for k in range(0, steps - 49, 50)]
+    print(f"mix N={n}: {sum(ms) / steps:.3f} ms/step {n * steps / sum(ms) * 1e3:,.0f} env-steps/s; per 50 steps: "
+          + " ".join(f"{x:.2f}" for x in seg) + f"; successes {d['successes']} iters/solve {d['newton_iters'] / max(d['solver_runs'], 1):.2f}")
 
 
 if __name__ == "__main__":
