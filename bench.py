@@ -269,6 +269,8 @@ def run_gpu(args):
 
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
+        from gym_so100_c_b200.engine import measure_fp32_peak
+        fp32_peak = measure_fp32_peak(local)
         n_total = n * world
         value = n_total * K / (total_ms * 1e-3)
         # dominant kernel of the step = the full-batch kernel with the largest share of device time.  The queue-driven
@@ -314,7 +316,10 @@ def run_gpu(args):
                                               "note": "the binding resource (DESIGN.md section 5): per-GPU share of all issue slots"},
                          "fp32_convention": {"flop_per_env_step": FLOP_PER_ENV_STEP, "achieved_tflops": fp32_tflops,
                                              "peak_tflops_nominal": FP32_PEAK_NOMINAL_TFLOPS,
-                                             "frac": fp32_tflops / FP32_PEAK_NOMINAL_TFLOPS}},
+                                             "peak_tflops_measured": fp32_peak,
+                                             "peak_source": "FFMA loop measured in this run (so100_measure_fp32_peak)",
+                                             "frac": fp32_tflops / fp32_peak,
+                                             "frac_of_nominal": fp32_tflops / FP32_PEAK_NOMINAL_TFLOPS}},
             "cpu_baseline": {"value": cpu_value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": f"{cpu_n} envs x {cpu_steps} steps of the same workload, fp64 C restatement (oracle/), OpenMP over envs"},
             "e2e": {"value": n_total * Ke / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world,

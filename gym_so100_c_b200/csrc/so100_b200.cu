@@ -34,8 +34,11 @@ constexpr int BLOCK = 128, TPB_K3L = SO100_TPB_K3L;
 #define SO100_K2B_BLOCKS_PER_SM 2     // and at least n / 8 blocks (one tile per ~2 envs; 0.18 GJK items per env)
 #endif
 #ifndef SO100_K3H_BLOCKS
-#define SO100_K3H_BLOCKS 296          // 2 per SM: random actions queue 0-10 heavy envs per 2048-env group and substep (any grid
-                                      // >= 37 blocks measures the same), synchronized grasps (scripted / trained policies) queue half the group
+#define SO100_K3H_BLOCKS 37           // heavy queue (> 8 contacts): 148 tiles; rare under any policy
+#endif
+#ifndef SO100_K3M_BLOCKS
+#define SO100_K3M_BLOCKS 148          // medium queue (arm-cube contact): 0-10 envs per 2048-env group and substep under random
+                                      // actions, half the group when a policy holds the cubes
 #endif
 enum { CLS_KIN = 0, CLS_BOX = 1, CLS_SOLVE = 2, CLS_TASK = 3, CLS_HULL = 4, CLS_HEAVY = 5, CLS_N = 6 };
 
@@ -56,8 +59,8 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 // bulk of another's.  The heavy solve queue of each group drains on a second stream beside the light kernel.
 struct EnvGroup {
   int off = 0, n = 0;
-  cudaStream_t st = nullptr, side = nullptr;            // st == nullptr: the caller's stream
-  cudaEvent_t fork = nullptr, join = nullptr, done = nullptr;
+  cudaStream_t st = nullptr, side = nullptr, side2 = nullptr;   // st == nullptr: the caller's stream; side: K3m, side2: K3h
+  cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr, done = nullptr;
   cudaEvent_t t_done = nullptr;                         // timing-enabled twin of `done` (so100_group_times)
   cudaEvent_t staged = nullptr;                         // recorded after the group's first position stage of a step (stagger)
   int* ctl = nullptr;                                   // this group's queue control words
@@ -76,7 +79,7 @@ struct so100_ctx {
   uchar4* bpair = nullptr;
   unsigned long long* diag = nullptr;
   float* work = nullptr;      // [N, WORK_WORDS] phase-pipeline workspace (L2-resident)
-  int* qmem = nullptr;        // queue control words + heavy queue [N] + hull-pair queue [N * NHP]
+  int* qmem = nullptr;        // queue control words + heavy queue [N] + hull-pair queue [N * NHP] + medium queue [N]
   int* order = nullptr;       // solve order permutations: [2][N] for the env groups, [2][N] for the whole-batch group
   // so100_step replays a CUDA graph of its whole launch sequence (all groups, forks and joins): the host cost of a step
   // drops from several hundred launch / event calls to one cudaGraphLaunch.  Actions are staged into a fixed buffer so
@@ -95,7 +98,7 @@ struct so100_ctx {
   // two are about a third of a substep apart for the rest of the step; 2 chains all groups that way.
   int stagger = 0;   // measured on B200: 1 and 2 are 1-9 % slower than 0 at 4096 / 16384 / 65536 envs (the groups drift apart on their own)
   int sm_count = 148;
-  int k3h_blocks = SO100_K3H_BLOCKS;   // SO100_K3H_BLOCKS (environment) overrides
+  int k3h_blocks = SO100_K3H_BLOCKS, k3m_blocks = SO100_K3M_BLOCKS;   // SO100_K3H_BLOCKS / SO100_K3M_BLOCKS (environment) override
   // so100_step ends with a collision stage on the post-step state (mj_step1), and the next so100_step starts with one on the
   // same state: while nothing else has touched the state in between, the first substep reuses those contact lists
   // (bit-identical by construction; envs auto-reset by the task kernel are marked stale and recomputed).  SO100_REUSE=0 disables.
@@ -108,7 +111,8 @@ struct so100_ctx {
   DevTables tables() const { return DevTables{geom, pair, vert, bpair}; }
   static constexpr int CTL_WORDS = 8 * 40;
   Queues queues(const EnvGroup& G) const {
-    return Queues{G.ctl, qmem + CTL_WORDS + n + (size_t)G.off * NHP, qmem + CTL_WORDS + G.off, G.order + (size_t)G.parity * n,
+    return Queues{G.ctl, qmem + CTL_WORDS + n + (size_t)G.off * NHP, qmem + CTL_WORDS + G.off,
+                  qmem + CTL_WORDS + (size_t)(1 + NHP) * n + G.off, G.order + (size_t)G.parity * n,
                   G.order + (size_t)(1 - G.parity) * n};
   }
 };
@@ -357,7 +361,8 @@ static int configure_kernels() {
   CUDA_OK(cudaFuncSetAttribute(phase_collide_box<LPE_K2A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<BoxS>(LPE_K2A)));
   CUDA_OK(cudaFuncSetAttribute(phase_collide_hull<LPE_K2B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<HullS>(LPE_K2B)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_light<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L)));
-  CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NC>>(LPE_K3H)));
+  CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NC>>(LPE_K3H)));
+  CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H, NCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3H)));
   done = true;
   return SO100_OK;
 }
@@ -397,15 +402,27 @@ static void launch_solve_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const
   float* state = h->state + (size_t)G.off * STATE_WORDS;
   const float* work = h->work + (size_t)G.off * WORK_WORDS;
   cudaEventRecord(G.fork, st);
-  cudaStreamWaitEvent(G.side, G.fork, 0);
-  mark(h, G.side, CLS_HEAVY, true);
-  phase_solve_heavy<LPE_K3H><<<std::min(grid_of(n, LPE_K3H), h->k3h_blocks), BLOCK, smem_of<SolS<NC>>(LPE_K3H), G.side>>>(state, work, T, Q, O);
-  mark(h, G.side, CLS_HEAVY, false);
-  cudaEventRecord(G.join, G.side);
+  if (h->timing) {
+    // timing mode: one stream, so that the event pair brackets both queue kernels
+    mark(h, st, CLS_HEAVY, true);
+    phase_solve_heavy<LPE_K3H, NCL><<<std::min(grid_of(n, LPE_K3H), h->k3m_blocks), BLOCK, smem_of<SolS<NCL>>(LPE_K3H), st>>>(state, work, T, Q, O);
+    phase_solve_heavy<LPE_K3H, NC><<<std::min(grid_of(n, LPE_K3H), h->k3h_blocks), BLOCK, smem_of<SolS<NC>>(LPE_K3H), st>>>(state, work, T, Q, O);
+    mark(h, st, CLS_HEAVY, false);
+  } else {
+    cudaStreamWaitEvent(G.side, G.fork, 0);
+    cudaStreamWaitEvent(G.side2, G.fork, 0);
+    phase_solve_heavy<LPE_K3H, NCL><<<std::min(grid_of(n, LPE_K3H), h->k3m_blocks), BLOCK, smem_of<SolS<NCL>>(LPE_K3H), G.side>>>(state, work, T, Q, O);
+    phase_solve_heavy<LPE_K3H, NC><<<std::min(grid_of(n, LPE_K3H), h->k3h_blocks), BLOCK, smem_of<SolS<NC>>(LPE_K3H), G.side2>>>(state, work, T, Q, O);
+    cudaEventRecord(G.join, G.side);
+    cudaEventRecord(G.join2, G.side2);
+  }
   mark(h, st, CLS_SOLVE, true);
   phase_solve_light<LPE_K3L><<<grid_of(n, LPE_K3L, TPB_K3L), TPB_K3L, smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L), st>>>(state, work, n, T, Q, O);
   mark(h, st, CLS_SOLVE, false);
-  cudaStreamWaitEvent(st, G.join, 0);
+  if (!h->timing) {
+    cudaStreamWaitEvent(st, G.join, 0);
+    cudaStreamWaitEvent(st, G.join2, 0);
+  }
 }
 
 static int make_group(so100_ctx* h, EnvGroup& G, int off, int n, int index, bool own_stream) {
@@ -419,6 +436,8 @@ static int make_group(so100_ctx* h, EnvGroup& G, int off, int n, int index, bool
   }
   if (own_stream) CUDA_OK(cudaStreamCreateWithFlags(&G.st, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&G.side, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&G.side2, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&G.join2, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.fork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.join, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
@@ -429,6 +448,8 @@ static int make_group(so100_ctx* h, EnvGroup& G, int off, int n, int index, bool
 static void free_group(EnvGroup& G) {
   if (G.st) cudaStreamDestroy(G.st);
   if (G.side) cudaStreamDestroy(G.side);
+  if (G.side2) cudaStreamDestroy(G.side2);
+  if (G.join2) cudaEventDestroy(G.join2);
   if (G.fork) cudaEventDestroy(G.fork);
   if (G.join) cudaEventDestroy(G.join);
   if (G.done) cudaEventDestroy(G.done);
@@ -499,8 +520,8 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   CUDA_OK(cudaMalloc(&h->diag, SO100_NDIAG * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&h->work, (size_t)num_envs * WORK_WORDS * sizeof(float)));
   CUDA_OK(cudaMemset(h->work, 0, (size_t)num_envs * WORK_WORDS * sizeof(float)));
-  CUDA_OK(cudaMalloc(&h->qmem, (so100_ctx::CTL_WORDS + (1 + NHP) * (size_t)num_envs) * sizeof(int)));
-  CUDA_OK(cudaMemset(h->qmem, 0, (so100_ctx::CTL_WORDS + (1 + NHP) * (size_t)num_envs) * sizeof(int)));
+  CUDA_OK(cudaMalloc(&h->qmem, (so100_ctx::CTL_WORDS + (2 + NHP) * (size_t)num_envs) * sizeof(int)));
+  CUDA_OK(cudaMemset(h->qmem, 0, (so100_ctx::CTL_WORDS + (2 + NHP) * (size_t)num_envs) * sizeof(int)));
   CUDA_OK(cudaMalloc(&h->order, 4 * (size_t)num_envs * sizeof(int)));
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->t_start));
@@ -511,6 +532,7 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   if (const char* e = getenv("SO100_GRAPH")) h->use_graph = atoi(e) != 0;
   if (const char* e = getenv("SO100_REUSE")) h->reuse_enabled = atoi(e) != 0;
   if (const char* e = getenv("SO100_K3H_BLOCKS")) h->k3h_blocks = std::max(1, atoi(e));
+  if (const char* e = getenv("SO100_K3M_BLOCKS")) h->k3m_blocks = std::max(1, atoi(e));
   {
     // env groups: SO100_GROUPS overrides; default one group per 1024 envs, at most 8 (measured on B200: 4096 envs
     // 1.50 -> 1.73 M env-steps/s with 4 groups, 16384 envs 4.0 -> 5.0 M with 8, no gain beyond 8 at any batch size)
@@ -576,7 +598,7 @@ int so100_num_envs(so100_handle h) { return h ? h->n : SO100_ERR_ARG; }
 
 int so100_launches_per_step(so100_handle h) {
   if (!h) return SO100_ERR_ARG;
-  const int per_group = h->nsub * 5 + 3 + 1;   // nsub x (K1, K2a, K2b, K3l, K3h) + trailing (K1, K2a, K2b) + K4
+  const int per_group = h->nsub * 6 + 3 + 1;   // nsub x (K1, K2a, K2b, K3l, K3m, K3h) + trailing (K1, K2a, K2b) + K4
   return per_group * (int)std::max<size_t>(h->groups.size(), 1);
 }
 
@@ -767,6 +789,37 @@ int so100_hull_stats(int32_t* out /* host [65536][4] */) {
   return n;
 }
 #endif
+
+int so100_measure_fp32_peak(int device, float* tflops) {
+  if (!tflops) return fail(SO100_ERR_ARG, "so100_measure_fp32_peak: null output");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(SO100_ERR_CUDA, "so100_measure_fp32_peak: no such CUDA device");
+  CUDA_OK(cudaSetDevice(device));
+  int sms = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int blocks = sms * 8, threads = 256, iters = 1 << 15;
+  float* sink = nullptr;
+  CUDA_OK(cudaMalloc(&sink, (size_t)blocks * threads * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  float best = 0.0f;
+  for (int rep = 0; rep < 4; rep++) {     // first repetition warms the clocks up
+    cudaEventRecord(e0);
+    fma_peak_kernel<<<blocks, threads>>>(sink, iters, 1.0001f);
+    cudaEventRecord(e1);
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0) best = std::max(best, (float)(flops / (ms * 1e-3) / 1e12));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink);
+  *tflops = best;
+  return SO100_OK;
+}
 
 int so100_group_times(so100_handle h, float* ms, int32_t* ngroups, void* stream) {
   if (!h || !ms || !ngroups) return fail(SO100_ERR_ARG, "so100_group_times: bad argument");

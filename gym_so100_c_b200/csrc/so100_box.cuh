@@ -226,8 +226,8 @@ __device__ int box_contacts(const Tile<LPE>& t, float* con, int base, const Obb&
 }
 
 // Stage A for one env.  Writes the contact list and the header of workspace record `w`; returns (on every lane)
-// the number of hull pairs that need GJK/EPA, with *ncon_out the contact count so far (NC + 1 = overflow, NC + 2 = an
-// arm-cube contact exists: the env belongs to the heavy solve kernel).
+// the number of hull pairs that need GJK/EPA, with *ncon_out the contact count so far (NC + 1 = overflow) and *coupled_out
+// whether one of them joins an arm link and the cube (dense Hessian: medium / heavy solve kernel).
 //   1. world bounds of the 25 collidable geoms (one lane each): centre + bounding radius, AABB half extents;
 //   2. broad phase over the static 191-pair table (one lane per pair): sphere-sphere and AABB-AABB; any
 //      conservative filter gives the same contacts, because every survivor goes through the exact test of 3;
@@ -235,7 +235,7 @@ __device__ int box_contacts(const Tile<LPE>& t, float* con, int base, const Obb&
 //      pairs in the same rounds): penetrating box pairs -> q1 with their axis code, hull pairs whose boxes
 //      overlap -> the GJK/EPA list in the workspace header;
 //   4. contact points, whole tile per penetrating box pair.
-template <unsigned LPE> __device__ int collide_box_env(const Tile<LPE>& t, BoxS* S, float* w, const DevTables& T, int* ncon_out) {
+template <unsigned LPE> __device__ int collide_box_env(const Tile<LPE>& t, BoxS* S, float* w, const DevTables& T, int* ncon_out, bool* coupled_out) {
   const int lane = t.thread_rank();
   const unsigned lt = (1u << lane) - 1u;
   float* con = w + W_CON;
@@ -315,7 +315,8 @@ template <unsigned LPE> __device__ int collide_box_env(const Tile<LPE>& t, BoxS*
   if (npen > NPEN || nsurv > NHP) { ncon = NC + 1; nsurv = min(nsurv, NHP); }
   if (lane == 0)
     *reinterpret_cast<int4*>(w + W_HDR) = make_int4(ncon, nsurv, min(nbox, 255) | (min(npen, 255) << 8) | (min(ncand - nbox, 255) << 16) | coupled, nsurv);
-  *ncon_out = coupled ? NC + 2 : ncon;    // a coupling contact sends the env to the heavy solve kernel whatever its count
+  *ncon_out = ncon;
+  *coupled_out = coupled != 0;
   return nsurv;
 }
 

@@ -407,9 +407,9 @@ __device__ V3 deepest_feature_point(const Tile<LPE>& t, const Shape& A, const Sh
 
 // Stage B, one queue item = one hull pair of one env: GJK/EPA with the whole tile; the result goes to the pair's
 // staging slot.  The tile that finishes an env's last pending pair merges the staged contacts into the contact list
-// in pair order (deterministic contact order, after the box contacts) and returns the final count (NC + 2 when an arm-cube
-// contact exists); every other tile returns -1.
-template <unsigned LPE> __device__ int collide_hull_item(const Tile<LPE>& t, HullS* S, float* w, int slot, const DevTables& T) {
+// in pair order (deterministic contact order, after the box contacts) and returns the final count, with *coupled_out
+// whether an arm-cube contact exists; every other tile returns -1.
+template <unsigned LPE> __device__ int collide_hull_item(const Tile<LPE>& t, HullS* S, float* w, int slot, const DevTables& T, bool* coupled_out) {
   const int lane = t.thread_rank();
   const int p = reinterpret_cast<const unsigned char*>(w + W_HULLP)[slot];
   const DevPair& P = T.pair[p];
@@ -476,7 +476,8 @@ template <unsigned LPE> __device__ int collide_hull_item(const Tile<LPE>& t, Hul
     hdr[0] = ncon;
     if (couples) hdr[2] |= HDR_COUPLED;
   }
-  return couples ? NC + 2 : ncon;
+  *coupled_out = couples;
+  return ncon;
 }
 
 }  // namespace so100

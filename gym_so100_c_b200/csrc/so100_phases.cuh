@@ -73,21 +73,22 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_box
   if (reuse) {
     const int4 hdr = *reinterpret_cast<const int4*>(w + W_HDR);
     if (hdr.w == 0) {
-      if (lane == 0 && ((hdr.z & HDR_COUPLED) || hdr.x > NCL)) Q.heavy[atomicAdd(&Q.ctl[Q_HEAVY_COUNT], 1)] = env;
+      if (lane == 0) Q.route(env, hdr.x, (hdr.z & HDR_COUPLED) != 0);
       return;
     }
   }
   copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
   t.sync();
   int ncon;
-  const int nsurv = collide_box_env(t, S, w, T, &ncon);
+  bool coupled;
+  const int nsurv = collide_box_env(t, S, w, T, &ncon, &coupled);
   if (nsurv > 0) {
     int base = 0;
     if (lane == 0) base = atomicAdd(&Q.ctl[Q_HULL_COUNT], nsurv);
     base = t.shfl(base, 0);
     if (lane < nsurv) Q.hull[base + lane] = env * NHP + lane;
-  } else if (lane == 0 && ncon > NCL) {
-    Q.heavy[atomicAdd(&Q.ctl[Q_HEAVY_COUNT], 1)] = env;
+  } else if (lane == 0) {
+    Q.route(env, ncon, coupled);
   }
 }
 
@@ -104,8 +105,9 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_hul
     float* w = work + (size_t)env * WORK_WORDS;
     copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
     t.sync();
-    const int ncon = collide_hull_item(t, S, w, item % NHP, T);
-    if (lane == 0 && ncon > NCL) Q.heavy[atomicAdd(&Q.ctl[Q_HEAVY_COUNT], 1)] = env;
+    bool coupled = false;
+    const int ncon = collide_hull_item(t, S, w, item % NHP, T, &coupled);
+    if (lane == 0 && ncon >= 0) Q.route(env, ncon, coupled);
     t.sync();
   }
 }
@@ -181,21 +183,29 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
   }
 }
 
-// K3h: persistent tiles drain the heavy queue
+// K3h / K3m: persistent tiles drain the heavy queue (NCAP = NC: more than NCL contacts) or the medium queue (NCAP = NCL: an
+// arm-cube contact among at most NCL), both with the dense Hessian.  The medium instantiation carries one contact row per
+// lane instead of three: fewer registers (more resident tiles when a policy holds thousands of cubes at once) and shorter
+// Newton iterations for the coupled stragglers that end every group's solve stage.
 #ifndef SO100_K3H_MINB
 #define SO100_K3H_MINB 1      // resident blocks per SM the heavy solve kernel's register allocation must allow (168 registers, 3
                               // blocks; measured on B200: 4 (128 registers, spills) -8 %, 5 (96 registers) -14 % env-steps/s)
 #endif
-template <unsigned LPE>
-__global__ void __launch_bounds__(128, SO100_K3H_MINB) phase_solve_heavy(float* state, const float* work, DevTables T, Queues Q, SolveOut O) {
-  SO100_TILE_PROLOGUE(LPE, 128, SolS<NC>);
-  const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_HEAVY_COUNT]);
+#ifndef SO100_K3M_MINB
+#define SO100_K3M_MINB 3      // the same for the medium instantiation
+#endif
+template <unsigned LPE, int NCAP>
+__global__ void __launch_bounds__(128, NCAP == NCL ? SO100_K3M_MINB : SO100_K3H_MINB) phase_solve_heavy(float* state, const float* work, DevTables T, Queues Q, SolveOut O) {
+  SO100_TILE_PROLOGUE(LPE, 128, SolS<NCAP>);
+  constexpr bool MED = NCAP == NCL;
+  const int* queue = MED ? Q.medium : Q.heavy;
+  const int count = *reinterpret_cast<volatile int*>(&Q.ctl[MED ? Q_MED_COUNT : Q_HEAVY_COUNT]);
   for (;;) {
     int i = 0;
-    if (lane == 0) i = atomicAdd(&Q.ctl[Q_HEAVY_NEXT], 1);
+    if (lane == 0) i = atomicAdd(&Q.ctl[MED ? Q_MED_NEXT : Q_HEAVY_NEXT], 1);
     i = t.shfl(i, 0);
     if (i >= count) break;
-    const int env = Q.heavy[i];
+    const int env = queue[i];
     const float* w = work + (size_t)env * WORK_WORDS;
     solve_env<true>(t, S, state + (size_t)env * STATE_WORDS, w, env, __float_as_int(w[W_HDR]), T, O);
     t.sync();
@@ -305,6 +315,18 @@ __global__ void init_state_kernel(float* state, int n) {
   float v = 0.0f;
   if (k == S_QPOS + 9) v = 1.0f;
   state[(size_t)env * STATE_WORDS + k] = v;
+}
+
+// so100_measure_fp32_peak: 8 independent FFMA chains per thread, everything in registers
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* sink, int iters, float m) {
+  float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const float c = 1e-3f;
+#pragma unroll 4
+  for (int i = 0; i < iters; i++) {
+    a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+    a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+  }
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
 // sums the per-env uint32 counters into out[8] (uint64)

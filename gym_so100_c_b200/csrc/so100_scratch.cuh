@@ -48,17 +48,24 @@ static_assert(WORK_WORDS % 8 == 0 && W_HDR % 4 == 0 && W_CON % 4 == 0, "workspac
 static_assert(NHP <= 16, "hull pair list is 4 words");
 
 // queue control words (device ints)
-enum { Q_HULL_COUNT = 0, Q_HULL_NEXT = 1, Q_HEAVY_COUNT = 2, Q_HEAVY_NEXT = 3, Q_SLOW = 4, Q_FAST = 5, Q_WORDS = 6 };
+enum { Q_HULL_COUNT = 0, Q_HULL_NEXT = 1, Q_HEAVY_COUNT = 2, Q_HEAVY_NEXT = 3, Q_SLOW = 4, Q_FAST = 5, Q_MED_COUNT = 6, Q_MED_NEXT = 7, Q_WORDS = 8 };
 
 struct Queues {
   int* ctl;      // [Q_WORDS]
   int* hull;     // [N * NHP] hull pairs for GJK/EPA this substep, one item = env * NHP + slot
   int* heavy;    // [N] envs with more than NCL contacts this substep
+  int* medium;   // [N] envs with at most NCL contacts, one of which couples the arm and the cube (dense Hessian)
   // Longest-first order of the light solve kernel: block b solves env order_in[b].  Envs that needed >= 3 Newton
   // iterations (or went to the heavy kernel) are written to the front of order_out, the rest to the back, so that the
   // next substep starts its likely stragglers first (the iteration count of an env is strongly correlated in time).
   const int* order_in;
   int* order_out;
+  // work class of an env whose collision stage is complete: > NCL contacts (or list overflow) -> heavy queue; an arm-cube
+  // contact among <= NCL -> medium queue; everything else is solved by the regular grid of the light kernel
+  __device__ __forceinline__ void route(int env, int ncon, bool coupled) const {
+    if (ncon > NCL) heavy[atomicAdd(&ctl[Q_HEAVY_COUNT], 1)] = env;
+    else if (coupled) medium[atomicAdd(&ctl[Q_MED_COUNT], 1)] = env;
+  }
 };
 
 // ---------------------------------------------------------------- scratch structs

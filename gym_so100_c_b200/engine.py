@@ -16,6 +16,13 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def measure_fp32_peak(device: int = 0) -> float:
+    """Achieved FP32 FFMA rate of `device` in TFLOP/s (so100_measure_fp32_peak)."""
+    out = C.c_float(0.0)
+    ext.check(ext.load().so100_measure_fp32_peak(int(device), C.byref(out)), "so100_measure_fp32_peak")
+    return float(out.value)
+
+
 class BatchedSim:
     """N independent bin-a-cube simulations resident on one CUDA device."""
 

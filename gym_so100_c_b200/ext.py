@@ -16,6 +16,7 @@ SYMBOLS = [
     "so100_create", "so100_destroy", "so100_num_envs", "so100_launches_per_step", "so100_reset", "so100_step", "so100_step_host",
     "so100_compute_reward", "so100_get_state", "so100_set_state", "so100_get_aux", "so100_set_aux",
     "so100_substeps", "so100_forward", "so100_diagnostics", "so100_phase_timing", "so100_group_times", "so100_debug_read", "so100_last_error",
+    "so100_measure_fp32_peak",
 ]
 
 MAX_CONTACTS = 24
@@ -62,6 +63,7 @@ def load():
     lib.so100_diagnostics.argtypes = [vp, vp, vp]
     lib.so100_phase_timing.argtypes = [vp, i32, vp, vp, vp]
     lib.so100_group_times.argtypes = [vp, vp, vp, vp]
+    lib.so100_measure_fp32_peak.argtypes = [i32, vp]
     lib.so100_debug_read.argtypes = [vp, i32, vp, vp, vp]
     lib.so100_last_error.restype = C.c_char_p
     for name in SYMBOLS:

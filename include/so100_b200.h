@@ -120,6 +120,11 @@ int so100_diagnostics(so100_handle h, int64_t* out8, void* stream);
  * queue, [5] constraint solve, heavy queue -- then clears the record and sets the mode. */
 int so100_phase_timing(so100_handle h, int enable, float* ms6, int32_t* launches6, void* stream);
 
+/* Measurement aid (SURVEY.md 8d "the builder must measure an FFMA-loop peak"): runs a register-resident FFMA loop (8
+ * independent chains per thread, 8 blocks of 256 threads per SM) on `device` and returns the achieved FP32 rate in TFLOP/s
+ * (FMA = 2 flops), timed with CUDA events.  bench.py quotes the step's FP32 fraction against this number. */
+int so100_measure_fp32_peak(int device, float* tflops);
+
 /* Development aid (SO100_GROUP_TIMES=1 in the environment at create): device time from the start of the last so100_step
  * to the completion of each env group's pipeline.  ms: host float[32]; *ngroups receives the count (0 when disabled). */
 int so100_group_times(so100_handle h, float* ms, int32_t* ngroups, void* stream);

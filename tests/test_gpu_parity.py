@@ -250,7 +250,7 @@ def test_groups_and_graph_replay_are_bit_invariant(model_blob, monkeypatch):
         for k in range(6):
             obs, r, term, trunc, succ = sim.step(acts[k], autoreset=True)
             rew.append(r.clone())
-        assert sim.launches_per_step() == 54 * int(groups)
+        assert sim.launches_per_step() == 64 * int(groups)
         results.append([t.cpu().numpy() for t in sim.get_state()] + [torch.stack(rew).cpu().numpy(), obs.cpu().numpy()])
         assert sim.diagnostics()["episodes"] >= n
         sim.close()
