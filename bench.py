@@ -31,20 +31,21 @@ FLOP_PER_ENV_STEP = 1.0e6             # SURVEY.md Appendix C convention F_contac
 FP32_PEAK_NOMINAL_TFLOPS = 74.4       # 148 SM x 128 lanes x 2 x 1.965 GHz
 METRIC = "env-steps/sec (bin-a-cube)"
 # warp-instructions per env-step of the steady-state workload, from the ncu launch list in profiles/r01_phase_launches.txt
-# (per 2048-env launch: solve_light 5.70 M, collide_box 3.18 M, kin_dyn 1.72 M, collide_hull 0.15 M, solve_heavy 0.02 M per
-# substep, plus the trailing position stage and the task kernel): 10 x 5259 + 2944
-WARP_INSTR_PER_ENV_STEP = 55.5e3
+# (per 2048-env launch: solve_light 5.64 M, collide_box 2.95 M averaged over the 10 full and 1 reusing launch, kin_dyn 1.73 M,
+# collide_hull 0.15 M, solve_heavy 0.05 M per launch of either instantiation, task 0.99 M):
+# (10 x 5.64 + 11 x (1.73 + 2.95 + 0.15) + 20 x 0.05 + 0.99) M / 2048
+WARP_INSTR_PER_ENV_STEP = 54.4e3
 ISSUE_SLOTS_PER_S = 148 * 4 * 1.965e9        # SMs x schedulers x max SM clock: one warp-instruction per scheduler and cycle
 # Algorithmic bytes one env moves per launch of each phase kernel (4-byte words):
 #   kin_dyn       reads qpos13+qvel12+ctrl6, writes frames102 + Marm/qfs/qas45
 #   collide_box   reads frames102, writes header4 + 8 words per contact (1 contact typical)
 #   collide_hull  (queued envs only, ~14 %) reads frames102 + header8, writes 8 words per contact + header
 #   solve_light   reads state43 + frames102 + dyn45 + header1 + contacts8, writes state43 + counters4
-#   solve_heavy   (queued envs only, < 1 %) the same with up to 24 contacts
+#   solve_heavy   (queued envs only, < 1 % under random actions; medium <= 8 and heavy <= 24 contacts) the same per contact
 #   task          reads state64 + frames102 + contacts9, writes state64 + obs15 + final_obs15 + goals6 + reward + flags
 PHASE_ALG_BYTES = {"kin_dyn": (31 + 147) * 4, "collide_box": (102 + 12) * 4, "collide_hull": (110 + 9) * 4,
                    "solve_light": (199 + 47) * 4, "solve_heavy": (199 + 47) * 4, "task": (175 + 103) * 4}
-# kernel launches per step: per env group 10 x (kin_dyn, collide_box, collide_hull, solve_light, solve_heavy) + 3 + task,
+# kernel launches per step: per env group 10 x (kin_dyn, collide_box, collide_hull, solve_light, solve_medium, solve_heavy) + 3 + task,
 # replayed as ONE CUDA graph; the count comes from the library (so100_launches_per_step)
 
 
