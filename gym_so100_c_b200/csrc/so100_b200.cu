@@ -84,7 +84,7 @@ struct so100_ctx {
   // so100_step replays a CUDA graph of its whole launch sequence (all groups, forks and joins): the host cost of a step
   // drops from several hundred launch / event calls to one cudaGraphLaunch.  Actions are staged into a fixed buffer so
   // that the graph's kernel arguments never change; one graph is cached per distinct set of output pointers.
-  struct StepGraph { const void* key[10]; cudaGraphExec_t exec; };
+  struct StepGraph { const void* key[18]; cudaGraphExec_t exec; };
   std::vector<StepGraph> graphs;
   cudaStream_t cap = nullptr;
   float* act_stage = nullptr;
@@ -614,8 +614,16 @@ int so100_reset(so100_handle h, const uint8_t* mask, const float* box_pose, floa
   return SO100_OK;
 }
 
+// Page-locked host destinations of so100_step_host: every env group copies its slice of the results out on its own stream
+// as soon as its task kernel is done, so the device -> host traffic of the early groups hides behind the late groups' compute
+// (and, under graph replay, costs no launch calls).
+struct HostOut {
+  float *obs = nullptr, *achieved = nullptr, *desired = nullptr, *reward = nullptr, *final_obs = nullptr;
+  uint8_t *terminated = nullptr, *truncated = nullptr, *success = nullptr;
+};
+
 // the launch sequence of one env step on `stream` (directly, or while `stream` is being captured into a graph)
-static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream, int reuse) {
+static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream, int reuse, const HostOut* ho = nullptr) {
   const float* action = A.action;
   for_each_group(h, stream, true, [&](EnvGroup& G, cudaStream_t st) {
     const SolveOut O{nullptr, nullptr, 0};
@@ -640,12 +648,18 @@ static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream, i
     mark(h, st, CLS_TASK, true);
     phase_task<LPE_K4><<<grid_of(G.n, LPE_K4), BLOCK, smem_of<TaskS>(LPE_K4), st>>>(B, h->work + o * WORK_WORDS, h->tables());
     mark(h, st, CLS_TASK, false);
+    if (ho) {
+      auto out = [&](void* dst, const void* src, size_t per_env) {
+        if (dst && src) cudaMemcpyAsync((char*)dst + o * per_env, src, (size_t)G.n * per_env, cudaMemcpyDeviceToHost, st);
+      };
+      out(ho->obs, B.obs, 60); out(ho->final_obs, B.final_obs, 60); out(ho->achieved, B.achieved, 12); out(ho->desired, B.desired, 12);
+      out(ho->reward, B.reward, 4); out(ho->terminated, B.terminated, 1); out(ho->truncated, B.truncated, 1); out(ho->success, B.success, 1);
+    }
   });
 }
 
-int so100_step(so100_handle h, const float* action, int autoreset, float* obs, float* achieved, float* desired, float* reward,
-               uint8_t* terminated, uint8_t* truncated, uint8_t* success, float* final_obs, void* stream) {
-  if (!h || !action) return fail(SO100_ERR_ARG, "so100_step: null handle or action");
+static int step_impl(so100_handle h, const float* action, int autoreset, float* obs, float* achieved, float* desired, float* reward,
+                     uint8_t* terminated, uint8_t* truncated, uint8_t* success, float* final_obs, void* stream, const HostOut* ho) {
   StepArgs A;
   A.state = h->state; A.action = action; A.obs = obs; A.achieved = achieved; A.desired = desired; A.reward = reward;
   A.final_obs = final_obs; A.terminated = terminated; A.truncated = truncated; A.success = success;
@@ -655,14 +669,18 @@ int so100_step(so100_handle h, const float* action, int autoreset, float* obs, f
   const int reuse = (h->reuse_enabled && h->work_fresh && h->nsub > 0) ? 1 : 0;
   h->work_fresh = true;
   if (!h->use_graph || h->timing) {
-    enqueue_step(h, A, st, reuse);
+    enqueue_step(h, A, st, reuse, ho);
     CUDA_OK(cudaGetLastError());
     return SO100_OK;
   }
   CUDA_OK(cudaMemcpyAsync(h->act_stage, action, (size_t)h->n * 6 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   A.action = h->act_stage;
-  const void* key[10] = {obs, achieved, desired, reward, terminated, truncated, success, final_obs,
+  const void* key[18] = {obs, achieved, desired, reward, terminated, truncated, success, final_obs,
                          reinterpret_cast<const void*>((size_t)(autoreset != 0)), reinterpret_cast<const void*>((size_t)reuse)};
+  if (ho) {
+    const void* hk[8] = {ho->obs, ho->achieved, ho->desired, ho->reward, ho->final_obs, ho->terminated, ho->truncated, ho->success};
+    memcpy(key + 10, hk, sizeof(hk));
+  }
   cudaGraphExec_t exec = nullptr;
   for (auto& g : h->graphs)
     if (memcmp(g.key, key, sizeof(key)) == 0) exec = g.exec;
@@ -670,7 +688,7 @@ int so100_step(so100_handle h, const float* action, int autoreset, float* obs, f
     cudaGraph_t graph = nullptr;
     CUDA_OK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal));
     h->capturing = true;
-    enqueue_step(h, A, h->cap, reuse);
+    enqueue_step(h, A, h->cap, reuse, ho);
     h->capturing = false;
     CUDA_OK(cudaStreamEndCapture(h->cap, &graph));
     CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
@@ -683,6 +701,12 @@ int so100_step(so100_handle h, const float* action, int autoreset, float* obs, f
   }
   CUDA_OK(cudaGraphLaunch(exec, st));
   return SO100_OK;
+}
+
+int so100_step(so100_handle h, const float* action, int autoreset, float* obs, float* achieved, float* desired, float* reward,
+               uint8_t* terminated, uint8_t* truncated, uint8_t* success, float* final_obs, void* stream) {
+  if (!h || !action) return fail(SO100_ERR_ARG, "so100_step: null handle or action");
+  return step_impl(h, action, autoreset, obs, achieved, desired, reward, terminated, truncated, success, final_obs, stream, nullptr);
 }
 
 int so100_step_host(so100_handle h, const float* action, int autoreset, float* obs, float* achieved, float* desired,
@@ -702,18 +726,33 @@ int so100_step_host(so100_handle h, const float* action, int autoreset, float* o
     CUDA_OK(cudaMalloc(&h->h_succ, n));
   }
   CUDA_OK(cudaMemcpyAsync(h->h_action, action, n * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
-  int rc = so100_step(h, h->h_action, autoreset, h->h_obs, achieved ? h->h_ag : nullptr, desired ? h->h_dg : nullptr,
-                      reward ? h->h_rew : nullptr, terminated ? h->h_term : nullptr, truncated ? h->h_trunc : nullptr,
-                      success ? h->h_succ : nullptr, final_obs ? h->h_fin : nullptr, stream);
+  // page-locked destinations: the copies out ride in the step's own pipeline (per env group, see HostOut); pageable ones are
+  // copied after the step (an asynchronous copy to pageable memory is staged by the driver and cannot be captured)
+  auto pinned = [](const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const bool in_pipeline = pinned(obs) && pinned(achieved) && pinned(desired) && pinned(reward) && pinned(terminated) &&
+                           pinned(truncated) && pinned(success) && pinned(final_obs);
+  HostOut ho;
+  ho.obs = obs; ho.achieved = achieved; ho.desired = desired; ho.reward = reward; ho.final_obs = final_obs;
+  ho.terminated = terminated; ho.truncated = truncated; ho.success = success;
+  int rc = step_impl(h, h->h_action, autoreset, h->h_obs, achieved ? h->h_ag : nullptr, desired ? h->h_dg : nullptr,
+                     reward ? h->h_rew : nullptr, terminated ? h->h_term : nullptr, truncated ? h->h_trunc : nullptr,
+                     success ? h->h_succ : nullptr, final_obs ? h->h_fin : nullptr, stream, in_pipeline ? &ho : nullptr);
   if (rc) return rc;
-  if (obs) CUDA_OK(cudaMemcpyAsync(obs, h->h_obs, n * 15 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (final_obs) CUDA_OK(cudaMemcpyAsync(final_obs, h->h_fin, n * 15 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (achieved) CUDA_OK(cudaMemcpyAsync(achieved, h->h_ag, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (desired) CUDA_OK(cudaMemcpyAsync(desired, h->h_dg, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (reward) CUDA_OK(cudaMemcpyAsync(reward, h->h_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (terminated) CUDA_OK(cudaMemcpyAsync(terminated, h->h_term, n, cudaMemcpyDeviceToHost, st));
-  if (truncated) CUDA_OK(cudaMemcpyAsync(truncated, h->h_trunc, n, cudaMemcpyDeviceToHost, st));
-  if (success) CUDA_OK(cudaMemcpyAsync(success, h->h_succ, n, cudaMemcpyDeviceToHost, st));
+  if (!in_pipeline) {
+    if (obs) CUDA_OK(cudaMemcpyAsync(obs, h->h_obs, n * 15 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (final_obs) CUDA_OK(cudaMemcpyAsync(final_obs, h->h_fin, n * 15 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (achieved) CUDA_OK(cudaMemcpyAsync(achieved, h->h_ag, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (desired) CUDA_OK(cudaMemcpyAsync(desired, h->h_dg, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (reward) CUDA_OK(cudaMemcpyAsync(reward, h->h_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (terminated) CUDA_OK(cudaMemcpyAsync(terminated, h->h_term, n, cudaMemcpyDeviceToHost, st));
+    if (truncated) CUDA_OK(cudaMemcpyAsync(truncated, h->h_trunc, n, cudaMemcpyDeviceToHost, st));
+    if (success) CUDA_OK(cudaMemcpyAsync(success, h->h_succ, n, cudaMemcpyDeviceToHost, st));
+  }
   CUDA_OK(cudaStreamSynchronize(st));
   return SO100_OK;
 }

@@ -481,3 +481,41 @@ def test_goal_vec_env_surface_and_host_step(model_blob):
     assert o["observation"].shape == (8, 15) and len(infos) == 8 and "is_success" in infos[0]
     assert ad.env_method("compute_reward", o["achieved_goal"], o["desired_goal"], {})[0].shape == (8,)
     env.close()
+
+
+def test_host_step_pinned_pageable_and_device_paths_agree(model_blob):
+    """so100_step_host copies the results out inside the step's own pipeline (per env group) when the caller's buffers are
+    page-locked and after the step when they are pageable; both must return exactly what the device entry point computes,
+    with and without env groups."""
+    import ctypes as C
+    import torch
+    from gym_so100_c_b200 import ext
+    from gym_so100_c_b200.engine import BatchedSim
+    n = 4096
+    g = torch.Generator(device="cuda").manual_seed(11)
+    acts = (torch.rand((4, n, 6), device="cuda", generator=g) * 2 - 1)
+    acts_h = acts.cpu().numpy()
+    sims = [BatchedSim(n, device="cuda:0", task=1, seed=21, model_blob=model_blob) for _ in range(3)]
+    for s in sims:
+        s.reset()
+        s.set_aux(step_count=torch.full((n,), 298, dtype=torch.int32))        # truncation + auto-reset at the second step
+    names = ("obs", "achieved", "desired", "reward", "terminated", "truncated", "success", "final_obs")
+    page = dict(obs=np.zeros((n, 15), np.float32), achieved=np.zeros((n, 3), np.float32), desired=np.zeros((n, 3), np.float32),
+                reward=np.zeros(n, np.float32), terminated=np.zeros(n, np.uint8), truncated=np.zeros(n, np.uint8),
+                success=np.zeros(n, np.uint8), final_obs=np.zeros((n, 15), np.float32))
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    for k in range(4):
+        dev = sims[0].step(acts[k], autoreset=True)
+        pin = sims[1].step_host(acts_h[k], autoreset=True)
+        ext.check(sims[2].lib.so100_step_host(sims[2].h, p(acts_h[k]), 1, p(page["obs"]), p(page["achieved"]), p(page["desired"]),
+                                              p(page["reward"]), p(page["terminated"]), p(page["truncated"]), p(page["success"]),
+                                              p(page["final_obs"]), sims[2]._stream()), "so100_step_host")
+        ref = dict(obs=sims[0].obs, achieved=sims[0].achieved, desired=sims[0].desired, reward=sims[0].reward,
+                   terminated=sims[0].terminated, truncated=sims[0].truncated, success=sims[0].success, final_obs=sims[0].final_obs)
+        for name in names:
+            want = ref[name].cpu().numpy()
+            assert np.array_equal(pin[name], want), (k, name, "pinned")
+            assert np.array_equal(page[name], want), (k, name, "pageable")
+        assert bool(ref["truncated"].all()) == (k == 1)
+    for s in sims:
+        s.close()
