@@ -534,9 +534,9 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   if (const char* e = getenv("SO100_K3H_BLOCKS")) h->k3h_blocks = std::max(1, atoi(e));
   if (const char* e = getenv("SO100_K3M_BLOCKS")) h->k3m_blocks = std::max(1, atoi(e));
   {
-    // env groups: SO100_GROUPS overrides; default one group per 1024 envs, at most 8 (measured on B200: 4096 envs
-    // 1.50 -> 1.73 M env-steps/s with 4 groups, 16384 envs 4.0 -> 5.0 M with 8, no gain beyond 8 at any batch size)
-    int ng = std::min(8, num_envs / 1024);
+    // env groups: SO100_GROUPS overrides; default one group per 1024 envs, at most 6 (measured on B200 at 16384 envs with the
+    // three solve classes: 5 groups 2.53 ms, 6 2.54, 7 2.54, 8 2.56, 10 2.62 per step; 4096 envs want 4)
+    int ng = std::min(6, num_envs / 1024);
     if (const char* e = getenv("SO100_GROUPS")) ng = atoi(e);
     ng = std::max(1, std::min(ng, 32));
     rc = make_group(h, h->whole, 0, num_envs, 32, false);

@@ -76,7 +76,8 @@ int so100_step(so100_handle h, const float* action, int autoreset, float* obs, f
                float* desired, float* reward, uint8_t* terminated, uint8_t* truncated,
                uint8_t* success, float* final_obs, void* stream);
 
-/* Same as so100_step with HOST buffers (pageable or pinned): copies the actions in, steps, copies
+/* Same as so100_step with HOST buffers (pageable or pinned; with page-locked result buffers every env group copies its slice
+ * out inside the step's own pipeline, pageable ones are copied after the step): copies the actions in, steps, copies
  * the results out and synchronises `stream` before returning -- what a CPU-side caller of the
  * reference's env.step sees. */
 int so100_step_host(so100_handle h, const float* action, int autoreset, float* obs, float* achieved,
