@@ -31,7 +31,10 @@ constexpr int BLOCK = 128, TPB_K3L = SO100_TPB_K3L;
 // small enough that the blocks that find the queue empty do not crowd the SMs (the heavy solve kernel holds 27 k registers
 // and 58 KB of shared memory per block)
 #ifndef SO100_K2B_BLOCKS_PER_SM
-#define SO100_K2B_BLOCKS_PER_SM 2     // and at least n / 8 blocks (one tile per ~2 envs; 0.18 GJK items per env)
+#define SO100_K2B_BLOCKS_PER_SM 1     // and at least n / 16 blocks (one tile per 4 envs; 0.18 GJK items per env under random actions).
+                                      // Measured with 6 groups at 16384 envs: 2 per SM or n / 8 (the earlier setting) 2.55 ms per
+                                      // step, 1 per SM or n / 16 2.51, 1/2 per SM or n / 32 2.55; the scripted-grasp phase prefers
+                                      // the larger grid by 5 %
 #endif
 #ifndef SO100_K3H_BLOCKS
 #define SO100_K3H_BLOCKS 37           // heavy queue (> 8 contacts): 148 tiles; rare under any policy
@@ -98,6 +101,7 @@ struct so100_ctx {
   // two are about a third of a substep apart for the rest of the step; 2 chains all groups that way.
   int stagger = 0;   // measured on B200: 1 and 2 are 1-9 % slower than 0 at 4096 / 16384 / 65536 envs (the groups drift apart on their own)
   int sm_count = 148;
+  int k2b_blocks = 148 * SO100_K2B_BLOCKS_PER_SM, k2b_div = 16;   // SO100_K2B_BLOCKS / SO100_K2B_DIV (environment) override
   int k3h_blocks = SO100_K3H_BLOCKS, k3m_blocks = SO100_K3M_BLOCKS;   // SO100_K3H_BLOCKS / SO100_K3M_BLOCKS (environment) override
   // so100_step ends with a collision stage on the post-step state (mj_step1), and the next so100_step starts with one on the
   // same state: while nothing else has touched the state in between, the first substep reuses those contact lists
@@ -388,7 +392,7 @@ static void launch_position_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, co
   mark(h, st, CLS_KIN, false); mark(h, st, CLS_BOX, true);
   phase_collide_box<LPE_K2A><<<grid_of(n, LPE_K2A), BLOCK, smem_of<BoxS>(LPE_K2A), st>>>(work, n, T, Q, reuse);
   mark(h, st, CLS_BOX, false); mark(h, st, CLS_HULL, true);
-  phase_collide_hull<LPE_K2B><<<std::min(grid_of(n, LPE_K2B), std::max(h->sm_count * SO100_K2B_BLOCKS_PER_SM, n / 8)), BLOCK, smem_of<HullS>(LPE_K2B), st>>>(work, T, Q);
+  phase_collide_hull<LPE_K2B><<<std::min(grid_of(n, LPE_K2B), std::max(h->k2b_blocks, n / h->k2b_div)), BLOCK, smem_of<HullS>(LPE_K2B), st>>>(work, T, Q);
   mark(h, st, CLS_HULL, false);
 }
 
@@ -533,6 +537,8 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   if (const char* e = getenv("SO100_REUSE")) h->reuse_enabled = atoi(e) != 0;
   if (const char* e = getenv("SO100_K3H_BLOCKS")) h->k3h_blocks = std::max(1, atoi(e));
   if (const char* e = getenv("SO100_K3M_BLOCKS")) h->k3m_blocks = std::max(1, atoi(e));
+  if (const char* e = getenv("SO100_K2B_BLOCKS")) h->k2b_blocks = std::max(1, atoi(e));
+  if (const char* e = getenv("SO100_K2B_DIV")) h->k2b_div = std::max(1, atoi(e));
   {
     // env groups: SO100_GROUPS overrides; default one group per 1024 envs, at most 6 (measured on B200 at 16384 envs with the
     // three solve classes: 5 groups 2.53 ms, 6 2.54, 7 2.54, 8 2.56, 10 2.62 per step; 4096 envs want 4)
