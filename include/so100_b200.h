@@ -56,7 +56,7 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
                  uint64_t seed, int64_t env_offset, so100_handle* out);
 int so100_destroy(so100_handle h);
 int so100_num_envs(so100_handle h);
-/* Kernel launches (CUDA-graph kernel nodes) one so100_step enqueues: 54 per env group (so100_b200.cu: EnvGroup). */
+/* Kernel launches (CUDA-graph kernel nodes) one so100_step enqueues: 64 per env group (so100_b200.cu: EnvGroup). */
 int so100_launches_per_step(so100_handle h);
 
 /* Replaces: SO100Env.reset / SO100GoalEnv.reset (env.py:148-170, 302-320) incl.
