@@ -31,10 +31,10 @@ FLOP_PER_ENV_STEP = 1.0e6             # SURVEY.md Appendix C convention F_contac
 FP32_PEAK_NOMINAL_TFLOPS = 74.4       # 148 SM x 128 lanes x 2 x 1.965 GHz
 METRIC = "env-steps/sec (bin-a-cube)"
 # warp-instructions per env-step of the steady-state workload, from the ncu launch list in profiles/r01_phase_launches.txt
-# (per 2048-env launch: solve_light 5.64 M, collide_box 2.95 M averaged over the 10 full and 1 reusing launch, kin_dyn 1.73 M,
-# collide_hull 0.15 M, solve_heavy 0.05 M per launch of either instantiation, task 0.99 M):
-# (10 x 5.64 + 11 x (1.73 + 2.95 + 0.15) + 20 x 0.05 + 0.99) M / 2048
-WARP_INSTR_PER_ENV_STEP = 54.4e3
+# (per 2731-env launch: solve_light 7.51 M, collide_box 3.92 M averaged over the 10 full and 1 reusing launch, kin_dyn 2.30 M,
+# collide_hull 0.17 M, solve_heavy 0.05 M per launch of either instantiation, task 1.31 M):
+# (10 x 7.51 + 11 x (2.30 + 3.92 + 0.17) + 20 x 0.05 + 1.31) M / 2731
+WARP_INSTR_PER_ENV_STEP = 54.1e3
 ISSUE_SLOTS_PER_S = 148 * 4 * 1.965e9        # SMs x schedulers x max SM clock: one warp-instruction per scheduler and cycle
 # Algorithmic bytes one env moves per launch of each phase kernel (4-byte words):
 #   kin_dyn       reads qpos13+qvel12+ctrl6, writes frames102 + Marm/qfs/qas45

@@ -520,3 +520,40 @@ def test_host_step_pinned_pageable_and_device_paths_agree(model_blob):
         assert (float(ref["truncated"].float().mean()) > 0.5) == (k == 1)
     for s in sims:
         s.close()
+
+
+def test_contact_reuse_is_invalidated_by_state_writes(model_blob):
+    """The first substep of a step reuses the contact lists the previous step left in the workspace; anything that changes the
+    state between two steps (set_state, a masked reset) must switch that off for the next step.  A handle that is stepped,
+    rewritten and stepped again equals a fresh handle given the same state, bit for bit."""
+    import torch
+    from gym_so100_c_b200.engine import BatchedSim
+    n = 2048
+    g = torch.Generator(device="cuda").manual_seed(3)
+    acts = torch.rand((6, n, 6), device="cuda", generator=g) * 2 - 1
+    a = BatchedSim(n, device="cuda:0", task=0, seed=5, model_blob=model_blob)
+    b = BatchedSim(n, device="cuda:0", task=0, seed=5, model_blob=model_blob)
+    a.reset(); b.reset()
+    for k in range(3):
+        a.step(acts[k])
+    # (1) set_state: move every cube onto the far side of the table, keep the arm
+    qpos, qvel, ctrl, warm = [t.clone() for t in a.get_state()]
+    qpos[:, 6] = -0.05; qpos[:, 7] = 0.45; qpos[:, 8] = 0.021
+    qvel[:, 6:] = 0
+    a.set_state(qpos, qvel, ctrl, warm)
+    b.set_state(qpos, qvel, ctrl, warm)
+    goal, step, total, episode = a.get_aux()
+    b.set_aux(step_count=step, total_steps=total, episode=episode)
+    ra = a.step(acts[3])[1].clone(); rb = b.step(acts[3])[1].clone()
+    for x, y in zip(a.get_state(), b.get_state()):
+        assert torch.equal(x, y)
+    assert torch.equal(ra, rb) and torch.equal(a.obs, b.obs)
+    # (2) masked reset of every other env between two steps
+    mask = (torch.arange(n, device="cuda") % 2).to(torch.uint8)
+    a.reset(mask=mask); b.reset(mask=mask)
+    ra = a.step(acts[4])[1].clone(); rb = b.step(acts[4])[1].clone()
+    a.step(acts[5]); b.step(acts[5])
+    for x, y in zip(a.get_state(), b.get_state()):
+        assert torch.equal(x, y)
+    assert torch.equal(ra, rb) and torch.equal(a.obs, b.obs)
+    a.close(); b.close()
