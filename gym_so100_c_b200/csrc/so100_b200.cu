@@ -101,6 +101,15 @@ struct so100_ctx {
   // two are about a third of a substep apart for the rest of the step; 2 chains all groups that way.
   int stagger = 0;   // measured on B200: 1 and 2 are 1-9 % slower than 0 at 4096 / 16384 / 65536 envs (the groups drift apart on their own)
   int sm_count = 148;
+  // Grid class of the queue kernels.  Their best grids depend on the workload: under random actions the queues hold a handful
+  // of envs and small grids win (resident-but-idle persistent blocks cost the other groups' kernels), while a policy that holds
+  // thousands of cubes at once fills them and wants twice the tiles.  Every step copies the largest relative queue lengths it saw
+  // (Queues::note) to pinned host memory; so100_step reads the last completed copy, without synchronising, and replays the graph
+  // captured for that class.  Results do not depend on the grids, so a stale reading costs time, never correctness.
+  int* qstat = nullptr;             // device [2]
+  volatile int* qstat_host = nullptr;   // pinned [2]
+  int grid_class = 0;               // 0 small grids, 1 large grids
+  bool adaptive_grids = true;       // SO100_ADAPTIVE_GRIDS=0 pins class 0
   int k2b_blocks = 148 * SO100_K2B_BLOCKS_PER_SM, k2b_div = 16;   // SO100_K2B_BLOCKS / SO100_K2B_DIV (environment) override
   int k3h_blocks = SO100_K3H_BLOCKS, k3m_blocks = SO100_K3M_BLOCKS;   // SO100_K3H_BLOCKS / SO100_K3M_BLOCKS (environment) override
   // so100_step ends with a collision stage on the post-step state (mj_step1), and the next so100_step starts with one on the
@@ -117,7 +126,7 @@ struct so100_ctx {
   Queues queues(const EnvGroup& G) const {
     return Queues{G.ctl, qmem + CTL_WORDS + n + (size_t)G.off * NHP, qmem + CTL_WORDS + G.off,
                   qmem + CTL_WORDS + (size_t)(1 + NHP) * n + G.off, G.order + (size_t)G.parity * n,
-                  G.order + (size_t)(1 - G.parity) * n};
+                  G.order + (size_t)(1 - G.parity) * n, qstat, (1024 * 1024) / std::max(G.n, 1)};
   }
 };
 
@@ -392,7 +401,7 @@ static void launch_position_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, co
   mark(h, st, CLS_KIN, false); mark(h, st, CLS_BOX, true);
   phase_collide_box<LPE_K2A><<<grid_of(n, LPE_K2A), BLOCK, smem_of<BoxS>(LPE_K2A), st>>>(work, n, T, Q, reuse);
   mark(h, st, CLS_BOX, false); mark(h, st, CLS_HULL, true);
-  phase_collide_hull<LPE_K2B><<<std::min(grid_of(n, LPE_K2B), std::max(h->k2b_blocks, n / h->k2b_div)), BLOCK, smem_of<HullS>(LPE_K2B), st>>>(work, T, Q);
+  phase_collide_hull<LPE_K2B><<<std::min(grid_of(n, LPE_K2B), std::max(h->k2b_blocks << h->grid_class, n / std::max(1, h->k2b_div >> h->grid_class))), BLOCK, smem_of<HullS>(LPE_K2B), st>>>(work, T, Q);
   mark(h, st, CLS_HULL, false);
 }
 
@@ -409,13 +418,13 @@ static void launch_solve_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const
   if (h->timing) {
     // timing mode: one stream, so that the event pair brackets both queue kernels
     mark(h, st, CLS_HEAVY, true);
-    phase_solve_heavy<LPE_K3H, NCL><<<std::min(grid_of(n, LPE_K3H), h->k3m_blocks), BLOCK, smem_of<SolS<NCL>>(LPE_K3H), st>>>(state, work, T, Q, O);
+    phase_solve_heavy<LPE_K3H, NCL><<<std::min(grid_of(n, LPE_K3H), h->k3m_blocks << h->grid_class), BLOCK, smem_of<SolS<NCL>>(LPE_K3H), st>>>(state, work, T, Q, O);
     phase_solve_heavy<LPE_K3H, NC><<<std::min(grid_of(n, LPE_K3H), h->k3h_blocks), BLOCK, smem_of<SolS<NC>>(LPE_K3H), st>>>(state, work, T, Q, O);
     mark(h, st, CLS_HEAVY, false);
   } else {
     cudaStreamWaitEvent(G.side, G.fork, 0);
     cudaStreamWaitEvent(G.side2, G.fork, 0);
-    phase_solve_heavy<LPE_K3H, NCL><<<std::min(grid_of(n, LPE_K3H), h->k3m_blocks), BLOCK, smem_of<SolS<NCL>>(LPE_K3H), G.side>>>(state, work, T, Q, O);
+    phase_solve_heavy<LPE_K3H, NCL><<<std::min(grid_of(n, LPE_K3H), h->k3m_blocks << h->grid_class), BLOCK, smem_of<SolS<NCL>>(LPE_K3H), G.side>>>(state, work, T, Q, O);
     phase_solve_heavy<LPE_K3H, NC><<<std::min(grid_of(n, LPE_K3H), h->k3h_blocks), BLOCK, smem_of<SolS<NC>>(LPE_K3H), G.side2>>>(state, work, T, Q, O);
     cudaEventRecord(G.join, G.side);
     cudaEventRecord(G.join2, G.side2);
@@ -527,6 +536,15 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   CUDA_OK(cudaMalloc(&h->qmem, (so100_ctx::CTL_WORDS + (2 + NHP) * (size_t)num_envs) * sizeof(int)));
   CUDA_OK(cudaMemset(h->qmem, 0, (so100_ctx::CTL_WORDS + (2 + NHP) * (size_t)num_envs) * sizeof(int)));
   CUDA_OK(cudaMalloc(&h->order, 4 * (size_t)num_envs * sizeof(int)));
+  CUDA_OK(cudaMalloc(&h->qstat, 2 * sizeof(int)));
+  CUDA_OK(cudaMemset(h->qstat, 0, 2 * sizeof(int)));
+  {
+    int* p = nullptr;
+    CUDA_OK(cudaHostAlloc(&p, 2 * sizeof(int), cudaHostAllocDefault));
+    p[0] = p[1] = 0;
+    h->qstat_host = p;
+  }
+  if (const char* e = getenv("SO100_ADAPTIVE_GRIDS")) h->adaptive_grids = atoi(e) != 0;
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&h->t_start));
   if (const char* e = getenv("SO100_GROUP_TIMES")) h->group_times = atoi(e) != 0;
@@ -587,6 +605,8 @@ int so100_destroy(so100_handle h) {
     if (g_live_handles > 0) g_live_handles--;
   }
   cudaSetDevice(h->device);
+  cudaFree(h->qstat);
+  if (h->qstat_host) cudaFreeHost((void*)h->qstat_host);
   cudaFree(h->state); cudaFree(h->geom); cudaFree(h->pair); cudaFree(h->vert); cudaFree(h->bpair); cudaFree(h->diag); cudaFree(h->work); cudaFree(h->qmem); cudaFree(h->order);
   free_group(h->whole);
   for (EnvGroup& G : h->groups) free_group(G);
@@ -662,6 +682,9 @@ static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream, i
       out(ho->reward, B.reward, 4); out(ho->terminated, B.terminated, 1); out(ho->truncated, B.truncated, 1); out(ho->success, B.success, 1);
     }
   });
+  // queue statistics of this step for the next steps' grid class (all groups have joined `stream` here)
+  cudaMemcpyAsync((void*)h->qstat_host, h->qstat, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream);
+  cudaMemsetAsync(h->qstat, 0, 2 * sizeof(int), stream);
 }
 
 static int step_impl(so100_handle h, const float* action, int autoreset, float* obs, float* achieved, float* desired, float* reward,
@@ -674,6 +697,8 @@ static int step_impl(so100_handle h, const float* action, int autoreset, float* 
   cudaStream_t st = (cudaStream_t)stream;
   const int reuse = (h->reuse_enabled && h->work_fresh && h->nsub > 0) ? 1 : 0;
   h->work_fresh = true;
+  // more than 1/16 of a group in the medium queue, or more than 1/2 hull pair per env: large grids
+  h->grid_class = (h->adaptive_grids && (h->qstat_host[0] > 64 || h->qstat_host[1] > 512)) ? 1 : 0;
   if (!h->use_graph || h->timing) {
     enqueue_step(h, A, st, reuse, ho);
     CUDA_OK(cudaGetLastError());
@@ -682,7 +707,7 @@ static int step_impl(so100_handle h, const float* action, int autoreset, float* 
   CUDA_OK(cudaMemcpyAsync(h->act_stage, action, (size_t)h->n * 6 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   A.action = h->act_stage;
   const void* key[18] = {obs, achieved, desired, reward, terminated, truncated, success, final_obs,
-                         reinterpret_cast<const void*>((size_t)(autoreset != 0)), reinterpret_cast<const void*>((size_t)reuse)};
+                         reinterpret_cast<const void*>((size_t)(autoreset != 0)), reinterpret_cast<const void*>((size_t)(reuse | (h->grid_class << 1)))};
   if (ho) {
     const void* hk[8] = {ho->obs, ho->achieved, ho->desired, ho->reward, ho->final_obs, ho->terminated, ho->truncated, ho->success};
     memcpy(key + 10, hk, sizeof(hk));

@@ -96,6 +96,7 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_box
 template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_hull(float* work, DevTables T, Queues Q) {
   SO100_TILE_PROLOGUE(LPE, 128, HullS);
   const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_HULL_COUNT]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) Q.note(1, count);
   for (;;) {
     int i = 0;
     if (lane == 0) i = atomicAdd(&Q.ctl[Q_HULL_NEXT], 1);
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(128, NCAP == NCL ? SO100_K3M_MINB : SO100_K3H_
   constexpr bool MED = NCAP == NCL;
   const int* queue = MED ? Q.medium : Q.heavy;
   const int count = *reinterpret_cast<volatile int*>(&Q.ctl[MED ? Q_MED_COUNT : Q_HEAVY_COUNT]);
+  if (MED && blockIdx.x == 0 && threadIdx.x == 0) Q.note(0, count);
   for (;;) {
     int i = 0;
     if (lane == 0) i = atomicAdd(&Q.ctl[MED ? Q_MED_NEXT : Q_HEAVY_NEXT], 1);

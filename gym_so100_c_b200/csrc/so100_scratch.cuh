@@ -60,6 +60,10 @@ struct Queues {
   // next substep starts its likely stragglers first (the iteration count of an env is strongly correlated in time).
   const int* order_in;
   int* order_out;
+  int* stat;     // [2] largest medium-queue / hull-pair-queue length (relative: count * 1024 / group size) seen since the host last
+                 // cleared it; the host sizes the queue kernels' grids for the next step from it (so100_b200.cu: grid class)
+  int scale;     // 1024 * 1024 / group size
+  __device__ __forceinline__ void note(int which, int count) const { atomicMax(&stat[which], (count * scale) >> 10); }
   // work class of an env whose collision stage is complete: > NCL contacts (or list overflow) -> heavy queue; an arm-cube
   // contact among <= NCL -> medium queue; everything else is solved by the regular grid of the light kernel
   __device__ __forceinline__ void route(int env, int ncon, bool coupled) const {
