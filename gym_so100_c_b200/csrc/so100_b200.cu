@@ -697,8 +697,12 @@ static int step_impl(so100_handle h, const float* action, int autoreset, float* 
   cudaStream_t st = (cudaStream_t)stream;
   const int reuse = (h->reuse_enabled && h->work_fresh && h->nsub > 0) ? 1 : 0;
   h->work_fresh = true;
-  // more than 1/16 of a group in the medium queue, or more than 1/2 hull pair per env: large grids
-  h->grid_class = (h->adaptive_grids && (h->qstat_host[0] > 64 || h->qstat_host[1] > 512)) ? 1 : 0;
+  // more than 1/16 of a group in the medium queue, or more than 1/2 hull pair per env: large grids (with hysteresis)
+  if (h->adaptive_grids) {
+    const int med = h->qstat_host[0], hull = h->qstat_host[1];
+    if (h->grid_class == 0 && (med > 64 || hull > 512)) h->grid_class = 1;
+    else if (h->grid_class == 1 && med < 32 && hull < 384) h->grid_class = 0;
+  }
   if (!h->use_graph || h->timing) {
     enqueue_step(h, A, st, reuse, ho);
     CUDA_OK(cudaGetLastError());
@@ -707,28 +711,44 @@ static int step_impl(so100_handle h, const float* action, int autoreset, float* 
   CUDA_OK(cudaMemcpyAsync(h->act_stage, action, (size_t)h->n * 6 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   A.action = h->act_stage;
   const void* key[18] = {obs, achieved, desired, reward, terminated, truncated, success, final_obs,
-                         reinterpret_cast<const void*>((size_t)(autoreset != 0)), reinterpret_cast<const void*>((size_t)(reuse | (h->grid_class << 1)))};
+                         reinterpret_cast<const void*>((size_t)(autoreset != 0)), nullptr};
   if (ho) {
     const void* hk[8] = {ho->obs, ho->achieved, ho->desired, ho->reward, ho->final_obs, ho->terminated, ho->truncated, ho->success};
     memcpy(key + 10, hk, sizeof(hk));
   }
-  cudaGraphExec_t exec = nullptr;
-  for (auto& g : h->graphs)
-    if (memcmp(g.key, key, sizeof(key)) == 0) exec = g.exec;
+  auto find = [&](int cls) -> cudaGraphExec_t {
+    key[9] = reinterpret_cast<const void*>((size_t)(reuse | (cls << 1)));
+    for (auto& g : h->graphs)
+      if (memcmp(g.key, key, sizeof(key)) == 0) return g.exec;
+    return nullptr;
+  };
+  const int chosen = h->grid_class;
+  cudaGraphExec_t exec = find(chosen);
   if (!exec) {
-    cudaGraph_t graph = nullptr;
-    CUDA_OK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal));
-    h->capturing = true;
-    enqueue_step(h, A, h->cap, reuse, ho);
-    h->capturing = false;
-    CUDA_OK(cudaStreamEndCapture(h->cap, &graph));
-    CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
-    cudaGraphDestroy(graph);
-    if (h->graphs.size() >= 8) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
-    so100_ctx::StepGraph g;
-    memcpy(g.key, key, sizeof(key));
-    g.exec = exec;
-    h->graphs.push_back(g);
+    // first use of this set of pointers: capture the graphs of both grid classes now, so that a later class change is a
+    // cache hit and not a capture in the middle of a rollout
+    for (int cls = 0; cls < (h->adaptive_grids ? 2 : 1); cls++) {
+      if (find(cls)) continue;
+      h->grid_class = cls;
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t ge = nullptr;
+      CUDA_OK(cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal));
+      h->capturing = true;
+      enqueue_step(h, A, h->cap, reuse, ho);
+      h->capturing = false;
+      CUDA_OK(cudaStreamEndCapture(h->cap, &graph));
+      CUDA_OK(cudaGraphInstantiate(&ge, graph, 0));
+      cudaGraphDestroy(graph);
+      if (h->graphs.size() >= 16) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+      so100_ctx::StepGraph g;
+      find(cls);                       // leaves this class's key in `key`
+      memcpy(g.key, key, sizeof(key));
+      g.exec = ge;
+      h->graphs.push_back(g);
+    }
+    h->grid_class = chosen;
+    exec = find(chosen);
+    if (!exec) return fail(SO100_ERR_CUDA, "so100_step: graph capture failed");
   }
   CUDA_OK(cudaGraphLaunch(exec, st));
   return SO100_OK;
