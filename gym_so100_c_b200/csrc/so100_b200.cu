@@ -1,6 +1,7 @@
 // Host side of libso100_b200.so: model narrowing/validation, device allocation, kernel
 // launches behind the C ABI of include/so100_b200.h.  No CPU fallback exists: every entry
 // point either launches the sm_100a kernels or fails with an error code.
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -47,9 +48,23 @@ enum { CLS_KIN = 0, CLS_BOX = 1, CLS_SOLVE = 2, CLS_TASK = 3, CLS_HULL = 4, CLS_
 
 static thread_local std::string g_err;
 static std::mutex g_model_mutex;
-static int g_live_handles = 0;
-static so100::DevModel g_live_model;
+// The uniform model constants live in __constant__ memory, and kernel attributes (opt-in shared memory) are per device:
+// both are tracked per device index, so that one process may drive several GPUs (one handle each, or more with one model).
+constexpr int MAX_DEVICES = 64;
+static int g_live_handles[MAX_DEVICES] = {0};
+static so100::DevModel g_live_model[MAX_DEVICES];
+static bool g_configured[MAX_DEVICES] = {false};
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+// Every entry point runs on its handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
 #define CUDA_OK(expr)                                                                              \
   do {                                                                                             \
     cudaError_t e_ = (expr);                                                                       \
@@ -73,6 +88,7 @@ struct EnvGroup {
 
 struct so100_ctx {
   int n = 0, device = 0, task = 0, nsub = 10;
+  bool registered = false;    // counted in g_live_handles[device]
   uint64_t seed = 0;
   int64_t env_offset = 0;
   float* state = nullptr;
@@ -87,8 +103,22 @@ struct so100_ctx {
   // so100_step replays a CUDA graph of its whole launch sequence (all groups, forks and joins): the host cost of a step
   // drops from several hundred launch / event calls to one cudaGraphLaunch.  Actions are staged into a fixed buffer so
   // that the graph's kernel arguments never change; one graph is cached per distinct set of output pointers.
-  struct StepGraph { const void* key[18]; cudaGraphExec_t exec; };
+  // The cache is bounded (GRAPH_SETS pointer sets, least recently used evicted).  A caller that keeps rotating its output
+  // buffers beyond that bound is switched to library-owned staging outputs: one more graph, keyed on those stable buffers and
+  // never re-captured, followed by device-to-device copies into whatever pointers the call names.
+  static constexpr int NKEY = 20, GRAPH_SETS = 8;
+  struct StepGraph { const void* key[NKEY]; cudaGraphExec_t exec; uint64_t used; };
   std::vector<StepGraph> graphs;
+  uint64_t graph_clock = 0;
+  int graph_captures = 0;     // captures since create (so100_graph_stats)
+  bool stage_outputs = false; // rotating caller pointers: run the graph on the staging outputs below
+  float *s_obs = nullptr, *s_ag = nullptr, *s_dg = nullptr, *s_rew = nullptr, *s_fin = nullptr;
+  uint8_t *s_term = nullptr, *s_trunc = nullptr, *s_succ = nullptr;
+  // optional per-env episode outputs (so100_set_episode_outputs): return / length of the episode an env has just finished
+  float* ep_return = nullptr;
+  int32_t* ep_length = nullptr;
+  std::vector<std::array<const void*, 8>> host_sets;   // page-locked destination sets of so100_step_host seen so far
+  double* ep_stats = nullptr;  // device [4] scratch of so100_episode_stats
   cudaStream_t cap = nullptr;
   float* act_stage = nullptr;
   bool use_graph = true;
@@ -367,8 +397,8 @@ static int build_dev_model(const so100_model& m, DevModel& dm, std::vector<DevGe
 template <class ST> static size_t smem_of(unsigned lpe, int tpb = BLOCK) { return (size_t)(tpb / lpe) * sizeof(ST); }
 static int grid_of(int n, unsigned lpe, int tpb = BLOCK) { const int epb = tpb / (int)lpe; return (n + epb - 1) / epb; }
 
-static int configure_kernels() {
-  static bool done = false;
+static int configure_kernels(int device) {
+  bool& done = g_configured[device];     // cudaFuncSetAttribute applies to the current device only
   if (done) return SO100_OK;
   CUDA_OK(cudaFuncSetAttribute(phase_kin_dyn<LPE_K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<KinS>(LPE_K1)));
   CUDA_OK(cudaFuncSetAttribute(phase_collide_box<LPE_K2A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<BoxS>(LPE_K2A)));
@@ -487,44 +517,11 @@ template <class F> static void for_each_group(so100_ctx* h, cudaStream_t st, boo
   }
 }
 
-extern "C" {
-
-const char* so100_last_error(void) { return g_err.c_str(); }
-
-int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device, int task, uint64_t seed,
-                 int64_t env_offset, so100_handle* out) {
-  if (!model_blob || !out || num_envs <= 0) return fail(SO100_ERR_ARG, "so100_create: bad argument");
-  if (nbytes != sizeof(so100_model)) return fail(SO100_ERR_ARG, "so100_create: model blob has the wrong size");
-  if (task < SO100_TASK_CUBE_TO_BIN || task > SO100_TASK_TOUCH_CUBE_SPARSE) return fail(SO100_ERR_ARG, "so100_create: unknown task");
-  so100_model m;
-  memcpy(&m, model_blob, sizeof(m));
-  if (m.magic != SO100_MODEL_MAGIC || m.version != SO100_MODEL_VERSION) return fail(SO100_ERR_ARG, "so100_create: model magic/version mismatch");
-  int ndev = 0;
-  cudaError_t ce = cudaGetDeviceCount(&ndev);
-  if (ce != cudaSuccess || ndev <= 0)
-    return fail(SO100_ERR_CUDA, "so100_create: no CUDA device available (this library has no CPU path)");
-  if (device < 0 || device >= ndev) return fail(SO100_ERR_ARG, "so100_create: bad device index");
-  CUDA_OK(cudaSetDevice(device));
-  DevModel dm;
-  std::vector<DevGeom> geoms;
-  std::vector<DevPair> pairs;
-  std::vector<float4> verts;
-  int rc = build_dev_model(m, dm, geoms, pairs, verts);
-  if (rc) return rc;
-  rc = configure_kernels();
-  if (rc) return rc;
-  // the uniform model constants live in __constant__ memory shared by every handle of this process on a device:
-  // live handles must agree on the model
-  {
-    std::lock_guard<std::mutex> lock(g_model_mutex);
-    if (g_live_handles > 0 && memcmp(&g_live_model, &dm, sizeof(dm)) != 0)
-      return fail(SO100_ERR_MODEL, "so100_create: a live handle of this process uses a different model (one model per process)");
-    g_live_model = dm;
-    g_live_handles++;
-  }
-  so100_ctx* h = new so100_ctx();
-  h->n = num_envs; h->device = device; h->task = task; h->seed = seed; h->env_offset = env_offset;
-  h->nsub = m.nsubstep;
+// device allocations, streams, events and tables of a new handle (any failure leaves a partially built context behind)
+static int create_device_side(so100_ctx* h, const DevModel& dm, const std::vector<DevGeom>& geoms, const std::vector<DevPair>& pairs,
+                              const std::vector<float4>& verts) {
+  const int num_envs = h->n, device = h->device;
+  int rc = SO100_OK;
   CUDA_OK(cudaMemcpyToSymbol(c_m, &dm, sizeof(dm)));
   CUDA_OK(cudaMalloc(&h->state, (size_t)num_envs * STATE_WORDS * sizeof(float)));
   CUDA_OK(cudaMalloc(&h->geom, geoms.size() * sizeof(DevGeom)));
@@ -594,24 +591,81 @@ int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device
   init_state_kernel<<<(total + 255) / 256, 256>>>(h->state, num_envs);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaDeviceSynchronize());
+  return SO100_OK;
+}
+
+extern "C" {
+
+const char* so100_last_error(void) { return g_err.c_str(); }
+
+int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device, int task, uint64_t seed,
+                 int64_t env_offset, so100_handle* out) {
+  if (!model_blob || !out || num_envs <= 0) return fail(SO100_ERR_ARG, "so100_create: bad argument");
+  if (nbytes != sizeof(so100_model)) return fail(SO100_ERR_ARG, "so100_create: model blob has the wrong size");
+  if (task < SO100_TASK_CUBE_TO_BIN || task > SO100_TASK_TOUCH_CUBE_SPARSE) return fail(SO100_ERR_ARG, "so100_create: unknown task");
+  so100_model m;
+  memcpy(&m, model_blob, sizeof(m));
+  if (m.magic != SO100_MODEL_MAGIC || m.version != SO100_MODEL_VERSION) return fail(SO100_ERR_ARG, "so100_create: model magic/version mismatch");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0)
+    return fail(SO100_ERR_CUDA, "so100_create: no CUDA device available (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(SO100_ERR_ARG, "so100_create: bad device index");
+  if (device >= MAX_DEVICES) return fail(SO100_ERR_ARG, "so100_create: device index beyond the library's table");
+  DeviceGuard guard(device);
+  DevModel dm;
+  std::vector<DevGeom> geoms;
+  std::vector<DevPair> pairs;
+  std::vector<float4> verts;
+  int rc = build_dev_model(m, dm, geoms, pairs, verts);
+  if (rc) return rc;
+  rc = configure_kernels(device);
+  if (rc) return rc;
+  // the uniform model constants live in __constant__ memory shared by every handle of this process on a device:
+  // live handles on one device must agree on the model
+  so100_ctx* h = new so100_ctx();
+  h->n = num_envs; h->device = device; h->task = task; h->seed = seed; h->env_offset = env_offset;
+  h->nsub = m.nsubstep;
+  {
+    std::lock_guard<std::mutex> lock(g_model_mutex);
+    if (g_live_handles[device] > 0 && memcmp(&g_live_model[device], &dm, sizeof(dm)) != 0) {
+      delete h;
+      return fail(SO100_ERR_MODEL, "so100_create: a live handle of this process uses a different model on this device (one model per process and device)");
+    }
+    g_live_model[device] = dm;
+    g_live_handles[device]++;
+    h->registered = true;
+  }
+  // everything below may fail half-way: so100_destroy releases whatever exists by then (and the live-handle count)
+  rc = create_device_side(h, dm, geoms, pairs, verts);
+  if (rc) {
+    const std::string msg = g_err;
+    so100_destroy(h);
+    g_err = msg;
+    return rc;
+  }
   *out = h;
   return SO100_OK;
 }
 
 int so100_destroy(so100_handle h) {
   if (!h) return SO100_OK;
-  {
+  if (h->registered) {
     std::lock_guard<std::mutex> lock(g_model_mutex);
-    if (g_live_handles > 0) g_live_handles--;
+    if (g_live_handles[h->device] > 0) g_live_handles[h->device]--;
   }
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaFree(h->qstat);
   if (h->qstat_host) cudaFreeHost((void*)h->qstat_host);
   cudaFree(h->state); cudaFree(h->geom); cudaFree(h->pair); cudaFree(h->vert); cudaFree(h->bpair); cudaFree(h->diag); cudaFree(h->work); cudaFree(h->qmem); cudaFree(h->order);
   free_group(h->whole);
   for (EnvGroup& G : h->groups) free_group(G);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->t_start) cudaEventDestroy(h->t_start);
+  for (auto& e : h->events) cudaEventDestroy(e.first);
   for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+  cudaFree(h->s_obs); cudaFree(h->s_ag); cudaFree(h->s_dg); cudaFree(h->s_rew); cudaFree(h->s_fin);
+  cudaFree(h->s_term); cudaFree(h->s_trunc); cudaFree(h->s_succ); cudaFree(h->ep_stats);
   if (h->cap) cudaStreamDestroy(h->cap);
   cudaFree(h->act_stage);
   cudaFree(h->h_action); cudaFree(h->h_obs); cudaFree(h->h_ag); cudaFree(h->h_dg); cudaFree(h->h_rew); cudaFree(h->h_fin);
@@ -631,6 +685,7 @@ int so100_launches_per_step(so100_handle h) {
 int so100_reset(so100_handle h, const uint8_t* mask, const float* box_pose, float* obs, float* achieved, float* desired,
                 void* stream) {
   if (!h) return fail(SO100_ERR_ARG, "so100_reset: null handle");
+  DeviceGuard guard(h->device);
   h->work_fresh = false;
   cudaStream_t st = (cudaStream_t)stream;
   reset_kernel<LPE_K4><<<grid_of(h->n, LPE_K4), BLOCK, smem_of<TaskS>(LPE_K4), st>>>(h->state, mask, box_pose, obs, achieved, desired, h->n,
@@ -671,6 +726,8 @@ static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream, i
     if (B.terminated) B.terminated += o;
     if (B.truncated) B.truncated += o;
     if (B.success) B.success += o;
+    if (B.ep_return) B.ep_return += o;
+    if (B.ep_length) B.ep_length += o;
     mark(h, st, CLS_TASK, true);
     phase_task<LPE_K4><<<grid_of(G.n, LPE_K4), BLOCK, smem_of<TaskS>(LPE_K4), st>>>(B, h->work + o * WORK_WORDS, h->tables());
     mark(h, st, CLS_TASK, false);
@@ -693,6 +750,7 @@ static int step_impl(so100_handle h, const float* action, int autoreset, float* 
   A.state = h->state; A.action = action; A.obs = obs; A.achieved = achieved; A.desired = desired; A.reward = reward;
   A.final_obs = final_obs; A.terminated = terminated; A.truncated = truncated; A.success = success;
   A.n = h->n; A.autoreset = autoreset; A.task = h->task;
+  A.ep_return = h->ep_return; A.ep_length = h->ep_length;
   A.seed_lo = (uint32_t)h->seed; A.seed_hi = (uint32_t)(h->seed >> 32); A.env_offset = h->env_offset;
   cudaStream_t st = (cudaStream_t)stream;
   const int reuse = (h->reuse_enabled && h->work_fresh && h->nsub > 0) ? 1 : 0;
@@ -710,21 +768,89 @@ static int step_impl(so100_handle h, const float* action, int autoreset, float* 
   }
   CUDA_OK(cudaMemcpyAsync(h->act_stage, action, (size_t)h->n * 6 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   A.action = h->act_stage;
-  const void* key[18] = {obs, achieved, desired, reward, terminated, truncated, success, final_obs,
-                         reinterpret_cast<const void*>((size_t)(autoreset != 0)), nullptr};
-  if (ho) {
-    const void* hk[8] = {ho->obs, ho->achieved, ho->desired, ho->reward, ho->final_obs, ho->terminated, ho->truncated, ho->success};
-    memcpy(key + 10, hk, sizeof(hk));
+  constexpr int NKEY = so100_ctx::NKEY;
+  const void* key[NKEY];
+  auto make_key = [&]() {
+    const void* k[NKEY] = {A.obs, A.achieved, A.desired, A.reward, A.terminated, A.truncated, A.success, A.final_obs,
+                           reinterpret_cast<const void*>((size_t)(autoreset != 0)), nullptr};
+    if (ho) {
+      const void* hk[8] = {ho->obs, ho->achieved, ho->desired, ho->reward, ho->final_obs, ho->terminated, ho->truncated, ho->success};
+      memcpy(k + 10, hk, sizeof(hk));
+    }
+    k[18] = A.ep_return; k[19] = A.ep_length;
+    memcpy(key, k, sizeof(k));
+  };
+  // same pointer set, any variant (key[9] = reuse | grid class << 1)
+  auto same_set = [&](const so100_ctx::StepGraph& g) {
+    return memcmp(g.key, key, 9 * sizeof(void*)) == 0 && memcmp(g.key + 10, key + 10, (NKEY - 10) * sizeof(void*)) == 0;
+  };
+  auto count_sets = [&]() {
+    int nset = 0;
+    for (size_t i = 0; i < h->graphs.size(); i++) {
+      bool first = true;
+      for (size_t j = 0; j < i; j++)
+        if (memcmp(h->graphs[j].key, h->graphs[i].key, 9 * sizeof(void*)) == 0 &&
+            memcmp(h->graphs[j].key + 10, h->graphs[i].key + 10, (NKEY - 10) * sizeof(void*)) == 0) { first = false; break; }
+      nset += first;
+    }
+    return nset;
+  };
+  // caller's pointers, kept for the copies out of the staging outputs
+  float *c_obs = obs, *c_ag = achieved, *c_dg = desired, *c_rew = reward, *c_fin = final_obs;
+  uint8_t *c_term = terminated, *c_trunc = truncated, *c_succ = success;
+  auto redirect = [&]() -> int {
+    const size_t n = (size_t)h->n;
+    if (!h->s_obs) {
+      CUDA_OK(cudaMalloc(&h->s_obs, n * 15 * sizeof(float)));
+      CUDA_OK(cudaMalloc(&h->s_fin, n * 15 * sizeof(float)));
+      CUDA_OK(cudaMalloc(&h->s_ag, n * 3 * sizeof(float)));
+      CUDA_OK(cudaMalloc(&h->s_dg, n * 3 * sizeof(float)));
+      CUDA_OK(cudaMalloc(&h->s_rew, n * sizeof(float)));
+      CUDA_OK(cudaMalloc(&h->s_term, n));
+      CUDA_OK(cudaMalloc(&h->s_trunc, n));
+      CUDA_OK(cudaMalloc(&h->s_succ, n));
+    }
+    A.obs = c_obs ? h->s_obs : nullptr; A.achieved = c_ag ? h->s_ag : nullptr; A.desired = c_dg ? h->s_dg : nullptr; A.reward = c_rew ? h->s_rew : nullptr;
+    A.final_obs = c_fin ? h->s_fin : nullptr; A.terminated = c_term ? h->s_term : nullptr; A.truncated = c_trunc ? h->s_trunc : nullptr;
+    A.success = c_succ ? h->s_succ : nullptr;
+    return SO100_OK;
+  };
+  bool staged = h->stage_outputs && !ho;
+  if (staged) { const int rc = redirect(); if (rc) return rc; }
+  make_key();
+  bool known = false;
+  for (auto& g : h->graphs) known = known || same_set(g);
+  if (!known && !staged && (int)count_sets() >= so100_ctx::GRAPH_SETS) {
+    if (!ho) {
+      // one pointer set too many: this caller rotates its output buffers.  From now on the graph runs on stable staging
+      // outputs (captured once) and the results are copied to wherever the call points.
+      h->stage_outputs = staged = true;
+      const int rc = redirect();
+      if (rc) return rc;
+      make_key();
+    } else {
+      // page-locked host destinations are part of the graph: evict the least recently used pointer set
+      size_t lru = 0;
+      for (size_t i = 1; i < h->graphs.size(); i++) if (h->graphs[i].used < h->graphs[lru].used) lru = i;
+      const so100_ctx::StepGraph victim = h->graphs[lru];
+      for (size_t i = h->graphs.size(); i-- > 0;) {
+        so100_ctx::StepGraph& g = h->graphs[i];
+        if (memcmp(g.key, victim.key, 9 * sizeof(void*)) == 0 && memcmp(g.key + 10, victim.key + 10, (NKEY - 10) * sizeof(void*)) == 0) {
+          cudaGraphExecDestroy(g.exec);
+          h->graphs.erase(h->graphs.begin() + i);
+        }
+      }
+    }
   }
-  auto find = [&](int cls) -> cudaGraphExec_t {
+  auto find = [&](int cls) -> so100_ctx::StepGraph* {
     key[9] = reinterpret_cast<const void*>((size_t)(reuse | (cls << 1)));
     for (auto& g : h->graphs)
-      if (memcmp(g.key, key, sizeof(key)) == 0) return g.exec;
+      if (memcmp(g.key, key, sizeof(key)) == 0) return &g;
     return nullptr;
   };
   const int chosen = h->grid_class;
-  cudaGraphExec_t exec = find(chosen);
-  if (!exec) {
+  so100_ctx::StepGraph* hit = find(chosen);
+  if (!hit) {
     // first use of this set of pointers: capture the graphs of both grid classes now, so that a later class change is a
     // cache hit and not a capture in the middle of a rollout
     for (int cls = 0; cls < (h->adaptive_grids ? 2 : 1); cls++) {
@@ -736,33 +862,52 @@ static int step_impl(so100_handle h, const float* action, int autoreset, float* 
       h->capturing = true;
       enqueue_step(h, A, h->cap, reuse, ho);
       h->capturing = false;
-      CUDA_OK(cudaStreamEndCapture(h->cap, &graph));
-      CUDA_OK(cudaGraphInstantiate(&ge, graph, 0));
-      cudaGraphDestroy(graph);
-      if (h->graphs.size() >= 16) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+      const cudaError_t launch_err = cudaGetLastError();
+      cudaError_t ce = cudaStreamEndCapture(h->cap, &graph);     // always closes the capture, also after a failed launch
+      if (ce == cudaSuccess && launch_err != cudaSuccess) ce = launch_err;
+      if (ce == cudaSuccess) ce = cudaGraphInstantiate(&ge, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) {
+        h->grid_class = chosen;
+        return fail(SO100_ERR_CUDA, std::string("so100_step: graph capture failed: ") + cudaGetErrorString(ce));
+      }
       so100_ctx::StepGraph g;
       find(cls);                       // leaves this class's key in `key`
       memcpy(g.key, key, sizeof(key));
       g.exec = ge;
+      g.used = 0;
       h->graphs.push_back(g);
+      h->graph_captures++;
     }
     h->grid_class = chosen;
-    exec = find(chosen);
-    if (!exec) return fail(SO100_ERR_CUDA, "so100_step: graph capture failed");
+    hit = find(chosen);
+    if (!hit) return fail(SO100_ERR_CUDA, "so100_step: graph capture failed");
   }
-  CUDA_OK(cudaGraphLaunch(exec, st));
+  hit->used = ++h->graph_clock;
+  CUDA_OK(cudaGraphLaunch(hit->exec, st));
+  if (staged) {
+    const size_t n = (size_t)h->n;
+    auto out = [&](void* dst, const void* src, size_t bytes) {
+      return (dst && dst != src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st) : cudaSuccess;
+    };
+    CUDA_OK(out(c_obs, h->s_obs, n * 60)); CUDA_OK(out(c_fin, h->s_fin, n * 60)); CUDA_OK(out(c_ag, h->s_ag, n * 12));
+    CUDA_OK(out(c_dg, h->s_dg, n * 12)); CUDA_OK(out(c_rew, h->s_rew, n * 4)); CUDA_OK(out(c_term, h->s_term, n));
+    CUDA_OK(out(c_trunc, h->s_trunc, n)); CUDA_OK(out(c_succ, h->s_succ, n));
+  }
   return SO100_OK;
 }
 
 int so100_step(so100_handle h, const float* action, int autoreset, float* obs, float* achieved, float* desired, float* reward,
                uint8_t* terminated, uint8_t* truncated, uint8_t* success, float* final_obs, void* stream) {
   if (!h || !action) return fail(SO100_ERR_ARG, "so100_step: null handle or action");
+  DeviceGuard guard(h->device);
   return step_impl(h, action, autoreset, obs, achieved, desired, reward, terminated, truncated, success, final_obs, stream, nullptr);
 }
 
 int so100_step_host(so100_handle h, const float* action, int autoreset, float* obs, float* achieved, float* desired,
                     float* reward, uint8_t* terminated, uint8_t* truncated, uint8_t* success, float* final_obs, void* stream) {
   if (!h || !action) return fail(SO100_ERR_ARG, "so100_step_host: null handle or action");
+  DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = h->n;
   if (!h->h_action) {
@@ -785,8 +930,19 @@ int so100_step_host(so100_handle h, const float* action, int autoreset, float* o
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeHost;
   };
-  const bool in_pipeline = pinned(obs) && pinned(achieved) && pinned(desired) && pinned(reward) && pinned(terminated) &&
-                           pinned(truncated) && pinned(success) && pinned(final_obs);
+  bool in_pipeline = pinned(obs) && pinned(achieved) && pinned(desired) && pinned(reward) && pinned(terminated) &&
+                     pinned(truncated) && pinned(success) && pinned(final_obs);
+  if (in_pipeline) {
+    // page-locked destinations are baked into the step graph: only the first few distinct sets ride in the pipeline, a
+    // caller that rotates more of them is served by copies after the step (stable device staging buffers, no re-capture)
+    const std::array<const void*, 8> set = {obs, achieved, desired, reward, terminated, truncated, success, final_obs};
+    bool seen = false;
+    for (const auto& k : h->host_sets) seen = seen || k == set;
+    if (!seen) {
+      if ((int)h->host_sets.size() < so100_ctx::GRAPH_SETS / 2) h->host_sets.push_back(set);
+      else in_pipeline = false;
+    }
+  }
   HostOut ho;
   ho.obs = obs; ho.achieved = achieved; ho.desired = desired; ho.reward = reward; ho.final_obs = final_obs;
   ho.terminated = terminated; ho.truncated = truncated; ho.success = success;
@@ -819,6 +975,7 @@ int so100_compute_reward(const float* achieved, const float* desired, int64_t n,
 static int state_io(so100_handle h, int dir, float* qpos, float* qvel, float* ctrl, float* warm, float* goal, int32_t* sc,
                     int32_t* ts, uint32_t* ep, void* stream) {
   if (!h) return fail(SO100_ERR_ARG, "state io: null handle");
+  DeviceGuard guard(h->device);
   if (dir == 1) h->work_fresh = false;
   const int total = h->n * STATE_WORDS;
   state_io_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, h->n, dir, qpos, qvel, ctrl, warm, goal, sc, ts, ep);
@@ -842,6 +999,7 @@ int so100_set_aux(so100_handle h, const float* goal, const int32_t* step_count, 
 
 int so100_substeps(so100_handle h, int nsub, void* stream) {
   if (!h || nsub < 0) return fail(SO100_ERR_ARG, "so100_substeps: bad argument");
+  DeviceGuard guard(h->device);
   h->work_fresh = false;
   for_each_group(h, (cudaStream_t)stream, true, [&](EnvGroup& G, cudaStream_t st) {
     const SolveOut O{nullptr, nullptr, 0};
@@ -857,6 +1015,7 @@ int so100_substeps(so100_handle h, int nsub, void* stream) {
 
 int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom, float* con_data, float* sites, void* stream) {
   if (!h) return fail(SO100_ERR_ARG, "so100_forward: null handle");
+  DeviceGuard guard(h->device);
   h->work_fresh = false;
   cudaStream_t st = (cudaStream_t)stream;
   launch_position_stage(h, h->whole, st, nullptr, 1);
@@ -885,7 +1044,7 @@ int so100_measure_fp32_peak(int device, float* tflops) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
     return fail(SO100_ERR_CUDA, "so100_measure_fp32_peak: no such CUDA device");
-  CUDA_OK(cudaSetDevice(device));
+  DeviceGuard guard(device);
   int sms = 0;
   CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int blocks = sms * 8, threads = 256, iters = 1 << 15;
@@ -913,6 +1072,7 @@ int so100_measure_fp32_peak(int device, float* tflops) {
 
 int so100_group_times(so100_handle h, float* ms, int32_t* ngroups, void* stream) {
   if (!h || !ms || !ngroups) return fail(SO100_ERR_ARG, "so100_group_times: bad argument");
+  DeviceGuard guard(h->device);
   *ngroups = 0;
   if (!h->group_times || h->groups.size() < 2) return SO100_OK;
   CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
@@ -926,6 +1086,7 @@ int so100_group_times(so100_handle h, float* ms, int32_t* ngroups, void* stream)
 
 int so100_phase_timing(so100_handle h, int enable, float* ms6, int32_t* launches6, void* stream) {
   if (!h) return fail(SO100_ERR_ARG, "so100_phase_timing: null handle");
+  DeviceGuard guard(h->device);
   if (ms6 || launches6) {
     CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
     float ms[CLS_N] = {0};
@@ -945,6 +1106,7 @@ int so100_phase_timing(so100_handle h, int enable, float* ms6, int32_t* launches
 
 int so100_debug_read(so100_handle h, int what, float* out, int64_t* words_per_env, void* stream) {
   if (!h || (what != 0 && what != 1)) return fail(SO100_ERR_ARG, "so100_debug_read: bad argument");
+  DeviceGuard guard(h->device);
   const size_t words = what == 0 ? STATE_WORDS : WORK_WORDS;
   if (words_per_env) *words_per_env = (int64_t)words;
   if (out)
@@ -953,8 +1115,36 @@ int so100_debug_read(so100_handle h, int what, float* out, int64_t* words_per_en
   return SO100_OK;
 }
 
+int so100_set_episode_outputs(so100_handle h, float* ep_return, int32_t* ep_length) {
+  if (!h) return fail(SO100_ERR_ARG, "so100_set_episode_outputs: null handle");
+  h->ep_return = ep_return; h->ep_length = ep_length;     // part of the step graph's key: a change captures a new graph
+  return SO100_OK;
+}
+
+int so100_episode_stats(so100_handle h, double* out4, void* stream) {
+  if (!h || !out4) return fail(SO100_ERR_ARG, "so100_episode_stats: bad argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->ep_stats) CUDA_OK(cudaMalloc(&h->ep_stats, 4 * sizeof(double)));
+  CUDA_OK(cudaMemsetAsync(h->ep_stats, 0, 4 * sizeof(double), st));
+  episode_reduce_kernel<<<148, 256, 0, st>>>(h->state, h->n, h->ep_stats);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(out4, h->ep_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return SO100_OK;
+}
+
+int so100_graph_stats(so100_handle h, int32_t* captures, int32_t* cached, int32_t* staged) {
+  if (!h) return fail(SO100_ERR_ARG, "so100_graph_stats: null handle");
+  if (captures) *captures = h->graph_captures;
+  if (cached) *cached = (int32_t)h->graphs.size();
+  if (staged) *staged = h->stage_outputs ? 1 : 0;
+  return SO100_OK;
+}
+
 int so100_diagnostics(so100_handle h, int64_t* out8, void* stream) {
   if (!h || !out8) return fail(SO100_ERR_ARG, "so100_diagnostics: bad argument");
+  DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_OK(cudaMemsetAsync(h->diag, 0, SO100_NDIAG * sizeof(unsigned long long), st));
   diag_reduce_kernel<<<148, 256, 0, st>>>(h->state, h->n, h->diag);

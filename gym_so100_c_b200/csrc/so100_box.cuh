@@ -226,7 +226,7 @@ __device__ int box_contacts(const Tile<LPE>& t, float* con, int base, const Obb&
 }
 
 // Stage A for one env.  Writes the contact list and the header of workspace record `w`; returns (on every lane)
-// the number of hull pairs that need GJK/EPA, with *ncon_out the contact count so far (NC + 1 = overflow) and *coupled_out
+// the number of hull pairs that need GJK/EPA, with *ncon_out the contact count so far (NC + 1 = list full) and *coupled_out
 // whether one of them joins an arm link and the cube (dense Hessian: medium / heavy solve kernel).
 //   1. world bounds of the 25 collidable geoms (one lane each): centre + bounding radius, AABB half extents;
 //   2. broad phase over the static 191-pair table (one lane per pair): sphere-sphere and AABB-AABB; any
@@ -309,12 +309,14 @@ template <unsigned LPE> __device__ int collide_box_env(const Tile<LPE>& t, BoxS*
     load_obb(S->f, T.geom[bp.y], mk(c2.x, c2.y, c2.z), B);
     const int nc = box_contacts(t, con, ncon, A, B, (int)S->qcode[k], S->qsep[k], (bp.z & 0x7f) == MODE_BOX_SINGLE, p);
     if (nc > 0 && (bp.z & PAIR_COUPLES)) coupled = HDR_COUPLED;
-    ncon = min(ncon + nc, NC + 1);   // NC + 1 marks overflow
+    ncon = min(ncon + nc, NC + 1);   // NC + 1: the list is full (the NC records written are valid)
   }
-  // more penetrating box pairs / hull pairs than the lists hold: counted as a contact overflow
-  if (npen > NPEN || nsurv > NHP) { ncon = NC + 1; nsurv = min(nsurv, NHP); }
+  // more penetrating box pairs / hull pairs than the lists hold: the contact count stays the number of valid records; the
+  // overflow is flagged in the header and counted by the task kernel (diagnostics[0])
+  int overflow = 0;
+  if (npen > NPEN || nsurv > NHP) { overflow = HDR_OVERFLOW; nsurv = min(nsurv, NHP); }
   if (lane == 0)
-    *reinterpret_cast<int4*>(w + W_HDR) = make_int4(ncon, nsurv, min(nbox, 255) | (min(npen, 255) << 8) | (min(ncand - nbox, 255) << 16) | coupled, nsurv);
+    *reinterpret_cast<int4*>(w + W_HDR) = make_int4(ncon, nsurv, min(nbox, 255) | (min(npen, 255) << 8) | (min(ncand - nbox, 255) << 16) | coupled | overflow, nsurv);
   *ncon_out = ncon;
   *coupled_out = coupled != 0;
   return nsurv;

@@ -120,9 +120,11 @@ struct SolveOut {
   int forward;       // 0: integrate and store the state (the step path)
 };
 
+// `active` = false (only with several tiles per warp): the tile has no env to solve but its warp sibling does; it loads a valid
+// record, takes part in the warp votes of the solver loop with "done", and stores nothing
 template <bool DENSE, unsigned LPE, class ES>
 __device__ int solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w, int env, int ncon_raw, const DevTables& T,
-                         const SolveOut& O) {
+                         const SolveOut& O, bool active = true) {
   const int lane = t.thread_rank();
   copy_vec<LPE, 48>(t, S->st, rec);
   copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
@@ -133,7 +135,8 @@ __device__ int solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w, 
   if (lane == 0) S->ncon = ncon;
   t.sync();
   make_contact_rows(t, S, T);
-  const int iters = solve<DENSE>(t, S, T, O.forward ? nullptr : reinterpret_cast<uint32_t*>(rec + S_DIAG));
+  const int iters = solve<DENSE>(t, S, T, (O.forward || !active) ? nullptr : reinterpret_cast<uint32_t*>(rec + S_DIAG), active);
+  if (!active) return iters;
   if (O.forward) {
     t.sync();
     if (O.qacc && lane < NV) O.qacc[(size_t)env * NV + lane] = S->a[lane];
@@ -151,11 +154,13 @@ template <unsigned LPE>
 __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TPB_K3L) phase_solve_light(float* state, const float* work, int n, DevTables T, Queues Q, SolveOut O) {
   SO100_TILE_PROLOGUE(LPE, SO100_TPB_K3L, SolS<NCL>);
   const int slot = blockIdx.x * EPB + t.meta_group_rank();
-  if (slot >= n) return;
-  const int env = Q.order_in[slot];
+  const bool live = slot < n;
+  if (LPE == 32 && !live) return;            // one tile per warp: nobody to vote with
+  const int env = Q.order_in[live ? slot : n - 1];
   const float* w = work + (size_t)env * WORK_WORDS;
   const int4 hdr = *reinterpret_cast<const int4*>(w + W_HDR);
   const int ncon_raw = (hdr.z & HDR_COUPLED) ? NC + 2 : hdr.x;      // arm-cube contacts: heavy kernel (dense Hessian)
+  const bool mine = live && ncon_raw <= NCL;
   int iters = 1000;                          // heavy envs count as slow
 #ifdef SO100_SOLVE_CLOCK
   unsigned long long t0_;
@@ -164,7 +169,9 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
 #ifdef SO100_SOLVE_CLOCK
   if (lane < 4) S->clk2[lane] = 0;
 #endif
-  if (ncon_raw <= NCL) iters = solve_env<false>(t, S, state + (size_t)env * STATE_WORDS, w, env, ncon_raw, T, O);
+  // several tiles per warp: every tile enters the solver (its loop votes warp-wide), the ones without work as inactive
+  if (LPE < 32) { const int it_ = solve_env<false>(t, S, state + (size_t)env * STATE_WORDS, w, env, min(ncon_raw, NCL), T, O, mine); if (mine) iters = it_; }
+  else if (mine) iters = solve_env<false>(t, S, state + (size_t)env * STATE_WORDS, w, env, ncon_raw, T, O);
 #ifdef SO100_SOLVE_CLOCK
   // development build: duration (ns) and iteration count of this env's last solve in the spare words of its state record
   unsigned long long t1_;
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
     rec_[60] = __int_as_float(S->clk2[0]); rec_[61] = __int_as_float(S->clk2[1]); rec_[63] = __int_as_float(S->clk2[2]);   // dense split replaces eval/grad/ls
   }
 #endif
-  if (!O.forward && lane == 0) {
+  if (!O.forward && live && lane == 0) {
     const int pos = iters >= 3 ? atomicAdd(&Q.ctl[Q_SLOW], 1) : n - 1 - atomicAdd(&Q.ctl[Q_FAST], 1);
     Q.order_out[pos] = env;
   }
@@ -343,6 +350,24 @@ __global__ void diag_reduce_kernel(const float* state, int n, unsigned long long
   }
   __syncthreads();
   if (threadIdx.x < SO100_NDIAG_K) atomicAdd(&out[threadIdx.x], acc[threadIdx.x]);
+}
+
+// episode statistics over all envs: out[0] episodes finished, [1] successes, [2] sum of episode returns, [3] sum of episode lengths
+__global__ void episode_reduce_kernel(const float* state, int n, double* out) {
+  __shared__ double acc[4];
+  if (threadIdx.x < 4) acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < n; env += gridDim.x * blockDim.x) {
+    const float* rec = state + (size_t)env * STATE_WORDS;
+    const uint32_t* d = reinterpret_cast<const uint32_t*>(rec + S_DIAG);
+    a[0] += (double)d[3]; a[1] += (double)d[4];
+    a[2] += (double)rec[S_RETSUM]; a[3] += (double)__float_as_uint(rec[S_LENSUM]);
+  }
+  for (int k = 0; k < 4; k++)
+    if (a[k] != 0.0) atomicAdd(&acc[k], a[k]);
+  __syncthreads();
+  if (threadIdx.x < 4) atomicAdd(&out[threadIdx.x], acc[threadIdx.x]);
 }
 
 }  // namespace so100

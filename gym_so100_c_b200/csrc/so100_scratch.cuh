@@ -27,6 +27,7 @@ template <unsigned LPE> using Tile = cg::thread_block_tile<LPE>;
 
 constexpr int PAIR_COUPLES = 0x80; // DevTables::bpair mode byte, bit 7: the pair joins an arm link and the cube
 constexpr int HDR_COUPLED = 1 << 30;   // workspace header word 2: the env has such a contact this substep
+constexpr int HDR_OVERFLOW = 1 << 29;  // workspace header word 2: more penetrating box pairs / hull pairs / contacts than the lists hold
 constexpr int HDR_STALE = -1;          // workspace header word 3 (hull pairs pending, 0 after a complete collision stage): the
                                        // env was reset after its last collision stage
 constexpr int NCL = 8;             // contact capacity of the light solve kernel (99.7 % of all solves)

@@ -18,11 +18,20 @@
 namespace so100 {
 
 constexpr int S_DIAG = 49;         // per-env diagnostic counters inside the state record (uint32 words 49..56)
+constexpr int S_EPRET = 57;        // float: return of the running episode
+constexpr int S_RETSUM = 58;       // float: sum of the returns of this env's finished episodes
+constexpr int S_LENSUM = 59;       // uint32: sum of their lengths (the -DSO100_SOLVE_CLOCK development build overwrites 57..63)
 #ifndef SO100_NEWTON_MAXIT
-#define SO100_NEWTON_MAXIT 50
+#define SO100_NEWTON_MAXIT 100
 #endif
-constexpr int NEWTON_MAXIT = SO100_NEWTON_MAXIT;   // MuJoCo: 100; warm-started solves need 1-3
-constexpr int LS_MAXIT = 10;
+#ifndef SO100_LS_MAXIT
+#define SO100_LS_MAXIT 50
+#endif
+// MuJoCo's defaults, which the scene's XML leaves untouched (so_arm100.xml:4 only sets cone / impratio): iterations 100,
+// ls_iterations 50.  Both loops are data-dependent (`#pragma unroll 1`), so the caps cost nothing until a solve reaches them:
+// warm-started solves need 1-3 Newton iterations and 1-3 line-search iterates.
+constexpr int NEWTON_MAXIT = SO100_NEWTON_MAXIT;
+constexpr int LS_MAXIT = SO100_LS_MAXIT;
 #ifndef SO100_GTOL
 #define SO100_GTOL 2e-6f     // gradient tolerance relative to |qfrc_smooth| + |J^T f|
 #endif
@@ -505,7 +514,7 @@ template <unsigned LPE, class ES> __device__ __forceinline__ float dense_newton_
 
 // Solves for qacc (left in S->a / S->ad, contact forces in S->cfrc).  `diag` (nullable): the env's uint32 counters.
 // Returns the number of Newton iterations.
-template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S, const DevTables& T, uint32_t* diag) {
+template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S, const DevTables& T, uint32_t* diag, bool active = true) {
   using Regs = SolveRegs<LPE, ES::NCAP>;
   const int lane = t.thread_rank();
   const int ncon = S->ncon;
@@ -551,7 +560,7 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
   };
   set_a(qas_d);
   int stage = 0, it = 0;
-  bool done = false, last = false, converged = false;
+  bool done = !active, last = false, converged = false;
   float Ma = 0, dof_force = 0, cost = 0, cost_qas = 0;
   // one Newton iteration from the iterate / forces of the last evaluation; sets `done` when the solve is over
   SOLVE_CLK_DECL;
@@ -683,6 +692,7 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
       d2 = e2 + pMp;
       if (fabsf(d1) <= SO100_LS_TOL * d10) break;
       if (d1 < 0) lo = alpha; else hi = alpha;
+      if (hi >= 0 && hi - lo <= 2e-7f * hi) break;     // bracket at float32 resolution: nothing left to search
     }
     if (!descent) { converged = true; done = true; return; }
     if (lane < NV) {

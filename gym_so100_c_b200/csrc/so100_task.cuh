@@ -11,6 +11,8 @@ struct StepArgs {
   const float* action;     // [N,6]
   float *obs, *achieved, *desired, *reward, *final_obs;
   uint8_t *terminated, *truncated, *success;
+  float* ep_return;        // [N] or null: return of the episode an env has just finished (untouched otherwise)
+  int32_t* ep_length;      // [N] or null: its length in env steps
   int n, autoreset, task;
   uint32_t seed_lo, seed_hi;
   long long env_offset;
@@ -40,6 +42,7 @@ __device__ void reset_env(const Tile<LPE>& t, TaskS* S, long long gid, const flo
 #pragma unroll
     for (int k = 0; k < NV; k++) { S->st[S_QVEL + k] = 0.0f; S->st[S_WARM + k] = 0.0f; }
     S->st[S_STEP] = __int_as_float(0);
+    S->st[S_EPRET] = 0.0f;
     if (task == 1) {
       uint32_t r[4];
       philox4x32((uint32_t)gid, (uint32_t)((unsigned long long)gid >> 32), episode, 1u, seed_lo, seed_hi, r);
@@ -158,10 +161,22 @@ template <unsigned LPE> __device__ void task_env(const Tile<LPE>& t, TaskS* S, c
   if (lane == 0) {
     S->st[S_STEP] = __int_as_float(step_count);
     S->st[S_TOTAL] = __int_as_float(total);
-    if (ncon_raw > NC) diag[0] += 1u;
+    if (ncon_raw > NC || (__float_as_int(w[W_HDR + 2]) & HDR_OVERFLOW)) diag[0] += 1u;
     if (bad) diag[2] += 1u;
     if (term || trunc) diag[3] += 1u;
     if (succ) diag[4] += 1u;
+    // RecordEpisodeStatistics (scripts/train_sac.py:290, train_sac_her.py:226): running return of the episode; on its end the
+    // return / length go to the per-env outputs and into the per-env sums that so100_episode_stats reduces
+    const float epret = S->st[S_EPRET] + reward;
+    if (term || trunc) {
+      S->st[S_RETSUM] += epret;
+      S->st[S_LENSUM] = __uint_as_float(__float_as_uint(S->st[S_LENSUM]) + (uint32_t)step_count);
+      if (A.ep_return) A.ep_return[env] = epret;
+      if (A.ep_length) A.ep_length[env] = step_count;
+      S->st[S_EPRET] = 0.0f;
+    } else {
+      S->st[S_EPRET] = epret;
+    }
     if (A.reward) A.reward[env] = reward;
     if (A.terminated) A.terminated[env] = term ? 1 : 0;
     if (A.truncated) A.truncated[env] = trunc ? 1 : 0;

@@ -54,6 +54,10 @@ class BatchedSim:
         self.terminated = torch.zeros(n, **u8)
         self.truncated = torch.zeros(n, **u8)
         self.success = torch.zeros(n, **u8)
+        # return / length of the episode an env finished last (RecordEpisodeStatistics' info["episode"]), written by the task kernel
+        self.ep_return = torch.zeros(n, **f32)
+        self.ep_length = torch.zeros(n, dtype=torch.int32, device=dev)
+        ext.check(self.lib.so100_set_episode_outputs(self.h, _ptr(self.ep_return), _ptr(self.ep_length)), "so100_set_episode_outputs")
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -203,6 +207,17 @@ class BatchedSim:
                                               cnt.ctypes.data_as(C.c_void_p) if read else None, self._stream()), "so100_phase_timing")
         names = ["kin_dyn", "collide_box", "solve_light", "task", "collide_hull", "solve_heavy"]
         return dict(zip(names, ms.tolist())), dict(zip(names, cnt.tolist()))
+
+    def episode_stats(self) -> Dict[str, float]:
+        """Episodes finished, successes, sum of episode returns and lengths over all envs since construction."""
+        out = np.zeros(4, dtype=np.float64)
+        ext.check(self.lib.so100_episode_stats(self.h, out.ctypes.data_as(C.c_void_p), self._stream()), "so100_episode_stats")
+        return {"episodes": int(out[0]), "successes": int(out[1]), "return_sum": float(out[2]), "length_sum": int(out[3])}
+
+    def graph_stats(self) -> Dict[str, int]:
+        c, k, s = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        ext.check(self.lib.so100_graph_stats(self.h, C.byref(c), C.byref(k), C.byref(s)), "so100_graph_stats")
+        return {"captures": c.value, "cached": k.value, "staged": s.value}
 
     def diagnostics(self) -> Dict[str, int]:
         out = np.zeros(ext.NDIAG, dtype=np.int64)

@@ -16,7 +16,7 @@ SYMBOLS = [
     "so100_create", "so100_destroy", "so100_num_envs", "so100_launches_per_step", "so100_reset", "so100_step", "so100_step_host",
     "so100_compute_reward", "so100_get_state", "so100_set_state", "so100_get_aux", "so100_set_aux",
     "so100_substeps", "so100_forward", "so100_diagnostics", "so100_phase_timing", "so100_group_times", "so100_debug_read", "so100_last_error",
-    "so100_measure_fp32_peak",
+    "so100_measure_fp32_peak", "so100_set_episode_outputs", "so100_episode_stats", "so100_graph_stats",
 ]
 
 MAX_CONTACTS = 24
@@ -65,6 +65,9 @@ def load():
     lib.so100_group_times.argtypes = [vp, vp, vp, vp]
     lib.so100_measure_fp32_peak.argtypes = [i32, vp]
     lib.so100_debug_read.argtypes = [vp, i32, vp, vp, vp]
+    lib.so100_set_episode_outputs.argtypes = [vp, vp, vp]
+    lib.so100_episode_stats.argtypes = [vp, vp, vp]
+    lib.so100_graph_stats.argtypes = [vp, vp, vp, vp]
     lib.so100_last_error.restype = C.c_char_p
     for name in SYMBOLS:
         if name != "so100_last_error":

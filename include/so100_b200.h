@@ -51,7 +51,9 @@ enum so100_task {
  * (gym_so100/env.py:29-77, 92-128).  `model_blob` (host) is the packed so100_model
  * (include/so100_model.h) produced by gym_so100_c_b200.model.pack(); `env_offset` is the global
  * index of this handle's env 0 (multi-GPU sharding: RNG streams depend on the global index only).  All live handles of a
- * process must use the same model (its constants sit in __constant__ memory); a different one fails with SO100_ERR_MODEL. */
+ * process on one device must use the same model (its constants sit in that device's __constant__ memory); a different one
+ * fails with SO100_ERR_MODEL.  Every entry point switches to the handle's device and restores the caller's current device;
+ * on any failure nothing stays allocated. */
 int so100_create(const void* model_blob, size_t nbytes, int num_envs, int device, int task,
                  uint64_t seed, int64_t env_offset, so100_handle* out);
 int so100_destroy(so100_handle h);
@@ -113,6 +115,20 @@ int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom,
  * states forced to reset, [3] episodes finished, [4] successes, [5] total Newton iterations,
  * [6] total solver runs, [7] total contacts seen. */
 int so100_diagnostics(so100_handle h, int64_t* out8, void* stream);
+
+/* Replaces: gymnasium's RecordEpisodeStatistics around the env (scripts/train_sac.py:290, scripts/train_sac_her.py:226).
+ * The task layer keeps every env's running episode return and length on the device.  so100_set_episode_outputs registers
+ * optional per-env outputs (device; float32 [N] / int32 [N]; either may be NULL): at the step an env's episode ends they
+ * receive its return and length (info["episode"]["r"], ["l"]); other entries are left untouched.  Call it before the first
+ * so100_step, or expect one more graph capture.  so100_episode_stats sums over all envs since create (host double[4]:
+ * episodes finished, successes, sum of episode returns, sum of episode lengths; synchronises the stream): the vector that
+ * gym_so100_c_b200.parallel.all_reduce_stats adds up over the GPUs. */
+int so100_set_episode_outputs(so100_handle h, float* ep_return, int32_t* ep_length);
+int so100_episode_stats(so100_handle h, double* out4, void* stream);
+
+/* Step-graph cache of this handle (host ints, any may be NULL): graphs captured since create, graphs cached now, and whether
+ * the handle has switched to staging outputs because the caller keeps rotating its output pointers (so100_b200.cu). */
+int so100_graph_stats(so100_handle h, int32_t* captures, int32_t* cached, int32_t* staged);
 
 /* Measurement aid (bench.py roofline): when enabled, every kernel launched by so100_step is bracketed by a CUDA
  * event pair on `stream`.  A call first reports (if ms6 / launches6 are non-NULL; synchronises the stream) the

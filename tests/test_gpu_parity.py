@@ -7,7 +7,10 @@ Scenario classes (tests/scenarios.py):
   * general-hull contacts (GJK/EPA): penetration depth and normal must agree for every env; the
     contact POINT is not unique when two features are parallel (hard part 2),
     and which vertices count as "the deepest feature" flips with the 1e-4 rad resolution of the
-    float32 EPA normal, so point / force / acceleration agreement is required for >= 80 % of the envs.
+    float32 EPA normal, so point / force / acceleration agreement is required for >= 95 % of the envs (measured on
+    256 envs per scenario: 97.7-100 %; the rest are parallel-feature contacts where the 1e-6 m deepest-feature band
+    sees a different vertex set through a normal that differs by 2e-5 rad).
+  * the bench's own state distribution (config 3 after 60 steps of U(-1,1) actions): test_config3_distribution_parity.
 """
 import numpy as np
 import pytest
@@ -55,7 +58,7 @@ def test_forward_parity(model_blob, name):
     tol_q = 2e-4 if name in CONTACT_FREE else 2e-3       # relative to (1 + |qacc|)
     ok = [e["pos"] < 2e-5 and e["force"] < 5e-3 and e["qacc"] < tol_q for e in errs]
     if name in HULL:
-        assert np.mean(ok) >= 0.8, (name, float(np.mean(ok)), worst)
+        assert np.mean(ok) >= 0.95, (name, float(np.mean(ok)), worst)
     else:
         assert all(ok), (name, worst)
 
@@ -75,7 +78,7 @@ def test_single_substep_parity(model_blob, name):
     ep = np.abs(qp_g - qp_o).max(axis=1)                # h * dv plus float32 rounding of qpos
     ok = (ev < tol_v) & (ep < 2e-6)
     if name in HULL:
-        assert ok.mean() >= 0.8, (name, float(ok.mean()), float(ev.max()))
+        assert ok.mean() >= 0.95, (name, float(ok.mean()), float(ev.max()))
     else:
         assert ok.all(), (name, float(ev.max()), float(ep.max()))
     sim.close()
@@ -556,4 +559,145 @@ def test_contact_reuse_is_invalidated_by_state_writes(model_blob):
     for x, y in zip(a.get_state(), b.get_state()):
         assert torch.equal(x, y)
     assert torch.equal(ra, rb) and torch.equal(a.obs, b.obs)
+    a.close(); b.close()
+
+
+def test_unnormalize_golden_set_on_device(model_blob):
+    """unnormalize_so100 (constants.py:44-47, 78-86) on the DEVICE over the whole golden action set produced by the
+    reference's own Python, including the actions beyond [-1, 1] that exercise the clip: ctrl after one env.step must equal
+    the reference's float32 values bit for bit."""
+    import json
+    import os
+    import torch
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.json")))["unnormalize_so100"]
+    act = np.array(gold["action"], dtype=np.float32)
+    want = np.array(gold["ctrl"], dtype=np.float32)
+    assert (np.abs(act) > 1).any() and (np.abs(act) <= 1).any()          # both clipped and unclipped cases are in the set
+    n = act.shape[0]
+    from gym_so100_c_b200.engine import BatchedSim
+    sim = BatchedSim(n, device="cuda:0", task=0, seed=1, model_blob=model_blob)
+    sim.reset()
+    sim.step(torch.from_numpy(act), autoreset=False)
+    ctrl = sim.get_state()[2].cpu().numpy()
+    assert np.array_equal(ctrl, want)
+    sim.close()
+
+
+def test_config3_distribution_parity(model_blob):
+    """Parity on the bench's own state distribution (BASELINE config 3): 16384 envs x 60 steps of U(-1,1) actions on the GPU
+    (arms on the table / base, cubes knocked about, joints at their limits), then a 1024-env subsample of that state is injected
+    into the fp64 oracle and both take one more env.step with identical actions.  Per contact class of the injected state
+    (no contact / box contacts only / at least one general-hull contact) the fraction of envs within
+        qvel 1e-4 relative to (1 + |qvel|) after the 10 substeps, contact force 1e-3 relative to max(1, |f|) in mj_forward,
+        reward / terminated / truncated / success exactly
+    must be >= 99 % (no contact, box) and >= 95 % (hull).  Measured: 100 % / 100 % / 97.9-100 %."""
+    import torch
+    from gym_so100_c_b200.engine import BatchedSim
+    from oracle.so100_oracle import Oracle
+    from gym_so100_c_b200 import model
+    n_big, stride, settle = 16384, 16, 60
+    dev = torch.device("cuda:0")
+    sim = BatchedSim(n_big, device=dev, task=0, seed=0x50100, model_blob=model_blob)
+    sim.reset()
+    g = torch.Generator(device=dev).manual_seed(1234)
+    for s in range(settle):
+        sim.step(torch.rand((n_big, 6), device=dev, generator=g) * 2 - 1, autoreset=True)
+    qpos, qvel, ctrl, warm = [t[::stride].contiguous().cpu() for t in sim.get_state()]
+    goal, step, total, episode = [t[::stride].contiguous().cpu() for t in sim.get_aux()]
+    sim.close()
+    n = qpos.shape[0]
+    act = (torch.rand((n, 6), generator=torch.Generator().manual_seed(99)) * 2 - 1)
+    sub = BatchedSim(n, device=dev, task=0, seed=0x50100, model_blob=model_blob)
+    orc = Oracle(model_blob, n, task=0, seed=0x50100)
+    sub.reset(); orc.reset()
+    st64 = [t.numpy().astype(np.float64) for t in (qpos, qvel, ctrl, warm)]
+    sub.set_state(qpos, qvel, ctrl, warm)
+    sub.set_aux(step_count=step, total_steps=total, episode=episode)
+    orc.set_state(*st64)
+    orc.set_counters(step_count=step.numpy(), episode=episode.numpy().astype(np.uint32))
+    # mj_forward on the injected state: contact classes and forces
+    fwd = sub.forward()
+    orc.forward()
+    m = model.unpack(model_blob)
+    hull_ids = {int(m["geom_mjid"][k]) for k in range(int(m["ngeom"])) if int(m["geom_type"][k]) == 7 and int(m["geom_vnum"][k]) != 8}
+    cls, force_ok = [], []
+    for i in range(n):
+        oc = orc.contacts(i)
+        cls.append("none" if not oc else ("hull" if any(c["geom1"] in hull_ids or c["geom2"] in hull_ids for c in oc) else "box"))
+        pairs = match_contacts(gpu_contacts(fwd, i), oc)
+        force_ok.append(pairs is not None and contact_errors(pairs)["force"] < 1e-3)
+    cls, force_ok = np.array(cls), np.array(force_ok)
+    # one env.step on both from the same state
+    sub.set_state(qpos, qvel, ctrl, warm)
+    orc.set_state(*st64)
+    out_o = orc.step(act.numpy(), autoreset=False)
+    obs, rew, term, trunc, succ = sub.step(act, autoreset=False)
+    qp_g, qv_g, ctrl_g, _ = [t.cpu().numpy().astype(np.float64) for t in sub.get_state()]
+    qp_o, qv_o, ctrl_o, _ = orc.get_state()
+    assert np.array_equal(ctrl_g, ctrl_o)
+    vel_ok = np.array([rel_err(qv_g[i], qv_o[i], floor=1.0) < 1e-4 for i in range(n)])
+    flags_ok = (rew.cpu().numpy() == out_o["reward"]) & (term.cpu().numpy().astype(bool) == out_o["terminated"]) & \
+               (trunc.cpu().numpy().astype(bool) == out_o["truncated"]) & (succ.cpu().numpy().astype(bool) == out_o["success"])
+    ok = vel_ok & force_ok & flags_ok
+    report = {c: (int((cls == c).sum()), float(ok[cls == c].mean()) if (cls == c).any() else 1.0) for c in ("none", "box", "hull")}
+    print("config-3 distribution parity (envs, fraction within tolerance):", report)
+    assert (cls == "box").sum() > 500 and (cls == "hull").sum() >= 20, report       # the distribution really has contacts
+    assert report["none"][1] >= 0.99 and report["box"][1] >= 0.99 and report["hull"][1] >= 0.95, report
+    assert flags_ok.mean() >= 0.999, float(flags_ok.mean())
+    sub.close(); orc.close()
+
+
+def test_episode_statistics_accumulate_on_device(model_blob):
+    """RecordEpisodeStatistics equivalent (scripts/train_sac.py:290): per-env episode return / length at the step an episode
+    ends, and their sums over all envs, against a host-side accumulation of the returned rewards / flags."""
+    import torch
+    from gym_so100_c_b200.engine import BatchedSim
+    n = 512
+    sim = BatchedSim(n, device="cuda:0", task=2, seed=3, model_blob=model_blob)      # shaped TouchCube reward: non-trivial returns
+    sim.reset()
+    sim.set_aux(step_count=torch.randint(285, 299, (n,), dtype=torch.int32))          # episodes end at different steps
+    g = torch.Generator(device="cuda").manual_seed(8)
+    ret = np.zeros(n); length = sim.get_aux()[1].cpu().numpy().astype(np.int64); ret_sum = 0.0; len_sum = 0; episodes = 0
+    for k in range(20):
+        obs, rew, term, trunc, succ = sim.step(torch.rand((n, 6), device="cuda", generator=g) * 2 - 1, autoreset=True)
+        r = rew.cpu().numpy().astype(np.float64); done = (term.bool() | trunc.bool()).cpu().numpy()
+        ret += r; length += 1
+        if done.any():
+            np.testing.assert_allclose(sim.ep_return.cpu().numpy()[done], ret[done], rtol=1e-5, atol=1e-5)
+            assert np.array_equal(sim.ep_length.cpu().numpy()[done], length[done])
+            ret_sum += ret[done].sum(); len_sum += int(length[done].sum()); episodes += int(done.sum())
+            ret[done] = 0; length[done] = 0
+    st = sim.episode_stats()
+    assert episodes >= n and st["episodes"] == episodes and st["length_sum"] == len_sum
+    assert abs(st["return_sum"] - ret_sum) < 1e-3 * max(1.0, abs(ret_sum))
+    sim.close()
+
+
+def test_rotating_output_buffers_do_not_recapture(model_blob):
+    """The step-graph cache is bounded and a caller that rotates its output buffers is moved to stable staging outputs: after
+    the switch no further graph is captured, and the results equal those of a handle that always passes the same buffers."""
+    import ctypes as C
+    import torch
+    from gym_so100_c_b200 import ext
+    from gym_so100_c_b200.engine import BatchedSim
+    n = 2048
+    a = BatchedSim(n, device="cuda:0", task=0, seed=5, model_blob=model_blob)
+    b = BatchedSim(n, device="cuda:0", task=0, seed=5, model_blob=model_blob)
+    a.reset(); b.reset()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    lib = a.lib
+    p = lambda t: C.c_void_p(t.data_ptr())
+    caps, hold = [], []
+    for k in range(24):
+        act = torch.rand((n, 6), device="cuda", generator=g) * 2 - 1
+        obs = torch.empty((n, 15), device="cuda"); rew = torch.empty(n, device="cuda")       # fresh buffers every call
+        term = torch.empty(n, dtype=torch.uint8, device="cuda")
+        ext.check(lib.so100_step(a.h, p(act), 1, p(obs), None, None, p(rew), p(term), None, None, None, a._stream()), "so100_step")
+        ref_obs, ref_rew, ref_term, _, _ = b.step(act, autoreset=True)
+        assert torch.equal(obs, ref_obs) and torch.equal(rew, ref_rew) and torch.equal(term, ref_term), k
+        caps.append(a.graph_stats()["captures"])
+        hold.append((obs, rew, term))                                                      # keeps every call's addresses distinct
+    st = a.graph_stats()
+    assert st["staged"] == 1 and caps[-1] == caps[12], (st, caps)                        # no capture during the last 12 calls
+    assert st["cached"] <= 4 * 9
     a.close(); b.close()

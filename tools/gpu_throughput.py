@@ -19,8 +19,8 @@ def main():
     acts = torch.rand((steps + 20, n, 6), device="cuda", generator=g) * 2 - 1
     if len(sys.argv) > 3 and sys.argv[3] == "mix":
         return mix(sim, n, steps, acts)
-    for s in range(20):
-        sim.step(acts[s])
+    for s in range(int(os.environ.get("WARM", "150"))):       # settle: the bench workload's steady state needs ~150 steps
+        sim.step(acts[s % 20])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
