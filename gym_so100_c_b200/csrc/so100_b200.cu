@@ -14,6 +14,7 @@
 
 namespace so100 { constexpr int SO100_NDIAG_K = SO100_NDIAG; }
 #include "so100_phases.cuh"
+#include "so100_her.cuh"
 
 using namespace so100;
 
@@ -1131,6 +1132,53 @@ int so100_episode_stats(so100_handle h, double* out4, void* stream) {
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(out4, h->ep_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
+  return SO100_OK;
+}
+
+// ---- HER ring (so100_her.cuh)
+static int her_ring(const so100_her_ring* r, HerRing& R) {
+  if (!r || r->capacity <= 0 || r->num_envs <= 0) return fail(SO100_ERR_ARG, "so100_her: bad ring geometry");
+  const void* ptrs[] = {r->obs, r->next_obs, r->achieved, r->next_achieved, r->desired, r->action, r->reward, r->done,
+                        r->ep_start, r->ep_length, r->cur_start, r->cur_length};
+  for (const void* p : ptrs) if (!p) return fail(SO100_ERR_ARG, "so100_her: null ring array");
+  R = HerRing{r->capacity, r->num_envs, r->obs, r->next_obs, r->achieved, r->next_achieved, r->desired, r->action, r->reward, r->done,
+              r->ep_start, r->ep_length, r->cur_start, r->cur_length};
+  return SO100_OK;
+}
+
+int so100_her_begin(const so100_her_ring* ring, int32_t pos, const float* obs, const float* achieved, const float* desired,
+                    const float* action, void* stream) {
+  HerRing R;
+  if (int rc = her_ring(ring, R)) return rc;
+  if (pos < 0 || pos >= R.capacity || !obs || !achieved || !desired || !action) return fail(SO100_ERR_ARG, "so100_her_begin: bad argument");
+  her_begin_kernel<<<(R.num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(R, pos, obs, achieved, desired, action);
+  CUDA_OK(cudaGetLastError());
+  return SO100_OK;
+}
+
+int so100_her_commit(const so100_her_ring* ring, int32_t pos, const float* obs, const float* achieved, const float* final_obs,
+                     const float* reward, const uint8_t* terminated, const uint8_t* truncated, void* stream) {
+  HerRing R;
+  if (int rc = her_ring(ring, R)) return rc;
+  if (pos < 0 || pos >= R.capacity || !obs || !achieved || !final_obs || !reward || !terminated || !truncated)
+    return fail(SO100_ERR_ARG, "so100_her_commit: bad argument");
+  her_commit_kernel<<<(R.num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(R, pos, obs, achieved, final_obs, reward, terminated, truncated);
+  CUDA_OK(cudaGetLastError());
+  return SO100_OK;
+}
+
+int so100_her_sample(const so100_her_ring* ring, int64_t batch, int32_t n_sampled_goal, float threshold, uint64_t seed, uint32_t call,
+                     float* obs, float* action, float* next_obs, float* achieved, float* next_achieved, float* desired, float* reward,
+                     uint8_t* done, int32_t* index, void* stream) {
+  HerRing R;
+  if (int rc = her_ring(ring, R)) return rc;
+  if (batch < 0 || n_sampled_goal < 0 || !obs || !action || !next_obs || !achieved || !next_achieved || !desired || !reward || !done || !index)
+    return fail(SO100_ERR_ARG, "so100_her_sample: bad argument");
+  if (batch == 0) return SO100_OK;
+  her_sample_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(R, batch, n_sampled_goal, threshold, (uint32_t)seed,
+                                                                                       (uint32_t)(seed >> 32), call, obs, action, next_obs,
+                                                                                       achieved, next_achieved, desired, reward, done, index);
+  CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
 

@@ -17,6 +17,7 @@ SYMBOLS = [
     "so100_compute_reward", "so100_get_state", "so100_set_state", "so100_get_aux", "so100_set_aux",
     "so100_substeps", "so100_forward", "so100_diagnostics", "so100_phase_timing", "so100_group_times", "so100_debug_read", "so100_last_error",
     "so100_measure_fp32_peak", "so100_set_episode_outputs", "so100_episode_stats", "so100_graph_stats",
+    "so100_her_begin", "so100_her_commit", "so100_her_sample",
 ]
 
 MAX_CONTACTS = 24
@@ -29,6 +30,13 @@ TASK_TOUCH_CUBE_SPARSE = 3
 
 class So100Error(RuntimeError):
     pass
+
+
+class HerRing(C.Structure):
+    """so100_her_ring (include/so100_b200.h): geometry + device pointers of the caller-owned replay ring."""
+    _fields_ = [("capacity", C.c_int32), ("num_envs", C.c_int32)] + [(k, C.c_void_p) for k in (
+        "obs", "next_obs", "achieved", "next_achieved", "desired", "action", "reward", "done", "ep_start", "ep_length", "cur_start",
+        "cur_length")]
 
 
 def lib_path() -> str:
@@ -68,6 +76,10 @@ def load():
     lib.so100_set_episode_outputs.argtypes = [vp, vp, vp]
     lib.so100_episode_stats.argtypes = [vp, vp, vp]
     lib.so100_graph_stats.argtypes = [vp, vp, vp, vp]
+    ring = C.POINTER(HerRing)
+    lib.so100_her_begin.argtypes = [ring, i32, vp, vp, vp, vp, vp]
+    lib.so100_her_commit.argtypes = [ring, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.so100_her_sample.argtypes = [ring, i64, i32, C.c_float, u64, C.c_uint32] + [vp] * 9 + [vp]
     lib.so100_last_error.restype = C.c_char_p
     for name in SYMBOLS:
         if name != "so100_last_error":

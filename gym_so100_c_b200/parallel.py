@@ -52,6 +52,37 @@ def all_reduce_stats(stats: Dict[str, int], device=None) -> Dict[str, int]:
     return {k: int(v) for k, v in zip(STAT_KEYS, t.tolist())}
 
 
+EPISODE_KEYS = ("episodes", "successes", "return_sum", "length_sum")
+
+
+def all_reduce_episode_stats(stats: Dict[str, float], device=None) -> Dict[str, float]:
+    """Sum the episode statistics of BatchedSim.episode_stats() (episodes finished, successes, return sum, length sum: the
+    vector SURVEY.md 8e names) over all ranks and add the means a logger reports."""
+    vals = [float(stats.get(k, 0.0)) for k in EPISODE_KEYS]
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(vals, dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        vals = t.tolist()
+    out = dict(zip(EPISODE_KEYS, vals))
+    n = max(out["episodes"], 1.0)
+    out.update(ep_rew_mean=out["return_sum"] / n, ep_len_mean=out["length_sum"] / n, success_rate=out["successes"] / n)
+    return out
+
+
+def gather_floats(value: float, device=None):
+    """[value of rank 0, value of rank 1, ...] on every rank (per-rank timings of a multi-GPU bench line)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [float(value)]
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(x.item()) for x in out]
+
+
 def max_over_ranks(value: float, device=None) -> float:
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return float(value)

@@ -171,10 +171,46 @@ class SO100GoalVecEnv(_VecBase):
         return float(r[0].item())
 
 
+class _LazyInfos:
+    """The per-env ``infos`` list of an SB3 ``VecEnv.step``: behaves like ``list[dict]`` (len, indexing, iteration) but builds
+    env i's dict only when it is asked for, from whole-batch numpy arrays.  Keys as in the reference's stack: ``is_success``,
+    ``TimeLimit.truncated`` (env.py:177, 403), and for envs that finished ``terminal_observation`` (SB3 VecEnv auto-reset) and
+    ``episode`` = {"r", "l"} (RecordEpisodeStatistics, scripts/train_sac.py:290)."""
+
+    def __init__(self, succ, timeout, done, final, goal_env, prev_desired, ep_return, ep_length):
+        self._a = (succ, timeout, done, final, goal_env, prev_desired, ep_return, ep_length)
+        self._n = len(done)
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        succ, timeout, done, final, goal_env, prev_desired, ep_return, ep_length = self._a
+        d = {"is_success": bool(succ[i]), "TimeLimit.truncated": bool(timeout[i])}
+        if done[i]:
+            if goal_env:
+                d["terminal_observation"] = {"observation": final[i].copy(), "achieved_goal": final[i, :3].copy(),
+                                             "desired_goal": None if prev_desired is None else prev_desired[i].copy()}
+            else:
+                d["terminal_observation"] = final[i].copy()
+            d["episode"] = {"r": float(ep_return[i]), "l": int(ep_length[i])}
+        return d
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+
 class SB3VecEnvAdapter:
     """Duck-typed stable_baselines3 ``VecEnv`` over a batched env: numpy in/out, same-step auto-reset,
     ``infos[i]["terminal_observation"]`` and ``env_method("compute_reward", ...)`` for ``HerReplayBuffer``
-    (scripts/train_sac_her.py:240-244).  Every call synchronises and copies to the host."""
+    (scripts/train_sac_her.py:240-244).  Every call synchronises and copies whole arrays to the host; there is no per-env
+    Python on the step path (``infos`` is a lazy sequence).  For rollouts that stay on the device use :class:`her.HerRollout`."""
 
     def __init__(self, venv: _VecBase):
         if not venv.autoreset:
@@ -207,24 +243,17 @@ class SB3VecEnvAdapter:
     def step_wait(self):
         obs, rew, term, trunc, infos = self.venv.step(self._actions)
         done = (term | trunc).cpu().numpy()
-        succ = infos["is_success"].cpu().numpy()
-        tl = infos["TimeLimit.truncated"].cpu().numpy()
-        final = infos["final_obs"].cpu().numpy()
         obs_np = self._np(obs)
-        prev_desired = getattr(self, "_desired", None)       # the goal of the episode that just ended (a reset draws a new one)
-        out = []
-        for i in range(self.num_envs):
-            d = {"is_success": bool(succ[i]), "TimeLimit.truncated": bool(tl[i])}
-            if done[i]:
-                if isinstance(obs, dict):
-                    d["terminal_observation"] = {"observation": final[i].copy(), "achieved_goal": final[i, :3].copy(),
-                                                 "desired_goal": None if prev_desired is None else prev_desired[i].copy()}
-                else:
-                    d["terminal_observation"] = final[i].copy()
-            out.append(d)
+        sim = self.venv.sim
+        # one device -> host copy per array, no per-env Python: the per-env info dicts are built lazily on access
+        info_list = _LazyInfos(
+            succ=infos["is_success"].cpu().numpy(), timeout=infos["TimeLimit.truncated"].cpu().numpy(), done=done,
+            final=infos["final_obs"].cpu().numpy(), goal_env=isinstance(obs, dict),
+            prev_desired=getattr(self, "_desired", None),       # the goal of the episode that just ended (a reset draws a new one)
+            ep_return=sim.ep_return.cpu().numpy(), ep_length=sim.ep_length.cpu().numpy())
         if isinstance(obs_np, dict):
             self._desired = obs_np["desired_goal"]
-        return obs_np, rew.cpu().numpy().copy(), done, out
+        return obs_np, rew.cpu().numpy().copy(), done, info_list
 
     def step(self, actions):
         self.step_async(actions)

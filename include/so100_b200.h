@@ -126,6 +126,35 @@ int so100_diagnostics(so100_handle h, int64_t* out8, void* stream);
 int so100_set_episode_outputs(so100_handle h, float* ep_return, int32_t* ep_length);
 int so100_episode_stats(so100_handle h, double* out4, void* stream);
 
+/* Replaces: stable_baselines3 HerReplayBuffer(n_sampled_goal, goal_selection_strategy="future") as the reference uses it
+ * around SO100GoalEnv (scripts/train_sac_her.py:231-246), kept on the device.  The ring holds `capacity` steps of `num_envs`
+ * envs in CALLER-owned device arrays (row-major [capacity, num_envs, width]); ep_start / ep_length / cur_* are its episode
+ * bookkeeping (int32, zero-initialised by the caller).  capacity must exceed the longest episode (GoalEnv: 300 steps).
+ * Per env step: so100_her_begin(ring, pos, obs, achieved, desired, action) with the observation the action was chosen on,
+ * then so100_step(..., autoreset = 1, final_obs != NULL), then so100_her_commit(ring, pos, new obs, new achieved, final_obs,
+ * reward, terminated, truncated); pos advances modulo capacity.  so100_her_sample draws `batch` transitions of finished
+ * episodes (Philox keyed by seed / call / sample index): the first batch / (n_sampled_goal + 1) keep their goal and reward,
+ * the others are relabelled with the achieved goal of a later step of the same episode and rewarded by the arithmetic of
+ * so100_compute_reward (env.py:341-353).  index int32 [batch,3] = (ring position, env, relabelling position or -1);
+ * (-1,-1,-1) marks a sample for which no finished episode was found. */
+typedef struct so100_her_ring {
+  int32_t capacity, num_envs;
+  float *obs, *next_obs;                        /* [capacity, num_envs, 15] */
+  float *achieved, *next_achieved, *desired;    /* [capacity, num_envs, 3]  */
+  float *action;                                /* [capacity, num_envs, 6]  */
+  float *reward;                                /* [capacity, num_envs]     */
+  uint8_t *done;                                /* terminated and not truncated (SB3: dones * (1 - timeouts)) */
+  int32_t *ep_start, *ep_length;                /* [capacity, num_envs]: start slot / length of the transition's episode (0: running) */
+  int32_t *cur_start, *cur_length;              /* [num_envs]: the running episode */
+} so100_her_ring;
+int so100_her_begin(const so100_her_ring* ring, int32_t pos, const float* obs, const float* achieved, const float* desired,
+                    const float* action, void* stream);
+int so100_her_commit(const so100_her_ring* ring, int32_t pos, const float* obs, const float* achieved, const float* final_obs,
+                     const float* reward, const uint8_t* terminated, const uint8_t* truncated, void* stream);
+int so100_her_sample(const so100_her_ring* ring, int64_t batch, int32_t n_sampled_goal, float threshold, uint64_t seed, uint32_t call,
+                     float* obs, float* action, float* next_obs, float* achieved, float* next_achieved, float* desired, float* reward,
+                     uint8_t* done, int32_t* index, void* stream);
+
 /* Step-graph cache of this handle (host ints, any may be NULL): graphs captured since create, graphs cached now, and whether
  * the handle has switched to staging outputs because the caller keeps rotating its output pointers (so100_b200.cu). */
 int so100_graph_stats(so100_handle h, int32_t* captures, int32_t* cached, int32_t* staged);

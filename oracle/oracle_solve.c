@@ -147,8 +147,20 @@ static void compute_jar(const oenv* e, int nv, const double* a, double* jar) {
   }
 }
 
+/* Solver mode.  0 (default, the CHECKER): iterate to the exact optimum (scaled gradient 1e-11, line search to 1e-14).
+ * 1 (the CPU BASELINE of bench.py): MuJoCo's own settings for this scene -- the XML leaves them at their defaults
+ * (so_arm100.xml:4 sets only cone / impratio): tolerance 1e-8 on the scaled gradient or the scaled improvement, at most 100
+ * Newton iterations, line search of at most 50 iterations stopping at ls_tolerance 0.01 (taken relative to the initial
+ * slope, which stops no later than MuJoCo's absolute rule). */
+static int g_solver_mode = 0;
+void so100o_set_solver_mode(int mode) { g_solver_mode = mode; }
+
 void o_solve(const so100_model* m, oenv* e) {
   int nv = m->nv, nefc = e->nefc;
+  const int fast = g_solver_mode == 1;
+  const double gtol = fast ? 1e-8 : 1e-11, lstol = fast ? 1e-2 : 1e-14;
+  const int maxit = fast ? 100 : 200, lsmax = fast ? 50 : 100;
+  double prev_cost = 0;
   static _Thread_local ctx c;
   double a[NVMAX], jar[MAXEFC], force[MAXEFC], jv[MAXEFC];
   /* warm start: previous qacc if it is cheaper than the unconstrained acceleration */
@@ -159,10 +171,12 @@ void o_solve(const so100_model* m, oenv* e) {
   memcpy(a, cw < cs ? e->warm : e->qacc_smooth, sizeof(a));
   double scale = 1.0 / (m->meaninertia * (nv > 1 ? nv : 1));
   e->solver_iter = 0;
-  for (int it = 0; it < 200; it++) {
+  for (int it = 0; it < maxit; it++) {
     compute_jar(e, nv, a, jar);
     double cost = total_cost(e, nv, a, jar, force, &c, 1);
-    (void)cost;
+    /* MuJoCo: stop when the last iteration improved the cost by less than the tolerance (scaled) */
+    if (fast && it > 0 && (prev_cost - cost) * scale < gtol) { e->solver_iter = it; break; }
+    prev_cost = cost;
     /* gradient = M a - qfrc_smooth - J^T force */
     double grad[NVMAX], H[NVMAX * NVMAX], L[NVMAX * NVMAX], p[NVMAX];
     for (int i = 0; i < nv; i++) {
@@ -177,7 +191,7 @@ void o_solve(const so100_model* m, oenv* e) {
     e->solver_grad = gn * scale;
     e->solver_iter = it;
     /* 1e-11 is ~100x above the fp64 round-off floor of this gradient and 1000x tighter than MuJoCo's 1e-8 */
-    if (gn * scale < 1e-11) break;
+    if (gn * scale < gtol) break;
     /* Hessian */
     memcpy(H, e->M, sizeof(H));
     for (int r = 0; r < nefc; r++) {
@@ -224,14 +238,14 @@ void o_solve(const so100_model* m, oenv* e) {
       fprintf(stderr, "   gp %.6e d1(0) %.6e   pHp %.6e d2(0) %.6e\n", gp, d1, pHp, d2);
     }
     if (d1 >= 0) break;                       /* not a descent direction: converged to round-off */
-    for (int ls = 0; ls < 100; ls++) {
+    for (int ls = 0; ls < lsmax; ls++) {
       double step = -d1 / d2, na = alpha + step;
       if (hi >= 0 && (na <= lo || na >= hi)) na = 0.5 * (lo + hi);
       else if (hi < 0 && na <= lo) na = 2 * alpha + 1e-6;
       alpha = na;
       ls_eval(e, jar, jv, alpha, &d1, &d2);
       d1 += pg + alpha * pMp; d2 += pMp;
-      if (fabs(d1) < 1e-14 * d10 + 1e-300) break;
+      if (fabs(d1) < lstol * d10 + 1e-300) break;
       if (d1 < 0) lo = alpha; else hi = alpha;
       if (hi >= 0 && hi - lo < 1e-16 * (1 + hi)) break;
     }

@@ -26,5 +26,7 @@ int so100o_get_contacts(const so100o* h, int i, int maxc, int32_t* geom, double*
 int so100o_get_solver(const so100o* h, int i, int* nefc, int* iters, double* grad, int* overflow);
 int so100o_get_efc(const so100o* h, int i, int maxr, double* J, double* aref, double* R, double* force, double* jar);
 int so100o_compute_reward(const float* ag, const float* dg, int n, float thr, float* out);
+/* 0: checker tolerances (default), 1: MuJoCo's solver settings (bench.py's CPU baseline), see oracle_solve.c */
+void so100o_set_solver_mode(int mode);
 int so100o_unnormalize(const so100o* h, const float* action, int n, float* out);
 #endif

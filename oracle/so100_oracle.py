@@ -27,12 +27,29 @@ def build(force: bool = False) -> str:
     return _LIB
 
 
+def build_native() -> str:
+    """The CPU-baseline build of the same sources (-O3 -march=native, FMA contraction): always rebuilt on the machine that
+    runs it, because a -march=native binary must not travel between hosts.  bench.py's CPU arm loads it with use_native()."""
+    subprocess.check_call(["make", "-C", _HERE, "-B", "libso100_oracle_native.so"], stdout=subprocess.DEVNULL)
+    return os.path.join(_HERE, "libso100_oracle_native.so")
+
+
+def use_native():
+    """Switch this process to the native build + MuJoCo's solver tolerances (bench.py's CPU arm only; never the checker)."""
+    global _lib, _LIB
+    _LIB = build_native()
+    _lib = None
+    lib().so100o_set_solver_mode(1)
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(_LIB):
             build()
         _lib = C.CDLL(_LIB)
+        _lib.so100o_set_solver_mode.restype = None
+        _lib.so100o_set_solver_mode.argtypes = [C.c_int]
         _lib.so100o_create.restype = C.c_void_p
         _lib.so100o_create.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_int64]
         _lib.so100o_destroy.argtypes = [C.c_void_p]

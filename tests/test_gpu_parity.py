@@ -701,3 +701,78 @@ def test_rotating_output_buffers_do_not_recapture(model_blob):
     assert st["staged"] == 1 and caps[-1] == caps[12], (st, caps)                        # no capture during the last 12 calls
     assert st["cached"] <= 4 * 9
     a.close(); b.close()
+
+
+def test_her_rollout_matches_host_replay(model_blob):
+    """the device-resident HER rollout (so100_her_begin / commit / sample) against a host-side replay of the same
+    rollout.  Every sampled transition must be the stored one at its reported (position, env); relabelled samples must carry
+    the achieved goal of a LATER step of the SAME finished episode and the reward compute_reward gives for it; 1/5 of the
+    batch keeps its goal and reward (n_sampled_goal = 4, scripts/train_sac_her.py:240-244); episode statistics match."""
+    import torch
+    from gym_so100_c_b200.her import HerRollout
+    from gym_so100_c_b200.vec_env import SO100GoalVecEnv
+    from oracle.so100_oracle import compute_reward
+    n, T = 256, 24
+    env = SO100GoalVecEnv(n, seed=6)
+    env.max_episode_steps = 300
+    roll = HerRollout.__new__(HerRollout)          # horizon below the TimeLimit on purpose: episodes are cut short via set_aux below
+    env_limit = env.max_episode_steps
+    env.max_episode_steps = 8
+    HerRollout.__init__(roll, env, horizon=T, n_sampled_goal=4, seed=3)
+    env.max_episode_steps = env_limit
+    roll.reset()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    # episodes of 4..8 steps: start every env close to the 300-step truncation, re-arm after each reset
+    env.sim.set_aux(step_count=torch.randint(292, 297, (n,), dtype=torch.int32))
+    log = []
+    for k in range(40):
+        o = {kk: v.clone() for kk, v in env._obs().items()}
+        a = torch.rand((n, 6), device="cuda", generator=g) * 2 - 1
+        obs, rew, done, info = roll.step(a)
+        fin = env.sim.final_obs.clone()
+        log.append(dict(obs=o["observation"].cpu().numpy(), ag=o["achieved_goal"].cpu().numpy(), dg=o["desired_goal"].cpu().numpy(),
+                        act=a.cpu().numpy(), rew=rew.cpu().numpy().copy(), done=done.cpu().numpy().copy(),
+                        term=info["is_success"].cpu().numpy().copy(),
+                        nobs=np.where(done.cpu().numpy()[:, None], fin.cpu().numpy(), obs["observation"].cpu().numpy())))
+        if done.any():
+            goal, step, total, ep = env.sim.get_aux()
+            step = torch.where(done.cpu(), torch.randint(292, 297, (n,), dtype=torch.int32), step.cpu())
+            env.sim.set_aux(step_count=step)
+    # host replay of the episode bookkeeping: for each (t, env) the [first, last] step of its episode, finished or not
+    first = np.zeros((40, n), int); last = np.full((40, n), -1)
+    for e in range(n):
+        s0 = 0
+        for t in range(40):
+            first[t, e] = s0
+            if log[t]["done"][e]:
+                last[s0:t + 1, e] = t
+                s0 = t + 1
+    B = 5000
+    batch = {k: v.cpu().numpy() for k, v in roll.sample(B).items()}
+    ix = batch["index"]
+    assert (ix[:, 0] >= 0).all()
+    n_real = B // 5
+    assert (ix[:n_real, 2] == -1).all() and (ix[n_real:, 2] >= 0).all()
+    relabel_changed = 0
+    for b in range(B):
+        pos, e, fut = ix[b]
+        # the ring position maps to the most recent step with t % T == pos
+        t = max(tt for tt in range(40) if tt % T == pos)
+        assert last[t, e] >= 0 and first[t, e] > 40 - 1 - T, (b, t, e)          # finished episode, still inside the ring
+        L = log[t]
+        assert np.array_equal(batch["obs"][b], L["obs"][e]) and np.array_equal(batch["action"][b], L["act"][e])
+        assert np.array_equal(batch["next_obs"][b], L["nobs"][e]) and np.array_equal(batch["next_achieved"][b], L["nobs"][e][:3])
+        assert batch["done"][b] == (1 if L["term"][e] else 0)
+        if fut < 0:
+            assert np.array_equal(batch["desired"][b], L["dg"][e]) and batch["reward"][b] == L["rew"][e]
+        else:
+            tf = max(tt for tt in range(40) if tt % T == fut)
+            assert t <= tf <= last[t, e], (b, t, tf, last[t, e])
+            goal = log[tf]["nobs"][e][:3]
+            assert np.array_equal(batch["desired"][b], goal)
+            assert batch["reward"][b] == compute_reward(batch["next_achieved"][b][None], goal[None])[0]
+            relabel_changed += int(batch["reward"][b] != L["rew"][e])
+    assert relabel_changed > 0          # hindsight really turns some failures into successes (the final step always does)
+    st = roll.stats()
+    assert st["episodes"] == int(sum(l["done"].sum() for l in log)) and 4 <= st["ep_len_mean"] <= 8.01
+    env.close()

@@ -111,6 +111,10 @@ parallel.barrier()
 assert tot["episodes"] == 1001, tot
 assert tot["contact_overflow"] == sum(range(1, world + 1)), tot
 assert mx == 10.0 + world - 1, mx
+ep = parallel.all_reduce_episode_stats({"episodes": 10 * (rank + 1), "successes": rank, "return_sum": -5.0 * (rank + 1), "length_sum": 100 * (rank + 1)})
+assert ep["episodes"] == 30 and ep["successes"] == 1 and ep["return_sum"] == -15.0 and ep["length_sum"] == 300, ep
+assert abs(ep["ep_rew_mean"] + 0.5) < 1e-12 and abs(ep["ep_len_mean"] - 10.0) < 1e-12 and abs(ep["success_rate"] - 1 / 30) < 1e-12, ep
+assert parallel.gather_floats(1.5 + rank) == [1.5 + r for r in range(world)]
 if rank == 0:
     print("GLOO_OK", world, tot["episodes"])
 dist.destroy_process_group()
@@ -151,3 +155,27 @@ def test_demonstration_loading_and_start_poses(tmp_path):
         pickle.dump([dict(observations=[])], f)
     with pytest.raises(ValueError):
         replay.load_demonstrations(str(path))
+
+
+def test_lazy_infos_behave_like_a_list_of_dicts():
+    """The SB3 adapter's infos (vec_env._LazyInfos): list protocol, keys of the reference's stack, terminal entries only for
+    envs that finished."""
+    import numpy as np
+    from gym_so100_c_b200.vec_env import _LazyInfos
+    n = 5
+    done = np.array([0, 1, 0, 1, 0], bool)
+    final = np.arange(n * 15, dtype=np.float32).reshape(n, 15)
+    prev = np.arange(n * 3, dtype=np.float32).reshape(n, 3)
+    infos = _LazyInfos(succ=done.copy(), timeout=~done, done=done, final=final, goal_env=True, prev_desired=prev,
+                       ep_return=np.arange(n, dtype=np.float32), ep_length=np.arange(n, dtype=np.int32) * 10)
+    assert len(infos) == n and len(list(infos)) == n and len(infos[1:3]) == 2
+    assert set(infos[0]) == {"is_success", "TimeLimit.truncated"} and infos[0]["TimeLimit.truncated"] is True
+    t = infos[3]
+    assert t["is_success"] is True and t["episode"] == {"r": 3.0, "l": 30}
+    assert np.array_equal(t["terminal_observation"]["observation"], final[3]) and np.array_equal(t["terminal_observation"]["desired_goal"], prev[3])
+    assert np.array_equal(infos[-1 - 1]["terminal_observation"]["achieved_goal"], final[3, :3])
+    with pytest.raises(IndexError):
+        infos[n]
+    flat = _LazyInfos(succ=done, timeout=done, done=done, final=final, goal_env=False, prev_desired=None,
+                      ep_return=np.zeros(n, np.float32), ep_length=np.zeros(n, np.int32))
+    assert np.array_equal(flat[1]["terminal_observation"], final[1])
