@@ -319,10 +319,10 @@ def run_gpu(args):
         from gym_so100_c_b200.vec_env import SO100GoalVecEnv
         n4 = 65536
         env4 = SO100GoalVecEnv(n4, device=dev, seed=0x50100)
-        roll = HerRollout(env4, horizon=32, n_sampled_goal=4)
+        roll = HerRollout(env4, horizon=320, n_sampled_goal=4)      # ring of 320 steps x 65536 envs (3.9 GB): holds whole 300-step episodes
         roll.reset()
         acts4 = torch.rand((8, n4, 6), device=dev, generator=gen) * 2 - 1
-        for s in range(40):
+        for s in range(310):                                        # every env finishes at least one episode: the ring has finished episodes to sample
             roll.step(acts4[s % 8])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

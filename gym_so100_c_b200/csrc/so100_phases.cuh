@@ -21,10 +21,11 @@
 namespace so100 {
 
 #ifndef SO100_TPB_K3L
-#define SO100_TPB_K3L 32      // threads per block of the light solve kernel: one env per block, so a slow env never pins idle tiles
+#define SO100_TPB_K3L 32      // threads per block of the light solve kernel: one warp per block, so a slow env pins at most its warp sibling
 #endif
 #ifndef SO100_WARPS_K3L
-#define SO100_WARPS_K3L 20    // resident warps per SM the register allocation of the light solve kernel must allow
+#define SO100_WARPS_K3L 16    // resident warps per SM the register allocation of the light solve kernel must allow (128 registers with
+                              // two envs per warp: no spills; 20 warps = 96 registers spills 132 bytes and is 4 % slower)
 #endif
 
 // K1: state -> frames (+ mass matrix, smooth forces, unconstrained acceleration); also re-arms the queues

@@ -561,7 +561,8 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
   set_a(qas_d);
   int stage = 0, it = 0;
   bool done = !active, last = false, converged = false;
-  float Ma = 0, dof_force = 0, cost = 0, cost_qas = 0;
+  float Ma = 0, dof_force = 0, cost = 0, cost_qas = 0, cost_prev = 3.0e38f;
+  int stall = 0;
   // one Newton iteration from the iterate / forces of the last evaluation; sets `done` when the solve is over
   SOLVE_CLK_DECL;
   auto newton_step = [&]() {
@@ -720,6 +721,13 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
       else if (stage == 1 && cost_qas < cost) { stage = 2; set_a(qas_d); }
       else {
         stage = 2;
+        // MuJoCo's "improvement < tolerance" test on the ACTUAL decrease: two consecutive iterations that did not lower the
+        // cost by one part in 10^7 (float32 resolution) mean the iterate sits at the float32 optimum; without this the rare
+        // solve whose predicted decrease stays above the tolerance (round-off in the cancelling terms) runs to the iteration cap
+        if (it > 0) {
+          if (cost > cost_prev - 1e-7f * fabsf(cost_prev)) { if (++stall >= 2) last = true; } else stall = 0;
+        }
+        cost_prev = cost;
         if (last || it >= NEWTON_MAXIT) done = true;
         else newton_step();
       }

