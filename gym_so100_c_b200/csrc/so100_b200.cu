@@ -79,8 +79,11 @@ struct DeviceGuard {
 // bulk of another's.  The heavy solve queue of each group drains on a second stream beside the light kernel.
 struct EnvGroup {
   int off = 0, n = 0;
-  cudaStream_t st = nullptr, side = nullptr, side2 = nullptr;   // st == nullptr: the caller's stream; side: K3m, side2: K3h
-  cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr, done = nullptr;
+  int index = 0, stage = 0;   // development builds (-DSO100_TRACE): trace record id = (index * 12 + stage) * 10 + kernel kind
+  // st == nullptr: the caller's stream.  side: medium queue a (beside the light grid), hull: K2b -> light queue b,
+  // side2: medium queue b + heavy queue (after K2b)
+  cudaStream_t st = nullptr, side = nullptr, side2 = nullptr, hull = nullptr;
+  cudaEvent_t fork = nullptr, fork2 = nullptr, join = nullptr, join2 = nullptr, join3 = nullptr, done = nullptr;
   cudaEvent_t t_done = nullptr;                         // timing-enabled twin of `done` (so100_group_times)
   cudaEvent_t staged = nullptr;                         // recorded after the group's first position stage of a step (stagger)
   int* ctl = nullptr;                                   // this group's queue control words
@@ -100,7 +103,7 @@ struct so100_ctx {
   uchar4* bpair = nullptr;
   unsigned long long* diag = nullptr;
   float* work = nullptr;      // [N, WORK_WORDS] phase-pipeline workspace (L2-resident)
-  int* qmem = nullptr;        // queue control words + heavy queue [N] + hull-pair queue [N * NHP] + medium queue [N]
+  int* qmem = nullptr;        // queue control words + heavy queue [N] + hull-pair queue [N * NHP] + medium queues a, b [N] each + light queue b [N]
   int* order = nullptr;       // solve order permutations: [2][N] for the env groups, [2][N] for the whole-batch group
   // so100_step replays a CUDA graph of its whole launch sequence (all groups, forks and joins): the host cost of a step
   // drops from several hundred launch / event calls to one cudaGraphLaunch.  Actions are staged into a fixed buffer so
@@ -131,6 +134,10 @@ struct so100_ctx {
   // Groups that start a step together stay in phase (all in the solve bulk, then all in its tail) and overlap little;
   // stagger = 1 starts every odd group only after its even neighbour has finished its first position stage, so that the
   // two are about a third of a substep apart for the rest of the step; 2 chains all groups that way.
+  int prio_low = 0, prio_mid = 0, prio_high = 0;   // kernel scheduling priorities (launch_p); all equal with SO100_PRIO=0
+  int dag = 0;       // SO100_DAG: schedule of a substep's kernels (launch_solve_stage); 0 = K2b before all solve classes (measured
+                     // fastest: the envs K2b completes are the ones with the long solves, so running K2b beside the light grid
+                     // (1, 2) only moves those solves behind a second kernel boundary: 3.3 vs 2.5 ms per step at 16384 envs)
   int stagger = 0;   // measured on B200: 1 and 2 are 1-9 % slower than 0 at 4096 / 16384 / 65536 envs (the groups drift apart on their own)
   int sm_count = 148;
   // Grid class of the queue kernels.  Their best grids depend on the workload: under random actions the queues hold a handful
@@ -154,11 +161,14 @@ struct so100_ctx {
   float *h_action = nullptr, *h_obs = nullptr, *h_ag = nullptr, *h_dg = nullptr, *h_rew = nullptr, *h_fin = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_succ = nullptr;
   DevTables tables() const { return DevTables{geom, pair, vert, bpair}; }
-  static constexpr int CTL_WORDS = 8 * 40;
+  static constexpr int CTL_WORDS = Q_STRIDE * 40;
+  static size_t qmem_words(size_t n) { return CTL_WORDS + (4 + NHP) * n; }
   Queues queues(const EnvGroup& G) const {
-    return Queues{G.ctl, qmem + CTL_WORDS + n + (size_t)G.off * NHP, qmem + CTL_WORDS + G.off,
-                  qmem + CTL_WORDS + (size_t)(1 + NHP) * n + G.off, G.order + (size_t)G.parity * n,
-                  G.order + (size_t)(1 - G.parity) * n, qstat, (1024 * 1024) / std::max(G.n, 1)};
+    int* base = qmem + CTL_WORDS;
+    const size_t N = (size_t)n;
+    return Queues{G.ctl, base + N + (size_t)G.off * NHP, base + G.off, base + (1 + NHP) * N + G.off, base + (2 + NHP) * N + G.off,
+                  base + (3 + NHP) * N + G.off, G.order + (size_t)G.parity * n, G.order + (size_t)(1 - G.parity) * n, qstat,
+                  (1024 * 1024) / std::max(G.n, 1), G.index < 8 ? (G.index * 12 + G.stage) * 10 : -1000000, dag != 0 ? 1 : 0};
   }
 };
 
@@ -406,6 +416,7 @@ static int configure_kernels(int device) {
   CUDA_OK(cudaFuncSetAttribute(phase_collide_box<LPE_K2A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<BoxS>(LPE_K2A)));
   CUDA_OK(cudaFuncSetAttribute(phase_collide_hull<LPE_K2B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<HullS>(LPE_K2B)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_light<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L)));
+  CUDA_OK(cudaFuncSetAttribute(phase_solve_light_queue<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NC>>(LPE_K3H)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H, NCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3H)));
   done = true;
@@ -421,57 +432,146 @@ static void mark(so100_ctx* h, cudaStream_t st, int cls, bool begin) {
   h->events.push_back({ev, begin ? cls : -1});
 }
 
-// K1: kinematics (+ dynamics), K2a/K2b: collision.  Leaves frames, M, qfrc_smooth and the contact list in the workspace.
-static void launch_position_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const float* action, int with_dyn, int reuse = 0) {
+// Kernel launch with a scheduling priority (cudaLaunchAttributePriority; also recorded in captured graph nodes).  The block
+// scheduler hands freed SM slots to the pending kernel of the highest priority: the queue kernels (a few blocks that gate a whole
+// env group's next substep) must not wait behind the thousands of pending blocks of the other groups' bulk kernels.
+template <class... KArgs, class... Args>
+static void launch_p(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, int prio, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributePriority;
+  at[0].val.priority = prio;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+static int k2b_grid(const so100_ctx* h, int n) {
+  return std::min(grid_of(n, LPE_K2B), std::max(h->k2b_blocks << h->grid_class, n / std::max(1, h->k2b_div >> h->grid_class)));
+}
+static int k3lb_grid(const so100_ctx* h, int n) {
+  // light queue b: ~14 % of a group's envs under random actions, two per block
+  return std::min(grid_of(n, LPE_K3L, TPB_K3L), std::max(h->sm_count, n / (8 >> h->grid_class)));
+}
+
+// K1: kinematics (+ dynamics), K2a: box collision stage.  Leaves frames, M, qfrc_smooth, the box contacts and the hull-pair queue.
+static void launch_kin_box(so100_ctx* h, EnvGroup& G, cudaStream_t st, const float* action, int with_dyn, int reuse = 0) {
   const int n = G.n;
   const DevTables T = h->tables();
   const Queues Q = h->queues(G);
   float* state = h->state + (size_t)G.off * STATE_WORDS;
   float* work = h->work + (size_t)G.off * WORK_WORDS;
   mark(h, st, CLS_KIN, true);
-  phase_kin_dyn<LPE_K1><<<grid_of(n, LPE_K1), BLOCK, smem_of<KinS>(LPE_K1), st>>>(state, work, action ? action + (size_t)G.off * 6 : nullptr, n, with_dyn, Q);
+  launch_p(phase_kin_dyn<LPE_K1>, grid_of(n, LPE_K1), BLOCK, smem_of<KinS>(LPE_K1), st, h->prio_mid, state, work, action ? action + (size_t)G.off * 6 : nullptr, n, with_dyn, Q);
   mark(h, st, CLS_KIN, false); mark(h, st, CLS_BOX, true);
-  phase_collide_box<LPE_K2A><<<grid_of(n, LPE_K2A), BLOCK, smem_of<BoxS>(LPE_K2A), st>>>(work, n, T, Q, reuse);
-  mark(h, st, CLS_BOX, false); mark(h, st, CLS_HULL, true);
-  phase_collide_hull<LPE_K2B><<<std::min(grid_of(n, LPE_K2B), std::max(h->k2b_blocks << h->grid_class, n / std::max(1, h->k2b_div >> h->grid_class))), BLOCK, smem_of<HullS>(LPE_K2B), st>>>(work, T, Q);
+  launch_p(phase_collide_box<LPE_K2A>, grid_of(n, LPE_K2A), BLOCK, smem_of<BoxS>(LPE_K2A), st, h->prio_mid, work, n, T, Q, reuse);
+  mark(h, st, CLS_BOX, false);
+}
+// K2b: GJK/EPA over the hull-pair queue
+static void launch_hull(so100_ctx* h, EnvGroup& G, cudaStream_t st) {
+  float* work = h->work + (size_t)G.off * WORK_WORDS;
+  mark(h, st, CLS_HULL, true);
+  launch_p(phase_collide_hull<LPE_K2B>, k2b_grid(h, G.n), BLOCK, smem_of<HullS>(LPE_K2B), st, h->prio_high, work, h->tables(), h->queues(G));
   mark(h, st, CLS_HULL, false);
 }
+// the whole position stage on one stream (trailing mj_step1, so100_forward)
+static void launch_position_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const float* action, int with_dyn, int reuse = 0) {
+  launch_kin_box(h, G, st, action, with_dyn, reuse);
+  launch_hull(h, G, st);
+}
 
-// K3l/K3h: constraint solve (+ Euler unless O.forward).  The heavy queue (a handful of envs with long serial Newton
-// runs) is drained on a side stream beside the light kernel; both rejoin `st`.
-static void launch_solve_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const SolveOut& O) {
+// One substep after K1 / K2a have been enqueued on `st`: K2b and the solve classes (+ Euler unless O.forward).
+//   st     K3l-a (regular light grid: envs without hull pairs)                       |
+//   side   K3m-a (medium queue a: arm-cube contact known after K2a)                  |  all rejoin `st`
+//   hull   K2b -> K3l-b (light queue b)                                              |
+//   side2  after K2b: K3m-b (medium queue b), K3h (heavy queue)                      |
+static void launch_solve_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const SolveOut& O, bool hull_done = false) {
   const int n = G.n;
   const DevTables T = h->tables();
   const Queues Q = h->queues(G);
   if (!O.forward) G.parity ^= 1;     // this launch writes the permutation the next one reads
   float* state = h->state + (size_t)G.off * STATE_WORDS;
   const float* work = h->work + (size_t)G.off * WORK_WORDS;
-  cudaEventRecord(G.fork, st);
-  if (h->timing) {
-    // timing mode: one stream, so that the event pair brackets both queue kernels
+  const int med_grid = std::min(grid_of(n, LPE_K3H), h->k3m_blocks << h->grid_class), heavy_grid = std::min(grid_of(n, LPE_K3H), h->k3h_blocks);
+  auto medium = [&](cudaStream_t s_, int which) {
+    launch_p(phase_solve_heavy<LPE_K3H, NCL>, med_grid, BLOCK, smem_of<SolS<NCL>>(LPE_K3H), s_, h->prio_high, state, work, T, Q, O, which);
+  };
+  auto heavy = [&](cudaStream_t s_) {
+    launch_p(phase_solve_heavy<LPE_K3H, NC>, heavy_grid, BLOCK, smem_of<SolS<NC>>(LPE_K3H), s_, h->prio_high, state, work, T, Q, O, 0);
+  };
+  auto light_a = [&](cudaStream_t s_) {
+    launch_p(phase_solve_light<LPE_K3L>, grid_of(n, LPE_K3L, TPB_K3L), TPB_K3L, smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L), s_, h->prio_low, state, work, n, T, Q, O);
+  };
+  auto light_b = [&](cudaStream_t s_) {
+    launch_p(phase_solve_light_queue<LPE_K3L>, k3lb_grid(h, n), TPB_K3L, smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L), s_, h->prio_high, state, work, T, Q, O);
+  };
+  const bool split = h->dag != 0;
+  if (h->timing || hull_done) {
+    // timing mode (one stream, so that every event pair brackets its kernels alone) and so100_forward (K2b already ran)
+    if (!hull_done) launch_hull(h, G, st);
     mark(h, st, CLS_HEAVY, true);
-    phase_solve_heavy<LPE_K3H, NCL><<<std::min(grid_of(n, LPE_K3H), h->k3m_blocks << h->grid_class), BLOCK, smem_of<SolS<NCL>>(LPE_K3H), st>>>(state, work, T, Q, O);
-    phase_solve_heavy<LPE_K3H, NC><<<std::min(grid_of(n, LPE_K3H), h->k3h_blocks), BLOCK, smem_of<SolS<NC>>(LPE_K3H), st>>>(state, work, T, Q, O);
+    medium(st, 0);
+    if (split) medium(st, 1);
+    heavy(st);
     mark(h, st, CLS_HEAVY, false);
-  } else {
+    mark(h, st, CLS_SOLVE, true);
+    light_a(st);
+    if (split) light_b(st);
+    mark(h, st, CLS_SOLVE, false);
+    return;
+  }
+  if (h->dag == 0) {
+    // K2b on the chain, then the three solve classes side by side
+    launch_hull(h, G, st);
+    cudaEventRecord(G.fork, st);
     cudaStreamWaitEvent(G.side, G.fork, 0);
     cudaStreamWaitEvent(G.side2, G.fork, 0);
-    phase_solve_heavy<LPE_K3H, NCL><<<std::min(grid_of(n, LPE_K3H), h->k3m_blocks << h->grid_class), BLOCK, smem_of<SolS<NCL>>(LPE_K3H), G.side>>>(state, work, T, Q, O);
-    phase_solve_heavy<LPE_K3H, NC><<<std::min(grid_of(n, LPE_K3H), h->k3h_blocks), BLOCK, smem_of<SolS<NC>>(LPE_K3H), G.side2>>>(state, work, T, Q, O);
+    medium(G.side, 0);
+    heavy(G.side2);
     cudaEventRecord(G.join, G.side);
     cudaEventRecord(G.join2, G.side2);
-  }
-  mark(h, st, CLS_SOLVE, true);
-  phase_solve_light<LPE_K3L><<<grid_of(n, LPE_K3L, TPB_K3L), TPB_K3L, smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L), st>>>(state, work, n, T, Q, O);
-  mark(h, st, CLS_SOLVE, false);
-  if (!h->timing) {
+    light_a(st);
     cudaStreamWaitEvent(st, G.join, 0);
     cudaStreamWaitEvent(st, G.join2, 0);
+    return;
   }
+  if (h->dag == 2) {
+    // only K2b beside the light grid; every queue kernel after K2b
+    cudaEventRecord(G.fork, st);
+    cudaStreamWaitEvent(G.hull, G.fork, 0);
+    launch_hull(h, G, G.hull);
+    cudaEventRecord(G.fork2, G.hull);
+    light_b(G.hull);
+    cudaEventRecord(G.join3, G.hull);
+    cudaStreamWaitEvent(G.side2, G.fork2, 0);
+    medium(G.side2, 0); medium(G.side2, 1); heavy(G.side2);
+    cudaEventRecord(G.join2, G.side2);
+    light_a(st);
+    cudaStreamWaitEvent(st, G.join2, 0);
+    cudaStreamWaitEvent(st, G.join3, 0);
+    return;
+  }
+  cudaEventRecord(G.fork, st);
+  cudaStreamWaitEvent(G.side, G.fork, 0);
+  cudaStreamWaitEvent(G.hull, G.fork, 0);
+  medium(G.side, 0);
+  cudaEventRecord(G.join, G.side);
+  launch_hull(h, G, G.hull);
+  cudaEventRecord(G.fork2, G.hull);
+  light_b(G.hull);
+  cudaEventRecord(G.join3, G.hull);
+  cudaStreamWaitEvent(G.side2, G.fork2, 0);
+  medium(G.side2, 1);
+  heavy(G.side2);
+  cudaEventRecord(G.join2, G.side2);
+  light_a(st);
+  cudaStreamWaitEvent(st, G.join, 0);
+  cudaStreamWaitEvent(st, G.join2, 0);
+  cudaStreamWaitEvent(st, G.join3, 0);
 }
 
 static int make_group(so100_ctx* h, EnvGroup& G, int off, int n, int index, bool own_stream) {
-  G.off = off; G.n = n; G.ctl = h->qmem + 8 * index;
+  G.off = off; G.n = n; G.ctl = h->qmem + Q_STRIDE * index; G.index = index;
   G.order = h->order + (own_stream ? 0 : 2 * (size_t)h->n) + off;
   {
     std::vector<int> ident(n);
@@ -482,7 +582,10 @@ static int make_group(so100_ctx* h, EnvGroup& G, int off, int n, int index, bool
   if (own_stream) CUDA_OK(cudaStreamCreateWithFlags(&G.st, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&G.side, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&G.side2, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&G.hull, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&G.join2, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&G.join3, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&G.fork2, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.fork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.join, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
@@ -494,7 +597,10 @@ static void free_group(EnvGroup& G) {
   if (G.st) cudaStreamDestroy(G.st);
   if (G.side) cudaStreamDestroy(G.side);
   if (G.side2) cudaStreamDestroy(G.side2);
+  if (G.hull) cudaStreamDestroy(G.hull);
   if (G.join2) cudaEventDestroy(G.join2);
+  if (G.join3) cudaEventDestroy(G.join3);
+  if (G.fork2) cudaEventDestroy(G.fork2);
   if (G.fork) cudaEventDestroy(G.fork);
   if (G.join) cudaEventDestroy(G.join);
   if (G.done) cudaEventDestroy(G.done);
@@ -532,8 +638,8 @@ static int create_device_side(so100_ctx* h, const DevModel& dm, const std::vecto
   CUDA_OK(cudaMalloc(&h->diag, SO100_NDIAG * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&h->work, (size_t)num_envs * WORK_WORDS * sizeof(float)));
   CUDA_OK(cudaMemset(h->work, 0, (size_t)num_envs * WORK_WORDS * sizeof(float)));
-  CUDA_OK(cudaMalloc(&h->qmem, (so100_ctx::CTL_WORDS + (2 + NHP) * (size_t)num_envs) * sizeof(int)));
-  CUDA_OK(cudaMemset(h->qmem, 0, (so100_ctx::CTL_WORDS + (2 + NHP) * (size_t)num_envs) * sizeof(int)));
+  CUDA_OK(cudaMalloc(&h->qmem, so100_ctx::qmem_words(num_envs) * sizeof(int)));
+  CUDA_OK(cudaMemset(h->qmem, 0, so100_ctx::qmem_words(num_envs) * sizeof(int)));
   CUDA_OK(cudaMalloc(&h->order, 4 * (size_t)num_envs * sizeof(int)));
   CUDA_OK(cudaMalloc(&h->qstat, 2 * sizeof(int)));
   CUDA_OK(cudaMemset(h->qstat, 0, 2 * sizeof(int)));
@@ -548,6 +654,15 @@ static int create_device_side(so100_ctx* h, const DevModel& dm, const std::vecto
   CUDA_OK(cudaEventCreate(&h->t_start));
   if (const char* e = getenv("SO100_GROUP_TIMES")) h->group_times = atoi(e) != 0;
   if (const char* e = getenv("SO100_STAGGER")) h->stagger = atoi(e);
+  if (const char* e = getenv("SO100_DAG")) h->dag = atoi(e);
+  {
+    int least = 0, greatest = 0, mode = 1;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));     // numerically lower = higher priority
+    if (const char* e = getenv("SO100_PRIO")) mode = atoi(e);
+    if (mode == 1) { h->prio_low = least; h->prio_high = greatest; h->prio_mid = (least + greatest) / 2; }
+    else if (mode == 2) { h->prio_low = least; h->prio_high = greatest; h->prio_mid = greatest; }
+    else if (mode == 3) { h->prio_low = least; h->prio_high = greatest; h->prio_mid = least; }
+  }
   CUDA_OK(cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking));
   CUDA_OK(cudaMalloc(&h->act_stage, (size_t)num_envs * 6 * sizeof(float)));
   if (const char* e = getenv("SO100_GRAPH")) h->use_graph = atoi(e) != 0;
@@ -680,7 +795,8 @@ int so100_num_envs(so100_handle h) { return h ? h->n : SO100_ERR_ARG; }
 
 int so100_launches_per_step(so100_handle h) {
   if (!h) return SO100_ERR_ARG;
-  const int per_group = h->nsub * 6 + 3 + 1;   // nsub x (K1, K2a, K2b, K3l, K3m, K3h) + trailing (K1, K2a, K2b) + K4
+  // nsub x (K1, K2a, K2b, K3l, K3m, K3h [+ K3l-b, K3m-b with the a / b work classes]) + trailing (K1, K2a, K2b) + K4
+  const int per_group = h->nsub * (h->dag != 0 ? 8 : 6) + 3 + 1;
   return per_group * (int)std::max<size_t>(h->groups.size(), 1);
 }
 
@@ -711,13 +827,16 @@ static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream, i
   for_each_group(h, stream, true, [&](EnvGroup& G, cudaStream_t st) {
     const SolveOut O{nullptr, nullptr, 0};
     for (int s = 0; s < h->nsub; s++) {
-      launch_position_stage(h, G, st, s == 0 ? action : nullptr, 1, s == 0 ? reuse : 0);
+      G.stage = s;
+      launch_kin_box(h, G, st, s == 0 ? action : nullptr, 1, s == 0 ? reuse : 0);
       if (s == 0) cudaEventRecord(G.staged, st);
       launch_solve_stage(h, G, st, O);
     }
     // trailing mj_step1 (dm_control's legacy step): positions + contacts of the new state, then the task layer
+    G.stage = std::min(h->nsub, 11);
     launch_position_stage(h, G, st, h->nsub == 0 ? action : nullptr, 0);
     StepArgs B = A;
+    B.trace = h->queues(G).trace;
     const size_t o = (size_t)G.off;
     B.state += o * STATE_WORDS; B.n = G.n; B.env_offset += G.off;
     if (B.obs) B.obs += o * 15;
@@ -731,7 +850,7 @@ static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream, i
     if (B.ep_return) B.ep_return += o;
     if (B.ep_length) B.ep_length += o;
     mark(h, st, CLS_TASK, true);
-    phase_task<LPE_K4><<<grid_of(G.n, LPE_K4), BLOCK, smem_of<TaskS>(LPE_K4), st>>>(B, h->work + o * WORK_WORDS, h->tables());
+    launch_p(phase_task<LPE_K4>, grid_of(G.n, LPE_K4), BLOCK, smem_of<TaskS>(LPE_K4), st, h->prio_mid, B, h->work + o * WORK_WORDS, h->tables());
     mark(h, st, CLS_TASK, false);
     if (ho) {
       auto out = [&](void* dst, const void* src, size_t per_env) {
@@ -867,7 +986,7 @@ static int step_impl(so100_handle h, const float* action, int autoreset, float* 
       const cudaError_t launch_err = cudaGetLastError();
       cudaError_t ce = cudaStreamEndCapture(h->cap, &graph);     // always closes the capture, also after a failed launch
       if (ce == cudaSuccess && launch_err != cudaSuccess) ce = launch_err;
-      if (ce == cudaSuccess) ce = cudaGraphInstantiate(&ge, graph, 0);
+      if (ce == cudaSuccess) ce = cudaGraphInstantiateWithFlags(&ge, graph, cudaGraphInstantiateFlagUseNodePriority);   // per-node priorities of launch_p
       if (graph) cudaGraphDestroy(graph);
       if (ce != cudaSuccess) {
         h->grid_class = chosen;
@@ -1006,7 +1125,7 @@ int so100_substeps(so100_handle h, int nsub, void* stream) {
   for_each_group(h, (cudaStream_t)stream, true, [&](EnvGroup& G, cudaStream_t st) {
     const SolveOut O{nullptr, nullptr, 0};
     for (int s = 0; s < nsub; s++) {
-      launch_position_stage(h, G, st, nullptr, 1);
+      launch_kin_box(h, G, st, nullptr, 1);
       if (s == 0) cudaEventRecord(G.staged, st);
       launch_solve_stage(h, G, st, O);
     }
@@ -1020,13 +1139,28 @@ int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom,
   DeviceGuard guard(h->device);
   h->work_fresh = false;
   cudaStream_t st = (cudaStream_t)stream;
-  launch_position_stage(h, h->whole, st, nullptr, 1);
+  // the whole batch as one group on the caller's stream, every kernel in sequence: K1, K2a, K2b, the contact export, then the
+  // solve classes in forward mode (nothing is integrated)
+  launch_kin_box(h, h->whole, st, nullptr, 1);
+  launch_hull(h, h->whole, st);
   const int threads = h->n * 32;
   export_forward_kernel<<<(threads + 255) / 256, 256, 0, st>>>(h->work, h->n, ncon, con_geom, con_data, sites, h->tables());
-  launch_solve_stage(h, h->whole, st, SolveOut{qacc, con_data, 1});
+  launch_solve_stage(h, h->whole, st, SolveOut{qacc, con_data, 1}, true);
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
+
+#ifdef SO100_TRACE
+// development build: copy out (host [TRACE_RECORDS][2] uint64 ns) and re-arm the kernel trace
+int so100_trace_read(unsigned long long* out) {
+  CUDA_OK(cudaDeviceSynchronize());
+  if (out) CUDA_OK(cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 2 * TRACE_RECORDS));
+  std::vector<unsigned long long> init(2 * TRACE_RECORDS);
+  for (int i = 0; i < TRACE_RECORDS; i++) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+  CUDA_OK(cudaMemcpyToSymbol(g_trace, init.data(), sizeof(unsigned long long) * 2 * TRACE_RECORDS));
+  return TRACE_RECORDS;
+}
+#endif
 
 #ifdef SO100_HULL_CLOCK
 // development build: copy out and clear the GJK/EPA item statistics; returns the number of items recorded

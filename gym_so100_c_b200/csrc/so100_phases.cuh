@@ -32,6 +32,7 @@ namespace so100 {
 template <unsigned LPE>
 __global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, const float* action, int n, int with_dyn, Queues Q) {
   SO100_TILE_PROLOGUE(LPE, 128, KinS);
+  SO100_TRACE_SCOPE(Q.trace + TR_KIN);
   if (blockIdx.x == 0 && threadIdx.x < Q_WORDS) Q.ctl[threadIdx.x] = 0;
   const int env = blockIdx.x * EPB + t.meta_group_rank();
   if (env >= n) return;
@@ -68,13 +69,14 @@ __global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, 
 // heavy queue, which K1 has just re-armed
 template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_box(float* work, int n, DevTables T, Queues Q, int reuse) {
   SO100_TILE_PROLOGUE(LPE, 128, BoxS);
+  SO100_TRACE_SCOPE(Q.trace + TR_BOX);
   const int env = blockIdx.x * EPB + t.meta_group_rank();
   if (env >= n) return;
   float* w = work + (size_t)env * WORK_WORDS;
   if (reuse) {
     const int4 hdr = *reinterpret_cast<const int4*>(w + W_HDR);
     if (hdr.w == 0) {
-      if (lane == 0) Q.route(env, hdr.x, (hdr.z & HDR_COUPLED) != 0);
+      if (lane == 0) Q.route(env, hdr.x, (hdr.z & HDR_COUPLED) != 0, hdr.y > 0);
       return;
     }
   }
@@ -89,13 +91,17 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_box
     base = t.shfl(base, 0);
     if (lane < nsurv) Q.hull[base + lane] = env * NHP + lane;
   } else if (lane == 0) {
-    Q.route(env, ncon, coupled);
+    Q.route(env, ncon, coupled, false);
   }
 }
 
 // K2b: persistent tiles drain the hull-pair queue
 template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_hull(float* work, DevTables T, Queues Q) {
   SO100_TILE_PROLOGUE(LPE, 128, HullS);
+  SO100_TRACE_SCOPE(Q.trace + TR_HULL);
+#ifdef SO100_DEV_SKIP_HULL
+  return;      // timing experiment only (wrong physics): what the step costs without any GJK/EPA work
+#endif
   const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_HULL_COUNT]);
   if (blockIdx.x == 0 && threadIdx.x == 0) Q.note(1, count);
   for (;;) {
@@ -109,7 +115,7 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_hul
     t.sync();
     bool coupled = false;
     const int ncon = collide_hull_item(t, S, w, item % NHP, T, &coupled);
-    if (lane == 0 && ncon >= 0) Q.route(env, ncon, coupled);
+    if (lane == 0 && ncon >= 0) Q.route(env, ncon, coupled, true);
     t.sync();
   }
 }
@@ -154,15 +160,19 @@ __device__ int solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w, 
 template <unsigned LPE>
 __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TPB_K3L) phase_solve_light(float* state, const float* work, int n, DevTables T, Queues Q, SolveOut O) {
   SO100_TILE_PROLOGUE(LPE, SO100_TPB_K3L, SolS<NCL>);
+  SO100_TRACE_SCOPE(Q.trace + TR_LIGHT_A);
   const int slot = blockIdx.x * EPB + t.meta_group_rank();
   const bool live = slot < n;
   if (LPE == 32 && !live) return;            // one tile per warp: nobody to vote with
   const int env = Q.order_in[live ? slot : n - 1];
   const float* w = work + (size_t)env * WORK_WORDS;
   const int4 hdr = *reinterpret_cast<const int4*>(w + W_HDR);
+  // hdr.y = hull pairs of the env (written by K2a only; K2b, which may be running beside this kernel, never touches it): such
+  // envs are solved by the queue kernel below once K2b has completed their contact list.  hdr.x / hdr.z of the others are final.
+  const bool hull_env = Q.split && hdr.y > 0;
   const int ncon_raw = (hdr.z & HDR_COUPLED) ? NC + 2 : hdr.x;      // arm-cube contacts: heavy kernel (dense Hessian)
-  const bool mine = live && ncon_raw <= NCL;
-  int iters = 1000;                          // heavy envs count as slow
+  const bool mine = live && !hull_env && ncon_raw <= NCL;
+  int iters = hull_env ? 0 : 1000;           // heavy / medium envs count as slow; hull envs are not this kernel's business
 #ifdef SO100_SOLVE_CLOCK
   unsigned long long t0_;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0_));
@@ -181,14 +191,35 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
     float* rec_ = state + (size_t)env * STATE_WORDS;
     rec_[57] = __int_as_float((int)(t1_ - t0_));
     rec_[58] = __int_as_float(iters);
-    rec_[59] = __int_as_float(ncon_raw | (S->coupled << 8));
+    rec_[59] = __int_as_float(ncon_raw | (S->coupled << 8) | (S->clk2[3] << 12));     // bits 12..: line-search iterations of the solve
     for (int k_ = 0; k_ < 4; k_++) rec_[60 + k_] = __int_as_float(S->clk[k_]);
-    rec_[60] = __int_as_float(S->clk2[0]); rec_[61] = __int_as_float(S->clk2[1]); rec_[63] = __int_as_float(S->clk2[2]);   // dense split replaces eval/grad/ls
   }
 #endif
   if (!O.forward && live && lane == 0) {
     const int pos = iters >= 3 ? atomicAdd(&Q.ctl[Q_SLOW], 1) : n - 1 - atomicAdd(&Q.ctl[Q_FAST], 1);
     Q.order_out[pos] = env;
+  }
+}
+
+// K3l-b: the light-class envs whose contact list K2b completed (light queue b), same solver code and tile width as the regular
+// grid above.  Persistent warps; the tiles of a warp pull their items independently but enter the solver together (its loop
+// votes warp-wide), a tile that found the queue empty as inactive.
+template <unsigned LPE>
+__global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TPB_K3L) phase_solve_light_queue(float* state, const float* work, DevTables T, Queues Q, SolveOut O) {
+  SO100_TILE_PROLOGUE(LPE, SO100_TPB_K3L, SolS<NCL>);
+  SO100_TRACE_SCOPE(Q.trace + TR_LIGHT_B);
+  const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_LB_COUNT]);
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&Q.ctl[Q_LB_NEXT], 1);
+    i = t.shfl(i, 0);
+    const bool have = i < count;
+    if (!warp_any<LPE>(t, have)) break;
+    const int env = Q.light_b[have ? i : 0];
+    const float* w = work + (size_t)env * WORK_WORDS;
+    if (LPE < 32) solve_env<false>(t, S, state + (size_t)env * STATE_WORDS, w, env, min(__float_as_int(w[W_HDR]), NCL), T, O, have);
+    else if (have) solve_env<false>(t, S, state + (size_t)env * STATE_WORDS, w, env, __float_as_int(w[W_HDR]), T, O);
+    t.sync();
   }
 }
 
@@ -203,16 +234,19 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
 #ifndef SO100_K3M_MINB
 #define SO100_K3M_MINB 3      // the same for the medium instantiation
 #endif
+// `which` (medium instantiation only): 0 = medium queue a (complete after K2a), 1 = medium queue b (complete after K2b)
 template <unsigned LPE, int NCAP>
-__global__ void __launch_bounds__(128, NCAP == NCL ? SO100_K3M_MINB : SO100_K3H_MINB) phase_solve_heavy(float* state, const float* work, DevTables T, Queues Q, SolveOut O) {
+__global__ void __launch_bounds__(128, NCAP == NCL ? SO100_K3M_MINB : SO100_K3H_MINB) phase_solve_heavy(float* state, const float* work, DevTables T, Queues Q, SolveOut O, int which) {
   SO100_TILE_PROLOGUE(LPE, 128, SolS<NCAP>);
   constexpr bool MED = NCAP == NCL;
-  const int* queue = MED ? Q.medium : Q.heavy;
-  const int count = *reinterpret_cast<volatile int*>(&Q.ctl[MED ? Q_MED_COUNT : Q_HEAVY_COUNT]);
+  SO100_TRACE_SCOPE(Q.trace + (MED ? (which ? TR_MED_B : TR_MED_A) : TR_HEAVY));
+  const int* queue = MED ? (which ? Q.medium_b : Q.medium_a) : Q.heavy;
+  const int qc = MED ? (which ? Q_MEDB_COUNT : Q_MEDA_COUNT) : Q_HEAVY_COUNT;
+  const int count = *reinterpret_cast<volatile int*>(&Q.ctl[qc]);
   if (MED && blockIdx.x == 0 && threadIdx.x == 0) Q.note(0, count);
   for (;;) {
     int i = 0;
-    if (lane == 0) i = atomicAdd(&Q.ctl[MED ? Q_MED_NEXT : Q_HEAVY_NEXT], 1);
+    if (lane == 0) i = atomicAdd(&Q.ctl[qc + 1], 1);
     i = t.shfl(i, 0);
     if (i >= count) break;
     const int env = queue[i];
@@ -227,6 +261,7 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_task(StepAr
   SO100_TILE_PROLOGUE(LPE, 128, TaskS);
   const int env = blockIdx.x * EPB + t.meta_group_rank();
   if (env >= A.n) return;
+  SO100_TRACE_SCOPE(A.trace + TR_TASK);
   float* w = work + (size_t)env * WORK_WORDS;
   float* rec = A.state + (size_t)env * STATE_WORDS;
   copy_vec<LPE, STATE_WORDS>(t, S->st, rec);

@@ -49,13 +49,49 @@ static_assert(WORK_WORDS % 8 == 0 && W_HDR % 4 == 0 && W_CON % 4 == 0, "workspac
 static_assert(NHP <= 16, "hull pair list is 4 words");
 
 // queue control words (device ints)
-enum { Q_HULL_COUNT = 0, Q_HULL_NEXT = 1, Q_HEAVY_COUNT = 2, Q_HEAVY_NEXT = 3, Q_SLOW = 4, Q_FAST = 5, Q_MED_COUNT = 6, Q_MED_NEXT = 7, Q_WORDS = 8 };
+enum { Q_HULL_COUNT = 0, Q_HULL_NEXT = 1, Q_HEAVY_COUNT = 2, Q_HEAVY_NEXT = 3, Q_SLOW = 4, Q_FAST = 5, Q_MEDA_COUNT = 6, Q_MEDA_NEXT = 7,
+       Q_MEDB_COUNT = 8, Q_MEDB_NEXT = 9, Q_LB_COUNT = 10, Q_LB_NEXT = 11, Q_WORDS = 12, Q_STRIDE = 16 };
+
+// Work classes of a substep.  The collision stage ends in two steps: the box stage (K2a) completes every env without a hull
+// pair, the GJK/EPA queue kernel (K2b) the other ~14 %.  Everything that only needs K2a starts right after it and runs BESIDE
+// K2b (the "a" classes: the regular grid of the light solve kernel, the medium queue a); the envs K2b completes are solved
+// after it (the "b" classes: light queue b, medium queue b) together with the rare heavy class.  K2b's latency (its slowest
+// EPA item, 35-55 us) is thereby off the critical path of a substep whenever the a-side is the longer one.
+#ifdef SO100_TRACE
+// development build: first-warp-start / last-warp-end (%globaltimer, ns) of every kernel launch of a step, keyed by
+// (env group, stage, kernel kind); read with so100_trace_read (tools/gpu_trace.py draws the per-group timeline)
+constexpr int TRACE_RECORDS = 8 * 12 * 10;
+__device__ unsigned long long g_trace[TRACE_RECORDS][2];
+struct TraceScope {
+  int id;
+  __device__ __forceinline__ explicit TraceScope(int id_) : id(id_) {
+    if ((threadIdx.x & 31) == 0 && id >= 0 && id < TRACE_RECORDS) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      atomicMin(&g_trace[id][0], t);
+    }
+  }
+  __device__ __forceinline__ ~TraceScope() {
+    if ((threadIdx.x & 31) == 0 && id >= 0 && id < TRACE_RECORDS) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      atomicMax(&g_trace[id][1], t);
+    }
+  }
+};
+#define SO100_TRACE_SCOPE(id_) TraceScope trace_scope_(id_)
+#else
+#define SO100_TRACE_SCOPE(id_) do { } while (0)
+#endif
+enum { TR_KIN = 0, TR_BOX = 1, TR_HULL = 2, TR_LIGHT_A = 3, TR_LIGHT_B = 4, TR_MED_A = 5, TR_MED_B = 6, TR_HEAVY = 7, TR_TASK = 8 };
 
 struct Queues {
   int* ctl;      // [Q_WORDS]
   int* hull;     // [N * NHP] hull pairs for GJK/EPA this substep, one item = env * NHP + slot
-  int* heavy;    // [N] envs with more than NCL contacts this substep
-  int* medium;   // [N] envs with at most NCL contacts, one of which couples the arm and the cube (dense Hessian)
+  int* heavy;    // [N] envs with more than NCL contacts this substep (solved after K2b)
+  int* medium_a; // [N] envs with at most NCL contacts, one of which couples the arm and the cube (dense Hessian); complete after K2a
+  int* medium_b; // [N] the same, complete after K2b
+  int* light_b;  // [N] envs of the light class (<= NCL contacts, no arm-cube contact) that had hull pairs: complete after K2b
   // Longest-first order of the light solve kernel: block b solves env order_in[b].  Envs that needed >= 3 Newton
   // iterations (or went to the heavy kernel) are written to the front of order_out, the rest to the back, so that the
   // next substep starts its likely stragglers first (the iteration count of an env is strongly correlated in time).
@@ -64,12 +100,21 @@ struct Queues {
   int* stat;     // [2] largest medium-queue / hull-pair-queue length (relative: count * 1024 / group size) seen since the host last
                  // cleared it; the host sizes the queue kernels' grids for the next step from it (so100_b200.cu: grid class)
   int scale;     // 1024 * 1024 / group size
+  int trace;     // development builds (-DSO100_TRACE): base record id of this (group, stage)
+  int split;     // 1: a / b work classes as described above; 0: K2b runs before every solve kernel, so there are no b classes
+                 // (every env is solved by the regular light grid or the medium a / heavy queue)
   __device__ __forceinline__ void note(int which, int count) const { atomicMax(&stat[which], (count * scale) >> 10); }
-  // work class of an env whose collision stage is complete: > NCL contacts (or list overflow) -> heavy queue; an arm-cube
-  // contact among <= NCL -> medium queue; everything else is solved by the regular grid of the light kernel
-  __device__ __forceinline__ void route(int env, int ncon, bool coupled) const {
+  // work class of an env whose collision stage is complete (`after_hull`: completed by K2b, or had hull pairs when the
+  // contact lists of the previous step's trailing stage are reused): > NCL contacts (or list overflow) -> heavy queue; an
+  // arm-cube contact among <= NCL -> medium queue a / b; light envs completed by K2a are solved by the regular grid of the
+  // light kernel, those completed by K2b go to light queue b
+  __device__ __forceinline__ void route(int env, int ncon, bool coupled, bool after_hull) const {
+    after_hull = after_hull && split;
     if (ncon > NCL) heavy[atomicAdd(&ctl[Q_HEAVY_COUNT], 1)] = env;
-    else if (coupled) medium[atomicAdd(&ctl[Q_MED_COUNT], 1)] = env;
+    else if (coupled) {
+      if (after_hull) medium_b[atomicAdd(&ctl[Q_MEDB_COUNT], 1)] = env;
+      else medium_a[atomicAdd(&ctl[Q_MEDA_COUNT], 1)] = env;
+    } else if (after_hull) light_b[atomicAdd(&ctl[Q_LB_COUNT], 1)] = env;
   }
 };
 

@@ -689,6 +689,9 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
         }
       }
       tsum2(t, e1, e2);
+#ifdef SO100_SOLVE_CLOCK
+      if (lane == 0) S->clk2[3] += 1;
+#endif
       d1 = e1 + pg + alpha * pMp;
       d2 = e2 + pMp;
       if (fabsf(d1) <= SO100_LS_TOL * d10) break;

@@ -14,6 +14,7 @@ struct StepArgs {
   float* ep_return;        // [N] or null: return of the episode an env has just finished (untouched otherwise)
   int32_t* ep_length;      // [N] or null: its length in env steps
   int n, autoreset, task;
+  int trace;               // development builds (-DSO100_TRACE): base record id
   uint32_t seed_lo, seed_hi;
   long long env_offset;
 };

@@ -26,17 +26,17 @@ for _ in range(20):
         st[:, 0].mean(), (st[:, 1] >= 8).sum()))
 a = np.concatenate(rows)
 ok = a[:, 1] < 1000
+ncon = a[:, 2] & 255
+ls = a[:, 2] >> 12
 for it in sorted(set(a[ok, 1].tolist())):
     m = ok & (a[:, 1] == it)
-    for cp in (0, 1):
-        mm = m & ((a[:, 2] >> 8) == cp)
-        if mm.sum():
-            print(f"its {it:3d} coupled {cp}: n {mm.sum():6d}  ns mean {a[mm, 0].mean():9.0f}  min {a[mm, 0].min():8d}  max {a[mm, 0].max():8d}")
-
-print("cycle split of multi-iteration solves (per Newton iteration): eval+driver, gradient, Hessian+factor, line search")
-for cp in (0, 1):
-    m = ok & ((a[:, 2] >> 8) == cp) & (a[:, 1] >= 6)
     if m.sum():
-        per_it = a[m, 3:7] / a[m, 1:2]
-        print(f"coupled {cp}: n {m.sum()}  cycles/iteration", np.round(per_it.mean(axis=0)).astype(int).tolist(),
-              " ns/iteration %.0f" % (a[m, 0] / a[m, 1]).mean())
+        print(f"its {it:3d}: n {m.sum():6d}  ns mean {a[m, 0].mean():9.0f}  min {a[m, 0].min():8d}  max {a[m, 0].max():8d}  ls its/newton it {ls[m].mean() / max(it, 1):5.2f}  ncon mean {ncon[m].mean():4.1f}")
+print("cycle split of multi-iteration light solves (per Newton iteration): eval+driver, gradient, Hessian+factor, line search")
+m = ok & (a[:, 1] >= 6)
+if m.sum():
+    per_it = a[m, 3:7] / a[m, 1:2]
+    print(f"n {m.sum()}  cycles/iteration", np.round(per_it.mean(axis=0)).astype(int).tolist(), " ns/iteration %.0f" % (a[m, 0] / a[m, 1]).mean(),
+          " ls iterations per Newton iteration %.2f (max %.1f)" % ((ls[m] / a[m, 1]).mean(), (ls[m] / a[m, 1]).max()))
+m = ok & (a[:, 1] == 1)
+print("single-iteration solves: cycles", np.round(a[m, 3:7].mean(axis=0)).astype(int).tolist(), " ls its %.2f" % ls[m].mean())
