@@ -82,6 +82,9 @@ struct EnvGroup {
   int index = 0, stage = 0;   // development builds (-DSO100_TRACE): trace record id = (index * 12 + stage) * 10 + kernel kind
   // st == nullptr: the caller's stream.  side: medium queue a (beside the light grid), hull: K2b -> light queue b,
   // side2: medium queue b + heavy queue (after K2b)
+  static constexpr int NSLOW = 12;
+  cudaStream_t slow[NSLOW] = {nullptr};                 // slow-lane kernel of stage s runs on slow[s % NSLOW], joined before the task kernel
+  cudaEvent_t slow_fork[NSLOW] = {nullptr}, slow_done[NSLOW] = {nullptr};
   cudaStream_t st = nullptr, side = nullptr, side2 = nullptr, hull = nullptr;
   cudaEvent_t fork = nullptr, fork2 = nullptr, join = nullptr, join2 = nullptr, join3 = nullptr, done = nullptr;
   cudaEvent_t t_done = nullptr;                         // timing-enabled twin of `done` (so100_group_times)
@@ -134,6 +137,12 @@ struct so100_ctx {
   // Groups that start a step together stay in phase (all in the solve bulk, then all in its tail) and overlap little;
   // stagger = 1 starts every odd group only after its even neighbour has finished its first position stage, so that the
   // two are about a third of a substep apart for the rest of the step; 2 chains all groups that way.
+  // slow lane (so100_scratch.cuh: Queues): on by default for the small grid class; budgets of the regular kernels
+  bool slowlane_enabled = false, slow_on = false;   // SO100_SLOWLANE=1 enables it.  Measured (B200, 16384 envs): 3.6-4.9 ms per step against
+                                                    // 2.5 without: one warp taking an env through kinematics, box collision, its hull pairs one
+                                                    // after the other and the solve needs 250-450 us per stage, longer than the regular
+                                                    // pipeline's whole stage, and the 255-register lane warps crowd the regular kernels
+  int budget_newton = 6, budget_gjk = 10, budget_epa = 5;
   int prio_low = 0, prio_mid = 0, prio_high = 0;   // kernel scheduling priorities (launch_p); all equal with SO100_PRIO=0
   int dag = 0;       // SO100_DAG: schedule of a substep's kernels (launch_solve_stage); 0 = K2b before all solve classes (measured
                      // fastest: the envs K2b completes are the ones with the long solves, so running K2b beside the light grid
@@ -162,13 +171,14 @@ struct so100_ctx {
   uint8_t *h_term = nullptr, *h_trunc = nullptr, *h_succ = nullptr;
   DevTables tables() const { return DevTables{geom, pair, vert, bpair}; }
   static constexpr int CTL_WORDS = Q_STRIDE * 40;
-  static size_t qmem_words(size_t n) { return CTL_WORDS + (4 + NHP) * n; }
+  static size_t qmem_words(size_t n) { return CTL_WORDS + (6 + NHP) * n; }
   Queues queues(const EnvGroup& G) const {
     int* base = qmem + CTL_WORDS;
     const size_t N = (size_t)n;
     return Queues{G.ctl, base + N + (size_t)G.off * NHP, base + G.off, base + (1 + NHP) * N + G.off, base + (2 + NHP) * N + G.off,
                   base + (3 + NHP) * N + G.off, G.order + (size_t)G.parity * n, G.order + (size_t)(1 - G.parity) * n, qstat,
-                  (1024 * 1024) / std::max(G.n, 1), G.index < 8 ? (G.index * 12 + G.stage) * 10 : -1000000, dag != 0 ? 1 : 0};
+                  (1024 * 1024) / std::max(G.n, 1), G.index < 8 ? (G.index * 12 + G.stage) * 10 : -1000000, dag != 0 ? 1 : 0,
+                  base + (4 + NHP) * N + G.off, base + (5 + NHP) * N + G.off, slow_on ? 1 : 0, budget_newton, budget_gjk, budget_epa};
   }
 };
 
@@ -416,6 +426,7 @@ static int configure_kernels(int device) {
   CUDA_OK(cudaFuncSetAttribute(phase_collide_box<LPE_K2A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<BoxS>(LPE_K2A)));
   CUDA_OK(cudaFuncSetAttribute(phase_collide_hull<LPE_K2B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<HullS>(LPE_K2B)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_light<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L)));
+  CUDA_OK(cudaFuncSetAttribute(phase_slow_lane<LPE_K1, LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLOW_SMEM));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_light_queue<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NC>>(LPE_K3H)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H, NCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3H)));
@@ -462,7 +473,7 @@ static void launch_kin_box(so100_ctx* h, EnvGroup& G, cudaStream_t st, const flo
   float* state = h->state + (size_t)G.off * STATE_WORDS;
   float* work = h->work + (size_t)G.off * WORK_WORDS;
   mark(h, st, CLS_KIN, true);
-  launch_p(phase_kin_dyn<LPE_K1>, grid_of(n, LPE_K1), BLOCK, smem_of<KinS>(LPE_K1), st, h->prio_mid, state, work, action ? action + (size_t)G.off * 6 : nullptr, n, with_dyn, Q);
+  launch_p(phase_kin_dyn<LPE_K1>, grid_of(n, LPE_K1), BLOCK, smem_of<KinS>(LPE_K1), st, h->prio_mid, state, work, action ? action + (size_t)G.off * 6 : nullptr, n, with_dyn, Q, G.stage);
   mark(h, st, CLS_KIN, false); mark(h, st, CLS_BOX, true);
   launch_p(phase_collide_box<LPE_K2A>, grid_of(n, LPE_K2A), BLOCK, smem_of<BoxS>(LPE_K2A), st, h->prio_mid, work, n, T, Q, reuse);
   mark(h, st, CLS_BOX, false);
@@ -506,6 +517,14 @@ static void launch_solve_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const
     launch_p(phase_solve_light_queue<LPE_K3L>, k3lb_grid(h, n), TPB_K3L, smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L), s_, h->prio_high, state, work, T, Q, O);
   };
   const bool split = h->dag != 0;
+  if (h->slow_on && !hull_done) {
+    // slow lane: the rare classes and the over-budget envs are suspended by the kernels below; the chain is K2b -> budgeted light grid
+    launch_hull(h, G, st);
+    mark(h, st, CLS_SOLVE, true);
+    light_a(st);
+    mark(h, st, CLS_SOLVE, false);
+    return;
+  }
   if (h->timing || hull_done) {
     // timing mode (one stream, so that every event pair brackets its kernels alone) and so100_forward (K2b already ran)
     if (!hull_done) launch_hull(h, G, st);
@@ -570,6 +589,30 @@ static void launch_solve_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const
   cudaStreamWaitEvent(st, G.join3, 0);
 }
 
+// Slow-lane kernel of stage `stage` (after that stage's light kernel): beside the regular pipeline on its own stream, joined by
+// join_slow_lanes before anything reads the whole group's state (the task kernel, the end of so100_substeps).
+static void launch_slow_lane(so100_ctx* h, EnvGroup& G, cudaStream_t st, int stage, int nsub, int trailing) {
+  if (!h->slow_on) return;
+  float* state = h->state + (size_t)G.off * STATE_WORDS;
+  float* work = h->work + (size_t)G.off * WORK_WORDS;
+  const int grid = std::max(32, std::min(4 * h->sm_count, G.n / 16));
+  const int k = stage % EnvGroup::NSLOW;
+  cudaStream_t s_ = st;
+  if (!h->timing) {
+    cudaEventRecord(G.slow_fork[k], st);
+    cudaStreamWaitEvent(G.slow[k], G.slow_fork[k], 0);
+    s_ = G.slow[k];
+  }
+  mark(h, s_, CLS_HEAVY, true);
+  launch_p(phase_slow_lane<LPE_K1, LPE_K3L>, grid, 32, SLOW_SMEM, s_, h->prio_high, state, work, h->tables(), h->queues(G), stage, nsub, trailing);
+  mark(h, s_, CLS_HEAVY, false);
+  if (!h->timing) cudaEventRecord(G.slow_done[k], G.slow[k]);
+}
+static void join_slow_lanes(so100_ctx* h, EnvGroup& G, cudaStream_t st, int nstages) {
+  if (!h->slow_on || h->timing) return;
+  for (int k = 0; k < std::min(nstages, (int)EnvGroup::NSLOW); k++) cudaStreamWaitEvent(st, G.slow_done[k], 0);
+}
+
 static int make_group(so100_ctx* h, EnvGroup& G, int off, int n, int index, bool own_stream) {
   G.off = off; G.n = n; G.ctl = h->qmem + Q_STRIDE * index; G.index = index;
   G.order = h->order + (own_stream ? 0 : 2 * (size_t)h->n) + off;
@@ -583,6 +626,11 @@ static int make_group(so100_ctx* h, EnvGroup& G, int off, int n, int index, bool
   CUDA_OK(cudaStreamCreateWithFlags(&G.side, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&G.side2, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&G.hull, cudaStreamNonBlocking));
+  for (int k = 0; k < EnvGroup::NSLOW; k++) {
+    CUDA_OK(cudaStreamCreateWithFlags(&G.slow[k], cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&G.slow_fork[k], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&G.slow_done[k], cudaEventDisableTiming));
+  }
   CUDA_OK(cudaEventCreateWithFlags(&G.join2, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.join3, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&G.fork2, cudaEventDisableTiming));
@@ -598,6 +646,11 @@ static void free_group(EnvGroup& G) {
   if (G.side) cudaStreamDestroy(G.side);
   if (G.side2) cudaStreamDestroy(G.side2);
   if (G.hull) cudaStreamDestroy(G.hull);
+  for (int k = 0; k < EnvGroup::NSLOW; k++) {
+    if (G.slow[k]) cudaStreamDestroy(G.slow[k]);
+    if (G.slow_fork[k]) cudaEventDestroy(G.slow_fork[k]);
+    if (G.slow_done[k]) cudaEventDestroy(G.slow_done[k]);
+  }
   if (G.join2) cudaEventDestroy(G.join2);
   if (G.join3) cudaEventDestroy(G.join3);
   if (G.fork2) cudaEventDestroy(G.fork2);
@@ -655,6 +708,10 @@ static int create_device_side(so100_ctx* h, const DevModel& dm, const std::vecto
   if (const char* e = getenv("SO100_GROUP_TIMES")) h->group_times = atoi(e) != 0;
   if (const char* e = getenv("SO100_STAGGER")) h->stagger = atoi(e);
   if (const char* e = getenv("SO100_DAG")) h->dag = atoi(e);
+  if (const char* e = getenv("SO100_SLOWLANE")) h->slowlane_enabled = atoi(e) != 0;
+  if (const char* e = getenv("SO100_BUDGET_NEWTON")) h->budget_newton = std::max(1, atoi(e));
+  if (const char* e = getenv("SO100_BUDGET_GJK")) h->budget_gjk = std::max(1, atoi(e));
+  if (const char* e = getenv("SO100_BUDGET_EPA")) h->budget_epa = std::max(1, atoi(e));
   {
     int least = 0, greatest = 0, mode = 1;
     CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));     // numerically lower = higher priority
@@ -796,7 +853,9 @@ int so100_num_envs(so100_handle h) { return h ? h->n : SO100_ERR_ARG; }
 int so100_launches_per_step(so100_handle h) {
   if (!h) return SO100_ERR_ARG;
   // nsub x (K1, K2a, K2b, K3l, K3m, K3h [+ K3l-b, K3m-b with the a / b work classes]) + trailing (K1, K2a, K2b) + K4
-  const int per_group = h->nsub * (h->dag != 0 ? 8 : 6) + 3 + 1;
+  // with the slow lane (default): nsub x (K1, K2a, K2b, K3l, slow lane) + trailing (K1, K2a, K2b) + K4
+  const bool slow = h->slowlane_enabled && h->grid_class == 0 && h->nsub >= 1 && h->nsub <= 11;
+  const int per_group = slow ? h->nsub * 5 + 3 + 1 : h->nsub * (h->dag != 0 ? 8 : 6) + 3 + 1;
   return per_group * (int)std::max<size_t>(h->groups.size(), 1);
 }
 
@@ -824,6 +883,9 @@ struct HostOut {
 // the launch sequence of one env step on `stream` (directly, or while `stream` is being captured into a graph)
 static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream, int reuse, const HostOut* ho = nullptr) {
   const float* action = A.action;
+  // the slow lane belongs to the small grid class: when a policy holds thousands of cubes at once (large class) the rare
+  // classes are not rare and the medium / heavy queue kernels serve them better
+  h->slow_on = h->slowlane_enabled && h->grid_class == 0 && h->nsub >= 1 && h->nsub <= 11;
   for_each_group(h, stream, true, [&](EnvGroup& G, cudaStream_t st) {
     const SolveOut O{nullptr, nullptr, 0};
     for (int s = 0; s < h->nsub; s++) {
@@ -831,10 +893,12 @@ static void enqueue_step(so100_ctx* h, const StepArgs& A, cudaStream_t stream, i
       launch_kin_box(h, G, st, s == 0 ? action : nullptr, 1, s == 0 ? reuse : 0);
       if (s == 0) cudaEventRecord(G.staged, st);
       launch_solve_stage(h, G, st, O);
+      launch_slow_lane(h, G, st, s, h->nsub, 1);
     }
     // trailing mj_step1 (dm_control's legacy step): positions + contacts of the new state, then the task layer
     G.stage = std::min(h->nsub, 11);
     launch_position_stage(h, G, st, h->nsub == 0 ? action : nullptr, 0);
+    join_slow_lanes(h, G, st, h->nsub);
     StepArgs B = A;
     B.trace = h->queues(G).trace;
     const size_t o = (size_t)G.off;
@@ -1122,14 +1186,22 @@ int so100_substeps(so100_handle h, int nsub, void* stream) {
   if (!h || nsub < 0) return fail(SO100_ERR_ARG, "so100_substeps: bad argument");
   DeviceGuard guard(h->device);
   h->work_fresh = false;
-  for_each_group(h, (cudaStream_t)stream, true, [&](EnvGroup& G, cudaStream_t st) {
-    const SolveOut O{nullptr, nullptr, 0};
-    for (int s = 0; s < nsub; s++) {
-      launch_kin_box(h, G, st, nullptr, 1);
-      if (s == 0) cudaEventRecord(G.staged, st);
-      launch_solve_stage(h, G, st, O);
-    }
-  });
+  h->slow_on = h->slowlane_enabled && h->grid_class == 0;
+  // at most 12 stages per pass: the slow lane keeps one queue cursor per stage of a pass
+  for (int base = 0; base < nsub; base += 12) {
+    const int chunk = std::min(12, nsub - base);
+    for_each_group(h, (cudaStream_t)stream, true, [&](EnvGroup& G, cudaStream_t st) {
+      const SolveOut O{nullptr, nullptr, 0};
+      for (int s = 0; s < chunk; s++) {
+        G.stage = s;
+        launch_kin_box(h, G, st, nullptr, 1);
+        if (s == 0) cudaEventRecord(G.staged, st);
+        launch_solve_stage(h, G, st, O);
+        launch_slow_lane(h, G, st, s, chunk, 0);
+      }
+      join_slow_lanes(h, G, st, chunk);
+    });
+  }
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
@@ -1141,6 +1213,8 @@ int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom,
   cudaStream_t st = (cudaStream_t)stream;
   // the whole batch as one group on the caller's stream, every kernel in sequence: K1, K2a, K2b, the contact export, then the
   // solve classes in forward mode (nothing is integrated)
+  h->slow_on = false;        // mj_forward solves every env in the regular kernels (no budgets, medium / heavy queue kernels)
+  h->whole.stage = 0;
   launch_kin_box(h, h->whole, st, nullptr, 1);
   launch_hull(h, h->whole, st);
   const int threads = h->n * 32;

@@ -198,9 +198,12 @@ __device__ int g_hull_stat_n;
 
 // Penetration of A into B.  On a hit: normal (A -> B), depth > 0, contact point (midpoint of the
 // witness points).  All lanes return the same values.
+// max_gjk / max_epa: iteration budgets of the regular (budgeted) GJK/EPA kernel; when one runs out *over_budget is set and the
+// result is void (the env goes to the slow lane, which calls this without budgets).
 template <unsigned LPE>
 __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 ca, V3 cb, const float4* vert,
-                        EpaScratch* E, V3& normal, float& depth, V3& pos) {
+                        EpaScratch* E, V3& normal, float& depth, V3& pos, int max_gjk = 48, int max_epa = EPA_MAXV - 4,
+                        bool* over_budget = nullptr) {
   const int lane = t.thread_rank();
   MV s[4];
   int n = 1;
@@ -211,6 +214,7 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
   bool hit = false;
   int gjk_its_ = 0;
   for (int it = 0; it < 48; it++) {
+    if (it >= max_gjk) { *over_budget = true; return false; }
     gjk_its_ = it + 1;
     if (dot(dir, dir) < 1e-24f) break;
     const MV w = msupport(t, A, B, dir, vert);
@@ -241,6 +245,7 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
   for (int k = 0; k < 4; k++) degenerate |= (E->fv[k][3] == 0);
   if (degenerate) return false;   // flat tetrahedron: touching
   for (int it = 0; it < EPA_MAXV - 4; it++) {
+    if (it >= max_epa) { *over_budget = true; t.sync(); return false; }
 #ifdef SO100_HULL_CLOCK
     if (lane == 0) E->dbg[1] = it + 1;
 #endif
@@ -409,7 +414,9 @@ __device__ V3 deepest_feature_point(const Tile<LPE>& t, const Shape& A, const Sh
 // staging slot.  The tile that finishes an env's last pending pair merges the staged contacts into the contact list
 // in pair order (deterministic contact order, after the box contacts) and returns the final count, with *coupled_out
 // whether an arm-cube contact exists; every other tile returns -1.
-template <unsigned LPE> __device__ int collide_hull_item(const Tile<LPE>& t, HullS* S, float* w, int slot, const DevTables& T, bool* coupled_out) {
+// With budgets (max_gjk / max_epa < their caps) an item that exceeds them returns -2 and leaves the env's pending counter alone.
+template <unsigned LPE> __device__ int collide_hull_item(const Tile<LPE>& t, HullS* S, float* w, int slot, const DevTables& T, bool* coupled_out,
+                                                         int max_gjk = 48, int max_epa = EPA_MAXV - 4) {
   const int lane = t.thread_rank();
   const int p = reinterpret_cast<const unsigned char*>(w + W_HULLP)[slot];
   const DevPair& P = T.pair[p];
@@ -441,11 +448,13 @@ template <unsigned LPE> __device__ int collide_hull_item(const Tile<LPE>& t, Hul
     g_hull_stat[k_][2] = E_->dbg[0] | (E_->dbg[1] << 8) | ((int)hit_ << 16); g_hull_stat[k_][3] = A.vnum + B.vnum;
   }
 #else
-  if (gjk_epa(t, A, B, c1, c2, T.vert, reinterpret_cast<EpaScratch*>(S->epa), n, depth, pos)) {
+  bool over = false;
+  if (gjk_epa(t, A, B, c1, c2, T.vert, reinterpret_cast<EpaScratch*>(S->epa), n, depth, pos, max_gjk, max_epa, &over)) {
     snap_normal(t, A, B, n, depth, T.vert);
     pos = deepest_feature_point(t, A, B, n, depth, pos, T.vert);
     pid = p;
   }
+  if (over) return -2;
 #endif
   int* hdr = reinterpret_cast<int*>(w + W_HDR);
   int last = 0;

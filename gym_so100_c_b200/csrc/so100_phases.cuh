@@ -28,16 +28,10 @@ namespace so100 {
                               // two envs per warp: no spills; 20 warps = 96 registers spills 132 bytes and is 4 % slower)
 #endif
 
-// K1: state -> frames (+ mass matrix, smooth forces, unconstrained acceleration); also re-arms the queues
+// K1 for one env: state -> frames (+ mass matrix, smooth forces, unconstrained acceleration) in the workspace
 template <unsigned LPE>
-__global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, const float* action, int n, int with_dyn, Queues Q) {
-  SO100_TILE_PROLOGUE(LPE, 128, KinS);
-  SO100_TRACE_SCOPE(Q.trace + TR_KIN);
-  if (blockIdx.x == 0 && threadIdx.x < Q_WORDS) Q.ctl[threadIdx.x] = 0;
-  const int env = blockIdx.x * EPB + t.meta_group_rank();
-  if (env >= n) return;
-  float* rec = state + (size_t)env * STATE_WORDS;
-  float* w = work + (size_t)env * WORK_WORDS;
+__device__ __forceinline__ void kin_dyn_env(const Tile<LPE>& t, KinS* S, float* rec, float* w, const float* action, int env, int with_dyn) {
+  const int lane = t.thread_rank();
   copy_vec<LPE, 32>(t, S->st, rec);       // qpos qvel ctrl (+ 1 word of warm)
   t.sync();
   if (action) {
@@ -63,6 +57,28 @@ __global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, 
   copy_vec<LPE, W_FRAMES_N>(t, w + W_FRAMES, reinterpret_cast<const float*>(&S->f));
 }
 
+// K1: regular grid over a group's envs; also re-arms the queues (`stage` = 0 for the first stage of a step, which also re-arms
+// the slow lane; every stage notes where the slow-lane queue stands: the entries a stage adds belong to that stage's slow-lane kernel)
+template <unsigned LPE>
+__global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, const float* action, int n, int with_dyn, Queues Q, int stage) {
+  SO100_TILE_PROLOGUE(LPE, 128, KinS);
+  SO100_TRACE_SCOPE(Q.trace + TR_KIN);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < Q_WORDS) Q.ctl[threadIdx.x] = 0;
+    if (threadIdx.x == Q_WORDS) {
+      if (stage == 0) Q.ctl[Q_LANE_COUNT] = 0;
+      if (stage >= 0 && stage < 12) Q.ctl[Q_LANE_CURSOR + stage] = stage == 0 ? 0 : Q.ctl[Q_LANE_COUNT];
+    }
+  }
+  const int env = blockIdx.x * EPB + t.meta_group_rank();
+  if (env >= n) return;
+  if (Q.slowlane) {
+    if (stage == 0) { if (lane == 0) Q.lane[env] = 0; }
+    else if (Q.lane[env] != 0) return;
+  }
+  kin_dyn_env(t, S, state + (size_t)env * STATE_WORDS, work + (size_t)env * WORK_WORDS, action, env, with_dyn);
+}
+
 // K2a: frames -> box contacts + surviving hull pairs; classifies the env
 // `reuse`: the workspace already holds the complete contact lists of exactly this state (the trailing collision stage of
 // the previous so100_step), except for envs whose header says HDR_STALE (reset since): everyone else only re-enters the
@@ -72,6 +88,7 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_box
   SO100_TRACE_SCOPE(Q.trace + TR_BOX);
   const int env = blockIdx.x * EPB + t.meta_group_rank();
   if (env >= n) return;
+  if (Q.suspended(env)) return;
   float* w = work + (size_t)env * WORK_WORDS;
   if (reuse) {
     const int4 hdr = *reinterpret_cast<const int4*>(w + W_HDR);
@@ -114,8 +131,10 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_hul
     copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
     t.sync();
     bool coupled = false;
-    const int ncon = collide_hull_item(t, S, w, item % NHP, T, &coupled);
+    const int ncon = Q.slowlane ? collide_hull_item(t, S, w, item % NHP, T, &coupled, Q.budget_gjk, Q.budget_epa)
+                                : collide_hull_item(t, S, w, item % NHP, T, &coupled);
     if (lane == 0 && ncon >= 0) Q.route(env, ncon, coupled, true);
+    if (lane == 0 && ncon == -2) Q.suspend(env);        // over budget: the slow lane redoes this env's collision stage
     t.sync();
   }
 }
@@ -129,9 +148,10 @@ struct SolveOut {
 
 // `active` = false (only with several tiles per warp): the tile has no env to solve but its warp sibling does; it loads a valid
 // record, takes part in the warp votes of the solver loop with "done", and stores nothing
+// `max_it`: Newton budget (regular light kernel with the slow lane on); an over-budget solve returns -1 and stores nothing.
 template <bool DENSE, unsigned LPE, class ES>
 __device__ int solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w, int env, int ncon_raw, const DevTables& T,
-                         const SolveOut& O, bool active = true) {
+                         const SolveOut& O, bool active = true, int max_it = NEWTON_MAXIT) {
   const int lane = t.thread_rank();
   copy_vec<LPE, 48>(t, S->st, rec);
   copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
@@ -142,8 +162,8 @@ __device__ int solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w, 
   if (lane == 0) S->ncon = ncon;
   t.sync();
   make_contact_rows(t, S, T);
-  const int iters = solve<DENSE>(t, S, T, (O.forward || !active) ? nullptr : reinterpret_cast<uint32_t*>(rec + S_DIAG), active);
-  if (!active) return iters;
+  const int iters = solve<DENSE>(t, S, T, (O.forward || !active) ? nullptr : reinterpret_cast<uint32_t*>(rec + S_DIAG), active, max_it);
+  if (!active || iters < 0) return iters;
   if (O.forward) {
     t.sync();
     if (O.qacc && lane < NV) O.qacc[(size_t)env * NV + lane] = S->a[lane];
@@ -171,7 +191,8 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
   // envs are solved by the queue kernel below once K2b has completed their contact list.  hdr.x / hdr.z of the others are final.
   const bool hull_env = Q.split && hdr.y > 0;
   const int ncon_raw = (hdr.z & HDR_COUPLED) ? NC + 2 : hdr.x;      // arm-cube contacts: heavy kernel (dense Hessian)
-  const bool mine = live && !hull_env && ncon_raw <= NCL;
+  const bool mine = live && !hull_env && ncon_raw <= NCL && !Q.suspended(env);
+  const int max_it = Q.slowlane ? Q.budget_newton : NEWTON_MAXIT;
   int iters = hull_env ? 0 : 1000;           // heavy / medium envs count as slow; hull envs are not this kernel's business
 #ifdef SO100_SOLVE_CLOCK
   unsigned long long t0_;
@@ -181,8 +202,12 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
   if (lane < 4) S->clk2[lane] = 0;
 #endif
   // several tiles per warp: every tile enters the solver (its loop votes warp-wide), the ones without work as inactive
-  if (LPE < 32) { const int it_ = solve_env<false>(t, S, state + (size_t)env * STATE_WORDS, w, env, min(ncon_raw, NCL), T, O, mine); if (mine) iters = it_; }
-  else if (mine) iters = solve_env<false>(t, S, state + (size_t)env * STATE_WORDS, w, env, ncon_raw, T, O);
+  if (LPE < 32) { const int it_ = solve_env<false>(t, S, state + (size_t)env * STATE_WORDS, w, env, min(ncon_raw, NCL), T, O, mine, max_it); if (mine) iters = it_; }
+  else if (mine) iters = solve_env<false>(t, S, state + (size_t)env * STATE_WORDS, w, env, ncon_raw, T, O, true, max_it);
+  if (iters < 0) {                           // over the Newton budget: nothing was stored; the slow lane takes the env from here
+    if (lane == 0) Q.suspend(env);
+    iters = 1000;
+  }
 #ifdef SO100_SOLVE_CLOCK
   // development build: duration (ns) and iteration count of this env's last solve in the spare words of its state record
   unsigned long long t1_;
@@ -253,6 +278,72 @@ __global__ void __launch_bounds__(128, NCAP == NCL ? SO100_K3M_MINB : SO100_K3H_
     const float* w = work + (size_t)env * WORK_WORDS;
     solve_env<true>(t, S, state + (size_t)env * STATE_WORDS, w, env, __float_as_int(w[W_HDR]), T, O);
     t.sync();
+  }
+}
+
+// Slow lane: persistent one-warp blocks take the envs suspended during stage `stage` (slow-lane queue entries from this
+// stage's cursor up to the queue length at launch) and run each of them, alone, through the rest of the step: the collision
+// stage of `stage` again (cheap, and it makes every suspension reason look the same), solve + integrate, then for every later
+// stage kinematics / dynamics -> collision -> solve -> integrate, and finally the trailing position stage.  The same device
+// functions with the same tile widths as the regular kernels run here (kinematics on a 16-lane sub-tile, the light solve on a
+// 16-lane sub-tile with an inactive sibling), so an env's result does not depend on which lane computed it.
+#ifndef SO100_SLOW_MINB
+#define SO100_SLOW_MINB 8
+#endif
+constexpr size_t slow_max2(size_t a, size_t b) { return a > b ? a : b; }
+constexpr size_t SLOW_SMEM = slow_max2(slow_max2(sizeof(KinS), sizeof(BoxS)), slow_max2(slow_max2(sizeof(HullS), 2 * sizeof(SolS<NCL>)), sizeof(SolS<NC>)));
+template <unsigned LPE_KIN, unsigned LPE_LIGHT>
+__global__ void __launch_bounds__(32, SO100_SLOW_MINB) phase_slow_lane(float* state, float* work, DevTables T, Queues Q, int stage, int nsub, int trailing) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::thread_block blk = cg::this_thread_block();
+  Tile<32> t = cg::tiled_partition<32>(blk);
+  Tile<LPE_KIN> tk = cg::tiled_partition<LPE_KIN>(blk);
+  Tile<LPE_LIGHT> tl = cg::tiled_partition<LPE_LIGHT>(blk);
+  const int lane = t.thread_rank();
+  SO100_TRACE_SCOPE(Q.trace + TR_SLOW);
+  const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_LANE_COUNT]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) Q.note(0, count >> 2);      // a quarter of the envs suspended so far this step
+  const SolveOut O{nullptr, nullptr, 0};
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&Q.ctl[Q_LANE_CURSOR + stage], 1);
+    i = t.shfl(i, 0);
+    if (i >= count) break;
+    const int env = Q.slow[i];
+    float* rec = state + (size_t)env * STATE_WORDS;
+    float* w = work + (size_t)env * WORK_WORDS;
+    for (int s = stage; s <= nsub; s++) {
+      const bool position_only = s == nsub;           // the trailing mj_step1 of the step
+      if (position_only && !trailing) break;
+      if (s > stage) {
+        if (tk.meta_group_rank() == 0) kin_dyn_env(tk, reinterpret_cast<KinS*>(smem_raw), rec, w, nullptr, env, position_only ? 0 : 1);
+        t.sync();
+      }
+      // collision stage from the frames in the workspace
+      BoxS* B = reinterpret_cast<BoxS*>(smem_raw);
+      copy_vec<32, W_FRAMES_N>(t, reinterpret_cast<float*>(&B->f), w + W_FRAMES);
+      t.sync();
+      int ncon = 0;
+      bool coupled = false;
+      const int nsurv = collide_box_env(t, B, w, T, &ncon, &coupled);
+      t.sync();
+      if (nsurv > 0) {
+        HullS* H = reinterpret_cast<HullS*>(smem_raw);     // its frame block is the one just loaded (both layouts start with it)
+        for (int slot = 0; slot < nsurv; slot++) {
+          bool cpl = false;
+          const int r = collide_hull_item(t, H, w, slot, T, &cpl);
+          if (r >= 0) { ncon = r; coupled = cpl; }
+          t.sync();
+        }
+      }
+      if (position_only) break;
+      if (ncon > NCL) solve_env<true>(t, reinterpret_cast<SolS<NC>*>(smem_raw), rec, w, env, ncon, T, O);
+      else if (coupled) solve_env<true>(t, reinterpret_cast<SolS<NCL>*>(smem_raw), rec, w, env, ncon, T, O);
+      else if constexpr (LPE_LIGHT < 32)
+        solve_env<false>(tl, reinterpret_cast<SolS<NCL>*>(smem_raw) + tl.meta_group_rank(), rec, w, env, ncon, T, O, tl.meta_group_rank() == 0);
+      else solve_env<false>(t, reinterpret_cast<SolS<NCL>*>(smem_raw), rec, w, env, ncon, T, O);
+      t.sync();
+    }
   }
 }
 

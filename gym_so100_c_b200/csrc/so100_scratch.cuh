@@ -50,7 +50,10 @@ static_assert(NHP <= 16, "hull pair list is 4 words");
 
 // queue control words (device ints)
 enum { Q_HULL_COUNT = 0, Q_HULL_NEXT = 1, Q_HEAVY_COUNT = 2, Q_HEAVY_NEXT = 3, Q_SLOW = 4, Q_FAST = 5, Q_MEDA_COUNT = 6, Q_MEDA_NEXT = 7,
-       Q_MEDB_COUNT = 8, Q_MEDB_NEXT = 9, Q_LB_COUNT = 10, Q_LB_NEXT = 11, Q_WORDS = 12, Q_STRIDE = 16 };
+       Q_MEDB_COUNT = 8, Q_MEDB_NEXT = 9, Q_LB_COUNT = 10, Q_LB_NEXT = 11, Q_WORDS = 12,     // words 0..11 are re-armed by every stage's K1
+       Q_LANE_COUNT = 12,        // slow-lane queue length: grows over the stages of a step, re-armed by the first stage only
+       Q_LANE_CURSOR = 16,       // [12] per stage: the next slow-lane queue entry of that stage's slow-lane kernel
+       Q_STRIDE = 32 };
 
 // Work classes of a substep.  The collision stage ends in two steps: the box stage (K2a) completes every env without a hull
 // pair, the GJK/EPA queue kernel (K2b) the other ~14 %.  Everything that only needs K2a starts right after it and runs BESIDE
@@ -83,7 +86,7 @@ struct TraceScope {
 #else
 #define SO100_TRACE_SCOPE(id_) do { } while (0)
 #endif
-enum { TR_KIN = 0, TR_BOX = 1, TR_HULL = 2, TR_LIGHT_A = 3, TR_LIGHT_B = 4, TR_MED_A = 5, TR_MED_B = 6, TR_HEAVY = 7, TR_TASK = 8 };
+enum { TR_KIN = 0, TR_BOX = 1, TR_HULL = 2, TR_LIGHT_A = 3, TR_LIGHT_B = 4, TR_MED_A = 5, TR_MED_B = 6, TR_HEAVY = 7, TR_TASK = 8, TR_SLOW = 9 };
 
 struct Queues {
   int* ctl;      // [Q_WORDS]
@@ -103,6 +106,20 @@ struct Queues {
   int trace;     // development builds (-DSO100_TRACE): base record id of this (group, stage)
   int split;     // 1: a / b work classes as described above; 0: K2b runs before every solve kernel, so there are no b classes
                  // (every env is solved by the regular light grid or the medium a / heavy queue)
+  // ---- slow lane (so100_phases.cuh: phase_slow_lane).  The duration of every kernel of a stage is set by its slowest env, and a
+  // stage's chain is the SUM of those maxima.  With the slow lane an env whose work exceeds a budget (Newton iterations of the
+  // light solve, GJK / EPA iterations of one hull pair) or that belongs to a rare class (arm-cube contact, > NCL contacts) is
+  // SUSPENDED: it leaves the regular kernels for the rest of the step and a slow-lane tile takes it through all remaining stages
+  // on its own (kinematics -> collision -> solve -> integrate, same device functions and tile widths, hence the same bits),
+  // beside the regular pipeline.  The regular chain then only carries budgeted work.
+  int* slow;     // [N] slow-lane queue: suspended envs in order of suspension
+  int* lane;     // [N] 1: the env is suspended (owned by the slow lane) for the rest of this step
+  int slowlane;  // 0: classic schedule (medium / heavy queue kernels, no budgets)
+  int budget_newton, budget_gjk, budget_epa;
+  __device__ __forceinline__ bool suspended(int env) const { return slowlane && lane[env] != 0; }
+  __device__ __forceinline__ void suspend(int env) const {
+    if (atomicExch(&lane[env], 1) == 0) slow[atomicAdd(&ctl[Q_LANE_COUNT], 1)] = env;
+  }
   __device__ __forceinline__ void note(int which, int count) const { atomicMax(&stat[which], (count * scale) >> 10); }
   // work class of an env whose collision stage is complete (`after_hull`: completed by K2b, or had hull pairs when the
   // contact lists of the previous step's trailing stage are reused): > NCL contacts (or list overflow) -> heavy queue; an
@@ -110,6 +127,7 @@ struct Queues {
   // light kernel, those completed by K2b go to light queue b
   __device__ __forceinline__ void route(int env, int ncon, bool coupled, bool after_hull) const {
     after_hull = after_hull && split;
+    if (slowlane) { if (ncon > NCL || coupled) suspend(env); return; }
     if (ncon > NCL) heavy[atomicAdd(&ctl[Q_HEAVY_COUNT], 1)] = env;
     else if (coupled) {
       if (after_hull) medium_b[atomicAdd(&ctl[Q_MEDB_COUNT], 1)] = env;

@@ -514,7 +514,10 @@ template <unsigned LPE, class ES> __device__ __forceinline__ float dense_newton_
 
 // Solves for qacc (left in S->a / S->ad, contact forces in S->cfrc).  `diag` (nullable): the env's uint32 counters.
 // Returns the number of Newton iterations.
-template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S, const DevTables& T, uint32_t* diag, bool active = true) {
+// max_it < NEWTON_MAXIT: iteration budget of the regular light kernel; a solve that uses it up without converging returns -1,
+// counts nothing in `diag` and leaves an unfinished iterate behind (the env goes to the slow lane, which solves it again in full).
+template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S, const DevTables& T, uint32_t* diag, bool active = true,
+                                                                   int max_it = NEWTON_MAXIT) {
   using Regs = SolveRegs<LPE, ES::NCAP>;
   const int lane = t.thread_rank();
   const int ncon = S->ncon;
@@ -731,13 +734,14 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
           if (cost > cost_prev - 1e-7f * fabsf(cost_prev)) { if (++stall >= 2) last = true; } else stall = 0;
         }
         cost_prev = cost;
-        if (last || it >= NEWTON_MAXIT) done = true;
+        if (last || it >= max_it) done = true;
         else newton_step();
       }
     }
   }
   SOLVE_CLK(0);
   SOLVE_CLK_STORE(S);
+  if (active && max_it < NEWTON_MAXIT && !(converged || last)) return -1;      // over budget (tile-uniform)
   if (lane == 0 && diag) {
     diag[1] += (converged || last) ? 0u : 1u;
     diag[5] += (uint32_t)it;

@@ -233,19 +233,27 @@ def test_autoreset_and_truncation(model_blob):
 
 def test_groups_and_graph_replay_are_bit_invariant(model_blob, monkeypatch):
     """The execution schedule (env groups on parallel streams, CUDA-graph replay, longest-first solve order, work queues
-    filled through atomics, reuse of the trailing collision stage by the next step's first
-    substep) must not change any env's result: 4096 envs stepped as 4 groups under graph replay equal the same envs stepped
-    as one group with plain launches and every shortcut off, bit for bit, including after auto-resets."""
+    filled through atomics, reuse of the trailing collision stage by the next step's first substep, and the slow lane that
+    takes over-budget / rare-class envs through the rest of a step on its own) must not change any env's result: 4096 envs
+    stepped under every combination below equal the same envs stepped as one group with plain launches and every shortcut
+    off, bit for bit, including after auto-resets.  The tight-budget rows push ~half of the envs through the slow lane."""
     import torch
     from gym_so100_c_b200.engine import BatchedSim
     n = 4096
     g = torch.Generator(device="cuda").manual_seed(5)
     acts = torch.rand((6, n, 6), device="cuda", generator=g) * 2 - 1
     results = []
-    for groups, graph, reuse in (("4", "1", "1"), ("1", "0", "0"), ("8", "0", "1"), ("4", "1", "0")):
+    #          groups graph reuse slowlane budgets (newton, gjk, epa)
+    configs = (("4", "1", "1", "1", None), ("1", "0", "0", "0", None), ("8", "0", "1", "1", None), ("4", "1", "0", "0", None),
+               ("6", "1", "1", "1", ("1", "2", "1")), ("1", "0", "1", "1", ("2", "4", "2")))
+    for groups, graph, reuse, slow, budgets in configs:
         monkeypatch.setenv("SO100_GROUPS", groups)
         monkeypatch.setenv("SO100_GRAPH", graph)
         monkeypatch.setenv("SO100_REUSE", reuse)
+        monkeypatch.setenv("SO100_SLOWLANE", slow)
+        monkeypatch.setenv("SO100_ADAPTIVE_GRIDS", "1" if budgets is None else "0")   # tight budgets: keep the slow lane on however full it gets
+        for name, val in zip(("SO100_BUDGET_NEWTON", "SO100_BUDGET_GJK", "SO100_BUDGET_EPA"), budgets or ("6", "10", "5")):
+            monkeypatch.setenv(name, val)
         sim = BatchedSim(n, device="cuda:0", task=0, seed=9, model_blob=model_blob)
         sim.reset()
         sim.set_aux(step_count=torch.full((n,), 697, dtype=torch.int32))     # everyone truncates (and auto-resets) at step 3
@@ -253,9 +261,11 @@ def test_groups_and_graph_replay_are_bit_invariant(model_blob, monkeypatch):
         for k in range(6):
             obs, r, term, trunc, succ = sim.step(acts[k], autoreset=True)
             rew.append(r.clone())
-        assert sim.launches_per_step() == 64 * int(groups)
-        results.append([t.cpu().numpy() for t in sim.get_state()] + [torch.stack(rew).cpu().numpy(), obs.cpu().numpy()])
-        assert sim.diagnostics()["episodes"] >= n
+        assert sim.launches_per_step() == (54 if slow == "1" else 64) * int(groups)
+        d = sim.diagnostics()
+        results.append([t.cpu().numpy() for t in sim.get_state()] + [torch.stack(rew).cpu().numpy(), obs.cpu().numpy(),
+                                                                     np.array([d["solver_runs"], d["newton_iters"], d["contacts_seen"]])])
+        assert d["episodes"] >= n
         sim.close()
     for other in results[1:]:
         for a, b in zip(results[0], other):

@@ -23,7 +23,7 @@ for s in range(warm):
     sim.step(acts[s % 16])
 lib = ext.load()
 buf = np.zeros((960, 2), dtype=np.uint64)
-KINDS = ["kin", "box", "hull", "lightA", "lightB", "medA", "medB", "heavy", "task"]
+KINDS = ["kin", "box", "hull", "lightA", "lightB", "medA", "medB", "heavy", "task", "slow"]
 for rep in range(2):
     lib.so100_trace_read(None)
     sim.step(acts[rep])
@@ -34,7 +34,7 @@ for rep in range(2):
     print(f"--- step {rep}: total {(a[valid, 1].max() - t0) / 1e3:.1f} us")
     ngroups = max(1, int(os.environ.get("SHOW_GROUPS", "2")))
     for gi in range(8):
-        rows = [(st, k) for st in range(12) for k in range(9) if valid[(gi * 12 + st) * 10 + k]]
+        rows = [(st, k) for st in range(12) for k in range(10) if valid[(gi * 12 + st) * 10 + k]]
         if not rows:
             continue
         gend = max(a[(gi * 12 + st) * 10 + k, 1] for st, k in rows)
@@ -43,14 +43,14 @@ for rep in range(2):
             continue
         for st in range(12):
             parts = []
-            for k in range(9):
+            for k in range(10):
                 i = (gi * 12 + st) * 10 + k
                 if valid[i]:
                     parts.append(f"{KINDS[k]} {(a[i, 0] - t0) / 1e3:6.1f}-{(a[i, 1] - t0) / 1e3:6.1f}")
             if parts:
                 print(f"  stage {st:2d}: " + " | ".join(parts))
     # durations per kind (mean over groups and stages)
-    for k in range(9):
+    for k in range(10):
         d = [a[(gi * 12 + st) * 10 + k, 1] - a[(gi * 12 + st) * 10 + k, 0] for gi in range(8) for st in range(12) if valid[(gi * 12 + st) * 10 + k]]
         if d:
             print(f"  {KINDS[k]:7s} n {len(d):3d}  mean {np.mean(d) / 1e3:6.1f} us  max {np.max(d) / 1e3:6.1f} us")
