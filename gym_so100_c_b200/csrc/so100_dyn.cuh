@@ -3,6 +3,7 @@
 // from pairwise lever-arm products, the RNE bias force via prefix-sum scans, position actuators and
 // the unconstrained acceleration (6x6 Cholesky in registers).
 #pragma once
+#include <type_traits>
 #include "so100_scratch.cuh"
 
 namespace so100 {
@@ -156,55 +157,80 @@ template <unsigned LPE> __device__ void smooth_forces(const Tile<LPE>& t, KinS* 
   t.sync();
 }
 
+// Compile-time loop: f(std::integral_constant<int, B>), ..., f(std::integral_constant<int, E - 1>).  The 6x6 factorisations below
+// index their register arrays with these constants only: with ordinary `#pragma unroll` loops ptxas kept the triangular
+// factor in LOCAL memory (51 LDL/STL in the light solve kernel, 146 in the dense ones, on the critical path of every Newton
+// iteration).
+template <int B, int E, class F> __device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+__host__ __device__ constexpr int tri_c(int i, int j) { return (i * (i + 1)) / 2 + j; }
+
 // In-register Cholesky of a 6x6 SPD block (FULL: row-major 6x6, else packed lower triangle): L[tri(i, j)] for i > j and
 // 1 / L_jj on the diagonal
 template <bool FULL> __device__ __forceinline__ void chol6_factor(const float* A, float* L) {
-#pragma unroll
-  for (int i = 0; i < NL; i++)
-#pragma unroll
-    for (int j = 0; j <= i; j++) L[tri(i, j)] = FULL ? A[i * NL + j] : A[tri(i, j)];
-#pragma unroll
-  for (int j = 0; j < NL; j++) {
-    float d = L[tri(j, j)];
-#pragma unroll
-    for (int k = 0; k < j; k++) d = fmaf(-L[tri(j, k)], L[tri(j, k)], d);
+  static_for<0, NL>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    static_for<0, i + 1>([&](auto jc) {
+      constexpr int j = decltype(jc)::value;
+      L[tri_c(i, j)] = FULL ? A[i * NL + j] : A[tri_c(i, j)];
+    });
+  });
+  static_for<0, NL>([&](auto jc) {
+    constexpr int j = decltype(jc)::value;
+    float d = L[tri_c(j, j)];
+    static_for<0, j>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      d = fmaf(-L[tri_c(j, k)], L[tri_c(j, k)], d);
+    });
     d = rsqrtf(fmaxf(d, 1e-20f));
-    L[tri(j, j)] = d;   // 1 / L_jj
-#pragma unroll
-    for (int i = j + 1; i < NL; i++) {
-      float s = L[tri(i, j)];
-#pragma unroll
-      for (int k = 0; k < j; k++) s = fmaf(-L[tri(i, k)], L[tri(j, k)], s);
-      L[tri(i, j)] = s * d;
-    }
-  }
+    L[tri_c(j, j)] = d;   // 1 / L_jj
+    static_for<j + 1, NL>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      float sum = L[tri_c(i, j)];
+      static_for<0, j>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        sum = fmaf(-L[tri_c(i, k)], L[tri_c(j, k)], sum);
+      });
+      L[tri_c(i, j)] = sum * d;
+    });
+  });
 }
 // x <- L^-1 x
 __device__ __forceinline__ void chol6_fwd(const float* L, float* x) {
-#pragma unroll
-  for (int i = 0; i < NL; i++) {
-    float s = x[i];
-#pragma unroll
-    for (int k = 0; k < i; k++) s = fmaf(-L[tri(i, k)], x[k], s);
-    x[i] = s * L[tri(i, i)];
-  }
+  static_for<0, NL>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    float sum = x[i];
+    static_for<0, i>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      sum = fmaf(-L[tri_c(i, k)], x[k], sum);
+    });
+    x[i] = sum * L[tri_c(i, i)];
+  });
 }
 // x <- L^-T x
 __device__ __forceinline__ void chol6_bwd(const float* L, float* x) {
-#pragma unroll
-  for (int i = NL - 1; i >= 0; i--) {
-    float s = x[i];
-#pragma unroll
-    for (int k = i + 1; k < NL; k++) s = fmaf(-L[tri(k, i)], x[k], s);
-    x[i] = s * L[tri(i, i)];
-  }
+  static_for<0, NL>([&](auto rc) {
+    constexpr int i = NL - 1 - decltype(rc)::value;
+    float sum = x[i];
+    static_for<i + 1, NL>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      sum = fmaf(-L[tri_c(k, i)], x[k], sum);
+    });
+    x[i] = sum * L[tri_c(i, i)];
+  });
 }
 // x = sign * A^-1 b
 template <bool FULL> __device__ __forceinline__ void chol6_solve(const float* A, const float* b6, float sign, float* x) {
   float L[21];
   chol6_factor<FULL>(A, L);
-#pragma unroll
-  for (int i = 0; i < NL; i++) x[i] = sign * b6[i];
+  static_for<0, NL>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    x[i] = sign * b6[i];
+  });
   chol6_fwd(L, x);
   chol6_bwd(L, x);
 }

@@ -82,47 +82,52 @@ __device__ __forceinline__ MV msupport(const Tile<LPE>& t, const Shape& A, const
   return m;
 }
 
-// triangle case of the simplex update: A = s[2] is the newest point
-__device__ inline void simplex_triangle(MV* s, int& n, V3& dir) {
-  const MV A = s[2], B = s[1], C = s[0];
+// GJK simplex in named registers: a is always the newest point, then b, c, d (n of them are live).  An indexed array
+// `MV s[4]` with a run-time count lives in local memory (150 LDL/STL in the hot loop of the queue kernel); the moves below
+// are the same permutations the array version made, so every dot / cross product sees the same operands.
+struct Simplex { MV a, b, c, d; int n; };
+
+// triangle case of the simplex update on (a, b, c)
+__device__ __forceinline__ void simplex_triangle(Simplex& s, V3& dir) {
+  const MV A = s.a, B = s.b, C = s.c;
   const V3 ao = -A.w, ab = B.w - A.w, ac = C.w - A.w, abc = cross(ab, ac);
   bool edge_ab = false;
   if (dot(cross(abc, ac), ao) > 0) {
-    if (dot(ac, ao) > 0) { s[0] = C; s[1] = A; n = 2; dir = cross(cross(ac, ao), ac); return; }
+    if (dot(ac, ao) > 0) { s.b = C; s.n = 2; dir = cross(cross(ac, ao), ac); return; }     // {a, c}
     edge_ab = true;
   } else if (dot(cross(ab, abc), ao) > 0) {
     edge_ab = true;
   }
   if (edge_ab) {
-    if (dot(ab, ao) > 0) { s[0] = B; s[1] = A; n = 2; dir = cross(cross(ab, ao), ab); }
-    else { s[0] = A; n = 1; dir = ao; }
+    if (dot(ab, ao) > 0) { s.n = 2; dir = cross(cross(ab, ao), ab); }                        // {a, b}
+    else { s.n = 1; dir = ao; }                                                              // {a}
     return;
   }
   if (dot(abc, ao) > 0) dir = abc;
-  else { s[0] = B; s[1] = C; s[2] = A; dir = -abc; }
+  else { s.b = C; s.c = B; dir = -abc; }                                                     // flip the winding
 }
 
-// simplex update; returns true when the tetrahedron encloses the origin
-__device__ inline bool do_simplex(MV* s, int& n, V3& dir) {
-  if (n == 2) {
-    const V3 ao = -s[1].w, ab = s[0].w - s[1].w;
+// simplex update after a point was pushed; returns true when the tetrahedron encloses the origin
+__device__ __forceinline__ bool do_simplex(Simplex& s, V3& dir) {
+  if (s.n == 2) {
+    const V3 ao = -s.a.w, ab = s.b.w - s.a.w;
     if (dot(ab, ao) > 0) dir = cross(cross(ab, ao), ab);
-    else { s[0] = s[1]; n = 1; dir = ao; }
+    else { s.n = 1; dir = ao; }
     return false;
   }
-  if (n == 3) { simplex_triangle(s, n, dir); return false; }
-  const MV A = s[3], B = s[2], C = s[1], D = s[0];
+  if (s.n == 3) { simplex_triangle(s, dir); return false; }
+  const MV A = s.a, B = s.b, C = s.c, D = s.d;
   const V3 ao = -A.w, ab = B.w - A.w, ac = C.w - A.w, ad = D.w - A.w;
   V3 abc = cross(ab, ac), acd = cross(ac, ad), adb = cross(ad, ab);
   if (dot(abc, ad) > 0) abc = -abc;
   if (dot(acd, ab) > 0) acd = -acd;
   if (dot(adb, ac) > 0) adb = -adb;
-  if (dot(abc, ao) > 0) { s[0] = C; s[1] = B; s[2] = A; }
-  else if (dot(acd, ao) > 0) { s[0] = D; s[1] = C; s[2] = A; }
-  else if (dot(adb, ao) > 0) { s[0] = B; s[1] = D; s[2] = A; }
+  if (dot(abc, ao) > 0) { }                                   // (a, b, c)
+  else if (dot(acd, ao) > 0) { s.b = C; s.c = D; }            // (a, c, d)
+  else if (dot(adb, ao) > 0) { s.b = D; s.c = B; }            // (a, d, b)
   else return true;
-  n = 3;
-  simplex_triangle(s, n, dir);
+  s.n = 3;
+  simplex_triangle(s, dir);
   return false;
 }
 
@@ -205,12 +210,13 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
                         EpaScratch* E, V3& normal, float& depth, V3& pos, int max_gjk = 48, int max_epa = EPA_MAXV - 4,
                         bool* over_budget = nullptr) {
   const int lane = t.thread_rank();
-  MV s[4];
-  int n = 1;
+  Simplex s;
   V3 dir = cb - ca;
   if (dot(dir, dir) < 1e-20f) dir = mk(1, 0, 0);
-  s[0] = msupport(t, A, B, dir, vert);
-  dir = -s[0].w;
+  s.a = msupport(t, A, B, dir, vert);
+  s.b = s.a; s.c = s.a; s.d = s.a;
+  s.n = 1;
+  dir = -s.a.w;
   bool hit = false;
   int gjk_its_ = 0;
   for (int it = 0; it < 48; it++) {
@@ -219,8 +225,8 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
     if (dot(dir, dir) < 1e-24f) break;
     const MV w = msupport(t, A, B, dir, vert);
     if (dot(w.w, dir) <= 0) break;
-    s[n++] = w;
-    if (do_simplex(s, n, dir)) { hit = true; break; }
+    s.d = s.c; s.c = s.b; s.b = s.a; s.a = w; s.n++;
+    if (do_simplex(s, dir)) { hit = true; break; }
   }
 #ifdef SO100_HULL_CLOCK
   E->dbg[0] = gjk_its_; E->dbg[1] = 0;
@@ -228,7 +234,11 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
   if (!hit) return false;
   // ---- EPA
   t.sync();
-  if (lane < 4) { st3(E->vw[lane], s[lane].w); st3(E->va[lane], s[lane].a); }
+  if (lane < 4) {
+    // polytope vertices 0..3 = oldest .. newest simplex point (d, c, b, a)
+    const MV m = lane == 0 ? s.d : (lane == 1 ? s.c : (lane == 2 ? s.b : s.a));
+    st3(E->vw[lane], m.w); st3(E->va[lane], m.a);
+  }
   t.sync();
   if (lane < 4) {
     const int tf[4][3] = {{0, 1, 2}, {0, 3, 1}, {0, 2, 3}, {1, 3, 2}};
