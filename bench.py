@@ -240,9 +240,10 @@ def run_gpu(args):
     acts = torch.rand((K + W, nl, 6), device=dev, generator=gen) * 2 - 1       # inputs resident in HBM
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
     # settle to the steady state of the workload first (always, independent of --warmup), then W warm-up steps
-    settle_acts = torch.rand((16, nl, 6), device=dev, generator=gen) * 2 - 1
+    settle_acts = torch.rand((64, nl, 6), device=dev, generator=gen) * 2 - 1
     for s in range(args.settle):
-        sim.step(settle_acts[s % 16], autoreset=True)
+        sim.step(settle_acts[s % 64], autoreset=True)
+    del settle_acts
     for s in range(W):
         sim.step(acts[s], autoreset=True)
     torch.cuda.synchronize()
@@ -299,12 +300,12 @@ def run_gpu(args):
         lo5, _hi5 = parallel.shard_range(n5 * world, rank, world)
         sim5 = BatchedSim(n5, device=dev, task=0, seed=0x50100, env_offset=lo5)
         sim5.reset()
-        acts5 = torch.rand((8, n5, 6), device=dev, generator=gen) * 2 - 1
+        acts5 = torch.rand((32 + 10, n5, 6), device=dev, generator=gen) * 2 - 1      # 32 sets cycled while settling, 10 fresh ones timed
         for s in range(args.settle):
-            sim5.step(acts5[s % 8], autoreset=True)
+            sim5.step(acts5[s % 32], autoreset=True)
         torch.cuda.synchronize()
         parallel.barrier()
-        ms5 = timed_steps(sim5, acts5, 0, 10, flush, torch)
+        ms5 = timed_steps(sim5, acts5, 32, 10, flush, torch)
         tot5 = parallel.max_over_ranks(float(sum(ms5)), device=dev)
         rank5 = parallel.gather_floats(float(sum(ms5)) / 10, device=dev)
         sim5.close()
@@ -321,19 +322,19 @@ def run_gpu(args):
         env4 = SO100GoalVecEnv(n4, device=dev, seed=0x50100)
         roll = HerRollout(env4, horizon=320, n_sampled_goal=4)      # ring of 320 steps x 65536 envs (3.9 GB): holds whole 300-step episodes
         roll.reset()
-        acts4 = torch.rand((8, n4, 6), device=dev, generator=gen) * 2 - 1
+        acts4 = torch.rand((32 + 10, n4, 6), device=dev, generator=gen) * 2 - 1
         for s in range(310):                                        # every env finishes at least one episode: the ring has finished episodes to sample
-            roll.step(acts4[s % 8])
+            roll.step(acts4[s % 32])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for s in range(10):
-            roll.step(acts4[s % 8])
-            batch = roll.sample(n4)                 # n4 real + 4 x n4 "future"-relabelled transitions, rewards recomputed
+            roll.step(acts4[32 + s])
+            batch = roll.sample(5 * n4)             # n4 real + 4 x n4 "future"-relabelled transitions (n_sampled_goal = 4), rewards recomputed
         e1.record()
         torch.cuda.synchronize()
         ms4 = e0.elapsed_time(e1) / 10
-        extra["config4_goal_env_her"] = {"envs": n4, "relabel_batch": int(batch["reward"].numel()), "ms_per_step": ms4,
+        extra["config4_goal_env_her"] = {"envs": n4, "sample_batch": int(batch["reward"].numel()), "relabelled": int(batch["reward"].numel()) * 4 // 5, "ms_per_step": ms4,
                                          "value": n4 / ms4 * 1e3, "unit": "env-steps/s", "steps": 10,
                                          "through": "SO100GoalVecEnv + HerRollout (device-resident ring buffer, future relabelling)",
                                          "episodes": roll.stats()}
