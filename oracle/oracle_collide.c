@@ -521,6 +521,16 @@ int so100o_test_box_pair(const double* cA, const double* RA, const double* hA, c
   return nc * 16 + hit;
 }
 
+/* entry used by the tests to check the box-box manifold (points, depths, normal) against an independent computation */
+int so100o_test_box_manifold(const double* cA, const double* RA, const double* hA, const double* cB, const double* RB,
+                             const double* hB, double* normal_out, double* pos_out /* [8][3] */, double* dist_out /* [8] */) {
+  double cpos[8][3], cdist[8], normal[3] = {0, 0, 0};
+  int nc = box_box(cA, RA, hA, cB, RB, hB, cpos, cdist, normal);
+  copy3(normal_out, normal);
+  for (int k = 0; k < nc; k++) { copy3(pos_out + 3 * k, cpos[k]); dist_out[k] = cdist[k]; }
+  return nc;
+}
+
 void o_collide(const so100_model* m, oenv* e) {
   e->ncon = 0;
   for (int p = 0; p < m->npair; p++) {

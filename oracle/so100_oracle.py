@@ -189,6 +189,16 @@ def test_box_pair(cA, RA, hA, cB, RB, hB):
     return sat[:3], sat[3], epa[:3], epa[3], rc // 16, rc % 16
 
 
+def test_box_manifold(cA, RA, hA, cB, RB, hB):
+    """(normal geom1 -> geom2, contact points [n,3], dist [n]) of the oracle's box-box narrow phase (row-major R)."""
+    l = lib()
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (cA, RA, hA, cB, RB, hB)]
+    nrm = np.zeros(3); pos = np.zeros((8, 3)); dist = np.zeros(8)
+    n = l.so100o_test_box_manifold(*[_p(x) for x in a], _p(nrm), _p(pos), _p(dist))
+    return nrm, pos[:n].copy(), dist[:n].copy()
+
+
+test_box_manifold.__test__ = False
 test_reward.__test__ = False
 test_touch_reward.__test__ = False
 test_box_pair.__test__ = False

@@ -232,3 +232,107 @@ def test_hull_contacts_match_qhull_minkowski_depth(model_blob, model_rec):
         o.close()
     print(f"qhull check: {checked} hull contacts, {normals} with a unique nearest facet")
     assert checked >= 30 and normals >= 15
+
+
+def test_box_manifold_matches_independent_clipping():
+    """The box-box contact MANIFOLD (SAT + Sutherland-Hodgman in the oracle, SAT + 24 candidate points in the CUDA path, which the
+    GPU parity tests compare with the oracle point by point) against a computation that shares nothing with either:
+      * normal and depth = nearest facet of the Minkowski difference of the two boxes' corners, from qhull;
+      * contact polygon = reference-face rectangle intersected with the projected incident face, from
+        scipy.spatial.HalfspaceIntersection (qhull's dual) -- its vertices that lie below the reference face, lifted half their
+        depth along the normal, must be exactly the oracle's contact points, with the same per-point depths.
+    Face-face manifolds only (the axis preference of 5 % / 2 um documented in DESIGN.md can pick a face where qhull's nearest
+    facet is an edge-edge one; those cases are skipped, edge contacts are covered by test_sat_equals_epa_on_boxes)."""
+    from scipy.spatial import ConvexHull, HalfspaceIntersection
+    rng = np.random.default_rng(11)
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], float)
+    checked = multi = 0
+    for trial in range(600):
+        hA, hB = rng.uniform(0.01, 0.05, 3), rng.uniform(0.01, 0.05, 3)
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        RA = quat_to_mat(q)
+        # B nearly face-aligned with A (small relative tilt): face-face manifolds with 3..8 points
+        axes = np.eye(3)[rng.permutation(3)] * rng.choice([-1, 1], size=(3, 1))
+        tilt = rng.normal(size=4) * (0.04 if trial % 2 else 0.002); tilt[0] = 1; tilt /= np.linalg.norm(tilt)
+        RB = RA @ axes.T @ quat_to_mat(tilt)
+        if np.linalg.det(RB) < 0:
+            RB[:, 2] *= -1
+        k = rng.integers(3)
+        sgn = rng.choice([-1, 1])
+        extB = np.abs(RB.T @ RA[:, k]) @ hB                  # half extent of B along A's axis k
+        off = rng.uniform(-0.6, 0.6, 3) * hA
+        off[k] = sgn * (hA[k] + extB - rng.uniform(2e-4, 3e-3))
+        cA = rng.uniform(-0.1, 0.1, 3)
+        cB = cA + RA @ off
+        nrm, pos, dist = O.test_box_manifold(cA, RA.ravel(), hA, cB, RB.ravel(), hB)
+        if len(pos) == 0:
+            continue
+        # ---- independent normal / depth: nearest facet of A (-) B
+        VA, VB = cA + (corners * hA) @ RA.T, cB + (corners * hB) @ RB.T
+        hull = ConvexHull((VA[:, None, :] - VB[None, :, :]).reshape(-1, 3))
+        offs = hull.equations[:, 3]
+        assert (offs < 1e-12).all()
+        best = int(np.argmax(offs))
+        depth, nq = -offs[best], hull.equations[best, :3]
+        # face axis of A or B?  (otherwise qhull's nearest facet is an edge-edge one: skipped)
+        face = [(0, j) for j in range(3) if abs(abs(nq @ RA[:, j]) - 1) < 1e-9] + [(1, j) for j in range(3) if abs(abs(nq @ RB[:, j]) - 1) < 1e-9]
+        if not face or abs(abs(nq @ nrm) - 1) > 1e-9:
+            continue
+        assert abs(depth - (-dist.min())) < 1e-10, (trial, depth, dist)
+        assert nrm @ (cB - cA) > 0                                        # geom1 -> geom2
+        # ---- independent polygon: reference face rectangle (of the box that owns the normal) x projected incident face
+        ref_is_A = face[0][0] == 0
+        cR, RR, hR = (cA, RA, hA) if ref_is_A else (cB, RB, hB)
+        cI, RI, hI = (cB, RB, hB) if ref_is_A else (cA, RA, hA)
+        nref = nrm if ref_is_A else -nrm                                  # outward normal of the reference face
+        ax = int(np.argmax(np.abs(RR.T @ nref)))
+        u, v = RR[:, (ax + 1) % 3], RR[:, (ax + 2) % 3]
+        hu, hv = hR[(ax + 1) % 3], hR[(ax + 2) % 3]
+        iax = int(np.argmax(np.abs(RI.T @ nref)))
+        isg = -np.sign(RI[:, iax] @ nref)
+        fc = cI + isg * hI[iax] * RI[:, iax]
+        eu, ev = RI[:, (iax + 1) % 3] * hI[(iax + 1) % 3], RI[:, (iax + 2) % 3] * hI[(iax + 2) % 3]
+        quad3 = np.array([fc + eu + ev, fc - eu + ev, fc - eu - ev, fc + eu - ev])
+        quad = np.stack([(quad3 - cR) @ u, (quad3 - cR) @ v], axis=1)
+        hs = [[1, 0, -hu], [-1, 0, -hu], [0, 1, -hv], [0, -1, -hv]]
+        ctr = quad.mean(axis=0)
+        for a, b in zip(quad, np.roll(quad, -1, axis=0)):
+            e = b - a
+            nn = np.array([e[1], -e[0]]); nn /= np.linalg.norm(nn)
+            if nn @ (ctr - a) > 0:
+                nn = -nn
+            hs.append([nn[0], nn[1], -(nn @ a)])
+        hs = np.array(hs)
+        # interior point: Chebyshev centre by a tiny LP
+        from scipy.optimize import linprog
+        res = linprog([0, 0, -1], A_ub=np.hstack([hs[:, :2], np.ones((len(hs), 1))]), b_ub=-hs[:, 2], bounds=[(None, None)] * 2 + [(0, None)])
+        if res.status != 0 or res.x[2] < 1e-6:
+            continue                                                      # sliver overlap: vertex set ill-conditioned
+        poly = HalfspaceIntersection(hs, res.x[:2]).intersections
+        # incident plane height above each polygon vertex, depth below the reference face
+        ni = np.cross(quad3[1] - quad3[0], quad3[3] - quad3[0])
+        pts, deps = [], []
+        for pu, pv in poly:
+            base = cR + pu * u + pv * v
+            tpar = ((quad3[0] - base) @ ni) / (nref @ ni)                 # base + t nref on the incident plane
+            d = hR[ax] - tpar
+            if d > 1e-9:
+                pts.append(base + (tpar + 0.5 * d) * nref); deps.append(d)
+        pts, deps = np.array(pts), np.array(deps)
+        # de-duplicate qhull's repeated vertices
+        keep = []
+        for i, p in enumerate(pts):
+            if all(np.linalg.norm(p - pts[j]) > 1e-9 for j in keep):
+                keep.append(i)
+        pts, deps = pts[keep], deps[keep]
+        near_zero = np.sum(np.abs(deps) < 1e-7) + np.sum(np.abs(dist) < 1e-7)
+        if near_zero:
+            continue                                                      # a vertex within 1e-7 m of the reference plane: either answer is right
+        assert len(pts) == len(pos), (trial, len(pts), len(pos))
+        for p, d in zip(pos, dist):
+            j = int(np.argmin(np.linalg.norm(pts - p, axis=1)))
+            assert np.linalg.norm(pts[j] - p) < 1e-9 and abs(deps[j] + d) < 1e-9, (trial, p, pts[j], d, deps[j])
+        checked += 1
+        multi += len(pos) >= 4
+    print(f"box manifold check: {checked} face-face manifolds, {multi} with >= 4 points")
+    assert checked >= 150 and multi >= 80
