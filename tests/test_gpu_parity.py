@@ -52,11 +52,15 @@ def test_forward_parity(model_blob, name):
     """mj_forward: contact list (geoms, dist, pos, normal), qacc and contact forces."""
     errs = _per_env_forward(model_blob, name)
     worst = {k: max(e[k] for e in errs) for k in errs[0]}
-    # penetration depth: float32 positions of O(0.5 m) -> 1e-6 m; normals: exact for box faces, ~1e-4 from float32 EPA
-    assert worst["dist"] < 2e-6, worst
+    # Tolerances = about 3x the worst case measured on B200 (tests/dev/gpu_tolerance_report.py, 64 envs per scenario):
+    #   penetration depth 1.8e-7 m (float32 positions of O(0.5 m)); normals exact for box faces, 8e-5 from the float32 EPA;
+    #   contact point 4e-7 m; contact force relative to max(1 N, |f|): 3.3e-4 box contacts, 2.2e-3 grasps (stiff pad contacts, solimp
+    #   0.9999); qacc relative to (1 + |qacc|): 4e-6 contact-free, 2.9e-4 box contacts / limits, 1.3e-3 grasps
+    assert worst["dist"] < 5e-7, worst
     assert worst["normal"] < (2e-4 if name in HULL else 2e-5), worst
-    tol_q = 2e-4 if name in CONTACT_FREE else 2e-3       # relative to (1 + |qacc|)
-    ok = [e["pos"] < 2e-5 and e["force"] < 5e-3 and e["qacc"] < tol_q for e in errs]
+    tol_q = 2e-5 if name in CONTACT_FREE else (2e-3 if name in HULL else 6e-4)
+    tol_f = 3e-3 if name in HULL else 1e-3
+    ok = [e["pos"] < 2e-6 and e["force"] < tol_f and e["qacc"] < tol_q for e in errs]
     if name in HULL:
         assert np.mean(ok) >= 0.95, (name, float(np.mean(ok)), worst)
     else:
@@ -73,7 +77,8 @@ def test_single_substep_parity(model_blob, name):
     sim.substeps(1)
     qp_o, qv_o, _, _ = orc.get_state()
     qp_g, qv_g, _, _ = [t.cpu().numpy().astype(np.float64) for t in sim.get_state()]
-    tol_v = 1e-5 if name in CONTACT_FREE else 1e-4     # relative to (1 + |v|)
+    # relative to (1 + |v|); measured worst cases 3.4e-8 contact-free, 1.9e-5 box contacts / limits, 6.7e-5 grasps
+    tol_v = 2e-7 if name in CONTACT_FREE else (1e-4 if name in HULL else 5e-5)
     ev = np.array([rel_err(qv_g[i], qv_o[i], floor=1.0) for i in range(N)])
     ep = np.abs(qp_g - qp_o).max(axis=1)                # h * dv plus float32 rounding of qpos
     ok = (ev < tol_v) & (ep < 2e-6)
