@@ -280,13 +280,16 @@ class SB3VecEnvAdapter:
         self.venv.close()
 
 
-def make(env_id: str, num_envs: int, **kw):
-    """Batched counterpart of ``gym.make`` for the registered ids (gym_so100/__init__.py:4-32)."""
+def make(env_id: str, num_envs: int, obs_type: str = "so100_pixels_agent_pos", **kw):
+    """Batched counterpart of ``gym.make`` for the registered ids (gym_so100/__init__.py:4-32).  The registered default
+    ``obs_type`` is the pixel observation (__init__.py:11,21,31), which this engine does not render: like the reference's
+    kwargs it has to be overridden explicitly, ``make(id, n, obs_type="so100_state")``; the default raises NotImplementedError
+    rather than quietly handing out a different observation."""
     ids = {"SO100CubeToBin-v0": "so100_cube_to_bin", "SO100TouchCube-v0": "so100_touch_cube",
            "SO100TouchCubeSparse-v0": "so100_touch_cube_sparse"}
     name = env_id.split("/")[-1]
     if name in ids:
-        return SO100VecEnv(num_envs, task=ids[name], **kw)
+        return SO100VecEnv(num_envs, task=ids[name], obs_type=obs_type, **kw)
     if name in ("SO100Goal-v0", "SO100GoalEnv"):
-        return SO100GoalVecEnv(num_envs, **kw)
+        return SO100GoalVecEnv(num_envs, **kw)          # the GoalEnv class is not registered and has no obs_type (env.py:191-198)
     raise NotImplementedError(f"{env_id}: not one of the registered ids (gym_so100/__init__.py:4-32) or the GoalEnv")

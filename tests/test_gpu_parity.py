@@ -446,11 +446,13 @@ def test_make_ids_and_sb3_terminal_observation(model_blob):
     from gym_so100_c_b200 import vec_env
     for env_id, limit in (("gym_so100/SO100CubeToBin-v0", 700), ("gym_so100/SO100TouchCube-v0", 300),
                           ("gym_so100/SO100TouchCubeSparse-v0", 300)):
-        env = vec_env.make(env_id, 4)
+        env = vec_env.make(env_id, 4, obs_type="so100_state")
         assert env.max_episode_steps == limit
         env.close()
+        with pytest.raises(NotImplementedError):          # the registered default is the pixel observation: never silently replaced
+            vec_env.make(env_id, 4)
     with pytest.raises(NotImplementedError):
-        vec_env.make("gym_so100/SO100Nope-v0", 4)
+        vec_env.make("gym_so100/SO100Nope-v0", 4, obs_type="so100_state")
     env = vec_env.SO100GoalVecEnv(6, seed=3)
     ad = vec_env.SB3VecEnvAdapter(env)
     first = ad.reset()
