@@ -15,6 +15,7 @@
 namespace so100 { constexpr int SO100_NDIAG_K = SO100_NDIAG; }
 #include "so100_phases.cuh"
 #include "so100_her.cuh"
+#include "so100_render.cuh"
 
 using namespace so100;
 
@@ -127,6 +128,12 @@ struct so100_ctx {
   int32_t* ep_length = nullptr;
   std::vector<std::array<const void*, 8>> host_sets;   // page-locked destination sets of so100_step_host seen so far
   double* ep_stats = nullptr;  // device [4] scratch of so100_episode_stats
+  // renderer (so100_render_config / so100_render)
+  bool render_ready = false;
+  RenderCfg rcfg;
+  float4* r_planes = nullptr;
+  int *r_adr = nullptr, *r_num = nullptr;
+  float* r_rgb = nullptr;
   cudaStream_t cap = nullptr;
   float* act_stage = nullptr;
   bool use_graph = true;
@@ -840,6 +847,7 @@ int so100_destroy(so100_handle h) {
   for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
   cudaFree(h->s_obs); cudaFree(h->s_ag); cudaFree(h->s_dg); cudaFree(h->s_rew); cudaFree(h->s_fin);
   cudaFree(h->s_term); cudaFree(h->s_trunc); cudaFree(h->s_succ); cudaFree(h->ep_stats);
+  cudaFree(h->r_planes); cudaFree(h->r_adr); cudaFree(h->r_num); cudaFree(h->r_rgb);
   if (h->cap) cudaStreamDestroy(h->cap);
   cudaFree(h->act_stage);
   cudaFree(h->h_action); cudaFree(h->h_obs); cudaFree(h->h_ag); cudaFree(h->h_dg); cudaFree(h->h_rew); cudaFree(h->h_fin);
@@ -1387,6 +1395,52 @@ int so100_her_sample(const so100_her_ring* ring, int64_t batch, int32_t n_sample
   her_sample_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(R, batch, n_sampled_goal, threshold, (uint32_t)seed,
                                                                                        (uint32_t)(seed >> 32), call, obs, action, next_obs,
                                                                                        achieved, next_achieved, desired, reward, done, index);
+  CUDA_OK(cudaGetLastError());
+  return SO100_OK;
+}
+
+int so100_render_config(so100_handle h, const float* planes, int32_t nplanes, const int32_t* geom_plane_adr, const int32_t* geom_plane_num,
+                        const float* geom_rgb, const float* camera13, const float* lights, int32_t nlights, float ambient, float head_diffuse,
+                        int32_t width, int32_t height) {
+  if (!h || !geom_plane_adr || !geom_plane_num || !geom_rgb || !camera13 || nplanes < 0 || (nplanes > 0 && !planes) || width <= 0 || height <= 0 ||
+      nlights < 0 || nlights > 4 || (nlights > 0 && !lights))
+    return fail(SO100_ERR_ARG, "so100_render_config: bad argument");
+  for (int g = 0; g < NGEOM; g++)
+    if (geom_plane_num[g] > 0 && (geom_plane_adr[g] < 0 || geom_plane_adr[g] + geom_plane_num[g] > nplanes))
+      return fail(SO100_ERR_ARG, "so100_render_config: plane range outside the table");
+  DeviceGuard guard(h->device);
+  cudaFree(h->r_planes); cudaFree(h->r_adr); cudaFree(h->r_num); cudaFree(h->r_rgb);
+  h->r_planes = nullptr; h->r_adr = nullptr; h->r_num = nullptr; h->r_rgb = nullptr; h->render_ready = false;
+  CUDA_OK(cudaMalloc(&h->r_planes, std::max(nplanes, 1) * sizeof(float4)));
+  CUDA_OK(cudaMalloc(&h->r_adr, NGEOM * sizeof(int)));
+  CUDA_OK(cudaMalloc(&h->r_num, NGEOM * sizeof(int)));
+  CUDA_OK(cudaMalloc(&h->r_rgb, NGEOM * 3 * sizeof(float)));
+  if (nplanes > 0) CUDA_OK(cudaMemcpy(h->r_planes, planes, (size_t)nplanes * sizeof(float4), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(h->r_adr, geom_plane_adr, NGEOM * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(h->r_num, geom_plane_num, NGEOM * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(h->r_rgb, geom_rgb, NGEOM * 3 * sizeof(float), cudaMemcpyHostToDevice));
+  RenderCfg& C = h->rcfg;
+  memset(&C, 0, sizeof(C));
+  C.width = width; C.height = height;
+  for (int k = 0; k < 3; k++) { C.cam_pos[k] = camera13[k]; C.cam_x[k] = camera13[3 + k]; C.cam_y[k] = camera13[6 + k]; C.cam_z[k] = camera13[9 + k]; }
+  C.tan_half_fovy = tanf(0.5f * camera13[12] * 3.14159265358979f / 180.0f);
+  C.ambient = ambient; C.head_diffuse = head_diffuse; C.nlight = nlights;
+  for (int l = 0; l < nlights; l++) {
+    const float* L = lights + 4 * l;
+    const float len = std::sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+    for (int k = 0; k < 3; k++) C.light_dir[l][k] = len > 0 ? L[k] / len : 0.0f;
+    C.light_diffuse[l] = L[3];
+  }
+  h->render_ready = true;
+  return SO100_OK;
+}
+
+int so100_render(so100_handle h, uint8_t* pixels, void* stream) {
+  if (!h || !pixels) return fail(SO100_ERR_ARG, "so100_render: bad argument");
+  if (!h->render_ready) return fail(SO100_ERR_ARG, "so100_render: call so100_render_config first");
+  DeviceGuard guard(h->device);
+  const RenderTables R{h->r_planes, h->r_adr, h->r_num, h->r_rgb};
+  render_kernel<<<h->n, 128, 0, (cudaStream_t)stream>>>(h->state, h->n, h->rcfg, h->tables(), R, pixels);
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }

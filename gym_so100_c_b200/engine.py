@@ -39,6 +39,7 @@ class BatchedSim:
         self.n = int(num_envs)
         self.task = int(task)
         blob = model_blob if model_blob is not None else _model.pack(_model.load_model())
+        self._blob = blob
         h = C.c_void_p()
         ext.check(self.lib.so100_create(blob, len(blob), self.n, index, self.task, C.c_uint64(seed & (2**64 - 1)),
                                         C.c_int64(env_offset), C.byref(h)), "so100_create")
@@ -207,6 +208,30 @@ class BatchedSim:
                                               cnt.ctypes.data_as(C.c_void_p) if read else None, self._stream()), "so100_phase_timing")
         names = ["kin_dyn", "collide_box", "solve_light", "task", "collide_hull", "solve_heavy"]
         return dict(zip(names, ms.tolist())), dict(zip(names, cnt.tolist()))
+
+    # ------------------------------------------------------------------ renderer (obs_type "so100_pixels_agent_pos")
+    def configure_render(self, width: int, height: int, camera: str = "top"):
+        """Scene tables + camera for so100_render (render.py).  Must be called once before `render`."""
+        from . import render as _render
+        if camera not in _render.CAMERAS:
+            raise ValueError(f"camera {camera!r}: one of {sorted(_render.CAMERAS)} (scene_so100.xml:26-29)")
+        m = _model.unpack(self._blob)
+        planes, adr, num, rgb = _render.scene_tables(m)
+        pos, x, y, z = _render.camera_frame(*_render.CAMERAS[camera][:2])
+        cam = np.concatenate([pos, x, y, z, [_render.CAMERAS[camera][2]]]).astype(np.float32)
+        lights = np.ascontiguousarray(_render.LIGHTS, dtype=np.float32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        ext.check(self.lib.so100_render_config(self.h, p(planes), int(planes.shape[0]), p(adr), p(num), p(rgb), p(cam), p(lights),
+                                               int(lights.shape[0]), C.c_float(_render.HEAD_AMBIENT), C.c_float(_render.HEAD_DIFFUSE),
+                                               int(width), int(height)), "so100_render_config")
+        self.pixels = torch.zeros((self.n, int(height), int(width), 3), dtype=torch.uint8, device=self.device)
+
+    def render(self) -> torch.Tensor:
+        """uint8 [N, H, W, 3]: every env's current state seen by the configured camera."""
+        if getattr(self, "pixels", None) is None:
+            raise ext.So100Error("call configure_render(width, height) first")
+        ext.check(self.lib.so100_render(self.h, _ptr(self.pixels), self._stream()), "so100_render")
+        return self.pixels
 
     def episode_stats(self) -> Dict[str, float]:
         """Episodes finished, successes, sum of episode returns and lengths over all envs since construction."""

@@ -17,7 +17,7 @@ SYMBOLS = [
     "so100_compute_reward", "so100_get_state", "so100_set_state", "so100_get_aux", "so100_set_aux",
     "so100_substeps", "so100_forward", "so100_diagnostics", "so100_phase_timing", "so100_group_times", "so100_debug_read", "so100_last_error",
     "so100_measure_fp32_peak", "so100_set_episode_outputs", "so100_episode_stats", "so100_graph_stats",
-    "so100_her_begin", "so100_her_commit", "so100_her_sample",
+    "so100_her_begin", "so100_her_commit", "so100_her_sample", "so100_render_config", "so100_render",
 ]
 
 MAX_CONTACTS = 24
@@ -76,6 +76,8 @@ def load():
     lib.so100_set_episode_outputs.argtypes = [vp, vp, vp]
     lib.so100_episode_stats.argtypes = [vp, vp, vp]
     lib.so100_graph_stats.argtypes = [vp, vp, vp, vp]
+    lib.so100_render_config.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, C.c_float, C.c_float, i32, i32]
+    lib.so100_render.argtypes = [vp, vp, vp]
     ring = C.POINTER(HerRing)
     lib.so100_her_begin.argtypes = [ring, i32, vp, vp, vp, vp, vp]
     lib.so100_her_commit.argtypes = [ring, i32, vp, vp, vp, vp, vp, vp, vp]

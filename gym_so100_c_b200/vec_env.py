@@ -10,7 +10,8 @@ Mirrors (names, argument meaning, returned tuple shapes, error behaviour):
 
 All returned arrays are device-resident ``torch`` tensors owned by the env and overwritten by
 the next call (the reference returns fresh numpy copies; copy if you keep them).  Declared
-deviations: no renderer, so ``obs_type`` must be ``"so100_state"`` and the
+deviations: ``obs_type="so100_pixels_agent_pos"`` is drawn by a low-resolution
+ray-caster over the collision geometry (render.py), not by MuJoCo's OpenGL renderer, and the
 GoalEnv ``"observation"`` entry is the 15-float state vector instead of flattened pixels.
 """
 from __future__ import annotations
@@ -95,22 +96,46 @@ class SO100VecEnv(_VecBase):
     TASKS = {"so100_cube_to_bin": (ext.TASK_CUBE_TO_BIN, 700), "so100_touch_cube": (ext.TASK_TOUCH_CUBE, 300),
              "so100_touch_cube_sparse": (ext.TASK_TOUCH_CUBE_SPARSE, 300)}
 
-    def __init__(self, num_envs: int, task: str = "so100_cube_to_bin", obs_type: str = "so100_state", **kw):
+    def __init__(self, num_envs: int, task: str = "so100_cube_to_bin", obs_type: str = "so100_state",
+                 observation_width: int = 640, observation_height: int = 480, **kw):
         if task not in self.TASKS:
             raise NotImplementedError(task)           # env.py:117-118
-        if obs_type != "so100_state":
-            raise NotImplementedError(f"obs_type {obs_type!r}: the batched engine has no renderer (so100_state only)")
+        if obs_type not in ("so100_state", "so100_pixels_agent_pos"):
+            raise NotImplementedError(f"obs_type {obs_type!r}")
         self._task, self.max_episode_steps = self.TASKS[task]     # __init__.py:7,17,27
         super().__init__(num_envs, **kw)
         self.task = task
         self.obs_type = obs_type
-        self.single_observation_space = Box(low=-100.0, high=100.0, shape=(15,), dtype=np.float32)   # env.py:67-73
-        self.observation_space = batch_box(self.single_observation_space, self.num_envs)
+        self.observation_width, self.observation_height = int(observation_width), int(observation_height)   # env.py:34-35
+        if obs_type == "so100_state":
+            self.single_observation_space = Box(low=-100.0, high=100.0, shape=(15,), dtype=np.float32)   # env.py:67-73
+            self.observation_space = batch_box(self.single_observation_space, self.num_envs)
+        else:
+            # env.py:50-66: the "top" camera image + the six joint angles.  Drawn by the library's low-resolution ray-caster over
+            # the collision geometry (render.py), NOT MuJoCo's OpenGL renderer: use it at the resolutions
+            # the reference's own example uses (64 x 48, scripts/example.py:13-14), not to compare pixels with MuJoCo.
+            self.sim.configure_render(self.observation_width, self.observation_height, camera="top")
+            self.single_observation_space = DictSpace({
+                "pixels": Box(low=0, high=255, shape=(self.observation_height, self.observation_width, 3), dtype=np.uint8),
+                "agent_pos": Box(low=-10.0, high=10.0, shape=(6,), dtype=np.float32)})
+            self.observation_space = DictSpace({k: batch_box(sp, self.num_envs) for k, sp in self.single_observation_space.items()})
+
+    def _format(self, obs):
+        """env.py:130-146 on the batch."""
+        if self.obs_type == "so100_state":
+            return obs
+        return {"pixels": self.sim.render(), "agent_pos": obs[:, 9:15]}
+
+    def render(self):
+        """Batched ``render()`` (env.py:79-90): uint8 [num_envs, H, W, 3] from the "top" camera at the observation size."""
+        if getattr(self.sim, "pixels", None) is None:
+            self.sim.configure_render(self.observation_width, self.observation_height, camera="top")
+        return self.sim.render()
 
     def reset(self, seed=None, options: Optional[dict] = None):
         obs, _, _ = self.sim.reset(mask=self._mask(options), box_pose=self._box_poses(seed))
         infos = {"is_success": torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)}   # env.py:169
-        return obs, infos
+        return self._format(obs), infos
 
     def step(self, actions):
         if getattr(actions, "ndim", 2) != 2:
@@ -122,7 +147,7 @@ class SO100VecEnv(_VecBase):
             infos["final_obs"] = self.sim.final_obs
             infos["_final_obs"] = term_b | trunc_b
         infos["TimeLimit.truncated"] = trunc_b & ~term_b
-        return obs, reward, term_b, trunc_b, infos
+        return self._format(obs), reward, term_b, trunc_b, infos
 
 
 class SO100GoalVecEnv(_VecBase):

@@ -155,6 +155,19 @@ int so100_her_sample(const so100_her_ring* ring, int64_t batch, int32_t n_sample
                      float* obs, float* action, float* next_obs, float* achieved, float* next_achieved, float* desired, float* reward,
                      uint8_t* done, int32_t* index, void* stream);
 
+/* Replaces (approximately -- see DESIGN.md section 11): physics.render(height, width, camera_id="top") behind obs_type
+ * "so100_pixels_agent_pos" (gym_so100/env.py:50-66, 79-90, 130-136; gym_so100/tasks/single_arm.py:87-91).  A ray-caster over the
+ * scene's collision geometry, not MuJoCo's OpenGL pipeline.  so100_render_config (host arrays, copied): `planes` float32
+ * [nplanes,4] = body-frame facets n.x <= w of the convex hulls; per collidable geom (library order, 25 entries) the first plane and
+ * the plane count (> 0 hull, 0 = box geom drawn from its size, < 0 = not drawn) and an rgb colour; `camera13` = position, x (right),
+ * y (up), z (backward) axes in the world and fovy in degrees; `lights` float32 [nlights,4] = direction of travel + diffuse
+ * intensity (nlights <= 4); headlight ambient / diffuse.  so100_render writes uint8 [N, height, width, 3] (device) for the current
+ * state of every env. */
+int so100_render_config(so100_handle h, const float* planes, int32_t nplanes, const int32_t* geom_plane_adr,
+                        const int32_t* geom_plane_num, const float* geom_rgb, const float* camera13, const float* lights,
+                        int32_t nlights, float ambient, float head_diffuse, int32_t width, int32_t height);
+int so100_render(so100_handle h, uint8_t* pixels, void* stream);
+
 /* Step-graph cache of this handle (host ints, any may be NULL): graphs captured since create, graphs cached now, and whether
  * the handle has switched to staging outputs because the caller keeps rotating its output pointers (so100_b200.cu). */
 int so100_graph_stats(so100_handle h, int32_t* captures, int32_t* cached, int32_t* staged);

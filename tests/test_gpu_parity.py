@@ -449,8 +449,10 @@ def test_make_ids_and_sb3_terminal_observation(model_blob):
         env = vec_env.make(env_id, 4, obs_type="so100_state")
         assert env.max_episode_steps == limit
         env.close()
-        with pytest.raises(NotImplementedError):          # the registered default is the pixel observation: never silently replaced
-            vec_env.make(env_id, 4)
+        px = vec_env.make(env_id, 4, observation_width=32, observation_height=24)     # the registered default: pixel observations
+        o, _ = px.reset()
+        assert set(o) == {"pixels", "agent_pos"} and o["pixels"].shape == (4, 24, 32, 3) and o["agent_pos"].shape == (4, 6)
+        px.close()
     with pytest.raises(NotImplementedError):
         vec_env.make("gym_so100/SO100Nope-v0", 4, obs_type="so100_state")
     env = vec_env.SO100GoalVecEnv(6, seed=3)
@@ -787,4 +789,42 @@ def test_her_rollout_matches_host_replay(model_blob):
     assert relabel_changed > 0          # hindsight really turns some failures into successes (the final step always does)
     st = roll.stats()
     assert st["episodes"] == int(sum(l["done"].sum() for l in log)) and 299.0 <= st["ep_len_mean"] <= 300.0     # lengths count env steps (set_aux placed them near 300)
+    env.close()
+
+
+def test_pixel_observation_matches_numpy_raycaster(model_blob, model_rec):
+    """obs_type "so100_pixels_agent_pos" (env.py:50-66, 130-136): the device ray-caster against the float64 numpy restatement
+    of the same renderer (gym_so100_c_b200/render.py: render_numpy) on the states of a short rollout.  The two may disagree
+    only at silhouette pixels (float32 vs float64 ray / facet arithmetic): >= 98.5 % of the pixels equal within 1 grey level,
+    the table / cube / arm are all visible, and the red cube's pixels sit where the camera model projects the cube."""
+    import torch
+    from gym_so100_c_b200 import render
+    from gym_so100_c_b200.vec_env import SO100VecEnv
+    n, W, H = 6, 64, 48
+    env = SO100VecEnv(n, obs_type="so100_pixels_agent_pos", observation_width=W, observation_height=H, seed=4)
+    obs, _ = env.reset(seed=10)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for k in range(12):
+        obs, rew, term, trunc, info = env.step(torch.rand((n, 6), device="cuda", generator=g) * 2 - 1)
+    assert obs["pixels"].dtype == torch.uint8 and obs["pixels"].shape == (n, H, W, 3)
+    qpos = env.get_state()[0].cpu().numpy().astype(np.float64)
+    np.testing.assert_array_equal(obs["agent_pos"].cpu().numpy(), qpos[:, :6].astype(np.float32))
+    pix = obs["pixels"].cpu().numpy().astype(int)
+    cube, table = int(model_rec["cg_cube"]), int(model_rec["cg_table"])
+    seen_cube = 0
+    for i in range(n):
+        ref, hit = render.render_numpy(model_rec, qpos[i], W, H)
+        same = (np.abs(pix[i] - ref.astype(int)).max(axis=-1) <= 1)
+        assert same.mean() >= 0.985, (i, float(same.mean()))
+        assert (hit == table).sum() > 800 and (hit >= 0).sum() > (hit == table).sum() + 30       # table, and arm / bin on top of it
+        red = (pix[i][..., 0] > 100) & (pix[i][..., 1] < 30) & (pix[i][..., 2] < 30)
+        assert np.array_equal(red & same, (hit == cube) & same)
+        if (hit == cube).sum() >= 3:
+            seen_cube += 1
+            rows, cols = np.nonzero(red)
+            th, asp, cz = np.tan(np.deg2rad(39.0)), W / H, 0.8 - qpos[i, 8]
+            col = ((qpos[i, 6] - 0.0) / (th * asp * cz) + 1) / 2 * W - 0.5              # camera at (0, 0.6, 0.8), x right, y up
+            row = (1 - (qpos[i, 7] - 0.6) / (th * cz)) / 2 * H - 0.5
+            assert abs(cols.mean() - col) < 1.5 and abs(rows.mean() - row) < 1.5, (i, cols.mean(), col, rows.mean(), row)
+    assert seen_cube >= 3
     env.close()

@@ -70,7 +70,7 @@ def test_create_fails_loudly_without_gpu(model_blob):
     rc = lib.so100_create(model_blob, len(model_blob), 4, 0, 7, C.c_uint64(0), C.c_int64(0), C.byref(h))
     assert rc == -1 and b"unknown task" in lib.so100_last_error()
     with pytest.raises(NotImplementedError):
-        SO100VecEnv(4, obs_type="so100_pixels_agent_pos")
+        SO100VecEnv(4, obs_type="so100_pixels")               # not one of env.py:50-73's two observation types
 
 
 def test_spaces_shim():
@@ -179,3 +179,29 @@ def test_lazy_infos_behave_like_a_list_of_dicts():
     flat = _LazyInfos(succ=done, timeout=done, done=done, final=final, goal_env=False, prev_desired=None,
                       ep_return=np.zeros(n, np.float32), ep_length=np.zeros(n, np.int32))
     assert np.array_equal(flat[1]["terminal_observation"], final[1])
+
+
+def test_render_tables_are_consistent(model_rec):
+    """Renderer scene tables (render.scene_tables): every hull's facet planes contain all of its vertices and each is touched by
+    at least three of them; pads are not drawn; the camera frames follow MuJoCo's targetbody rule."""
+    import numpy as np
+    from gym_so100_c_b200 import render
+    m = model_rec
+    planes, adr, num, rgb = render.scene_tables(m)
+    assert (num[[g for g in range(int(m["ngeom"])) if (int(m["pad_mask"]) >> g) & 1]] == -1).all() and (num == -1).sum() == 8
+    assert num[int(m["cg_cube"])] == 0 and num[int(m["cg_table"])] == 0 and tuple(rgb[int(m["cg_cube"])]) == (1.0, 0.0, 0.0)
+    for g in range(int(m["ngeom"])):
+        if num[g] <= 0:
+            continue
+        a = int(m["geom_vadr"][g])
+        V = np.asarray(m["vert"][a:a + int(m["geom_vnum"][g])], float)
+        P = planes[adr[g]:adr[g] + num[g]].astype(float)
+        h = V @ P[:, :3].T - P[:, 3]                       # signed height of every vertex over every plane
+        assert h.max() < 2e-6 and ((np.abs(h) < 2e-6).sum(axis=0) >= 3).all(), g
+        assert np.abs(np.linalg.norm(P[:, :3], axis=1) - 1).max() < 1e-5
+    pos, x, y, z = render.camera_frame(*render.CAMERAS["top"][:2])
+    assert np.allclose(x, [1, 0, 0]) and np.allclose(y, [0, 1, 0]) and np.allclose(z, [0, 0, 1])      # straight above the table
+    pos, x, y, z = render.camera_frame(*render.CAMERAS["angle"][:2])
+    assert abs(x @ z) < 1e-12 and abs(y @ z) < 1e-12 and np.allclose(np.cross(x, y), z) and abs(x[2]) < 1e-12
+    img, hit = render.render_numpy(m, np.concatenate([m["start_pose"][:6], [-0.2, 0.35, 0.02, 1, 0, 0, 0]]), 32, 24)
+    assert img.shape == (24, 32, 3) and (hit == int(m["cg_cube"])).any() and (hit == int(m["cg_table"])).sum() > 200
