@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
                               // blocks; measured on B200: 4 (128 registers, spills) -8 %, 5 (96 registers) -14 % env-steps/s)
 #endif
 #ifndef SO100_K3M_MINB
-#define SO100_K3M_MINB 3      // the same for the medium instantiation
+#define SO100_K3M_MINB 4      // the same for the medium instantiation: 128 registers without spills since the Cholesky factors moved out of local
+                              // memory (round 2; 3 blocks = 160 registers: +1.5 % step time when a policy holds thousands of cubes)
 #endif
 // `which` (medium instantiation only): 0 = medium queue a (complete after K2a), 1 = medium queue b (complete after K2b)
 template <unsigned LPE, int NCAP>
