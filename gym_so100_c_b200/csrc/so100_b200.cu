@@ -21,7 +21,7 @@ using namespace so100;
 
 static_assert(NC == SO100_MAX_CONTACTS, "contact capacity mismatch");
 
-// lanes per env (tile width) of each phase kernel; the box collision stage needs >= 24 lanes (one per clipping candidate)
+// lanes per env (tile width) of each phase kernel
 #ifndef SO100_LPE_K1
 #define SO100_LPE_K1 16
 #endif
@@ -29,7 +29,11 @@ static_assert(NC == SO100_MAX_CONTACTS, "contact capacity mismatch");
 #define SO100_LPE_K3L 16     // two envs per warp in the light solve kernel (12 dof lanes + contact rows fit 16 lanes): measured on B200
                              // against one env per warp, both at their best register budget: +3 % env-steps/s at 16384 envs, +9.5 % at 65536
 #endif
-constexpr unsigned LPE_K1 = SO100_LPE_K1, LPE_K2A = 32, LPE_K2B = 32, LPE_K3L = SO100_LPE_K3L, LPE_K3H = 32, LPE_K4 = 32;
+#ifndef SO100_LPE_K2A
+#define SO100_LPE_K2A 16     // two envs per warp in the box collision stage too (one lane per geom / candidate pair; the 24 clipping
+                             // candidates of a box pair in two passes)
+#endif
+constexpr unsigned LPE_K1 = SO100_LPE_K1, LPE_K2A = SO100_LPE_K2A, LPE_K2B = 32, LPE_K3L = SO100_LPE_K3L, LPE_K3H = 32, LPE_K4 = 32;
 constexpr int BLOCK = 128, TPB_K3L = SO100_TPB_K3L;
 // grids of the queue-driven persistent kernels (4 tiles per block): large enough for one item per tile in a 2048-env group,
 // small enough that the blocks that find the queue empty do not crowd the SMs (the heavy solve kernel holds 27 k registers
@@ -433,7 +437,7 @@ static int configure_kernels(int device) {
   CUDA_OK(cudaFuncSetAttribute(phase_collide_box<LPE_K2A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<BoxS>(LPE_K2A)));
   CUDA_OK(cudaFuncSetAttribute(phase_collide_hull<LPE_K2B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<HullS>(LPE_K2B)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_light<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L)));
-  CUDA_OK(cudaFuncSetAttribute(phase_slow_lane<LPE_K1, LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLOW_SMEM));
+  CUDA_OK(cudaFuncSetAttribute(phase_slow_lane<LPE_K1, LPE_K2A, LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLOW_SMEM));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_light_queue<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NC>>(LPE_K3H)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H, NCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3H)));
@@ -611,7 +615,7 @@ static void launch_slow_lane(so100_ctx* h, EnvGroup& G, cudaStream_t st, int sta
     s_ = G.slow[k];
   }
   mark(h, s_, CLS_HEAVY, true);
-  launch_p(phase_slow_lane<LPE_K1, LPE_K3L>, grid, 32, SLOW_SMEM, s_, h->prio_high, state, work, h->tables(), h->queues(G), stage, nsub, trailing);
+  launch_p(phase_slow_lane<LPE_K1, LPE_K2A, LPE_K3L>, grid, 32, SLOW_SMEM, s_, h->prio_high, state, work, h->tables(), h->queues(G), stage, nsub, trailing);
   mark(h, s_, CLS_HEAVY, false);
   if (!h->timing) cudaEventRecord(G.slow_done[k], G.slow[k]);
 }

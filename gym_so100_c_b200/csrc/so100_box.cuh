@@ -100,7 +100,7 @@ __device__ __forceinline__ float sel_h(const Obb& b, int k) { return k == 0 ? b.
 template <unsigned LPE>
 __device__ int box_contacts(const Tile<LPE>& t, float* con, int base, const Obb& A, const Obb& B, int code, float sep, bool single,
                             int pair) {
-  static_assert(LPE >= 24, "box_contacts needs one lane per candidate point (24)");
+  static_assert(LPE == 16 || LPE == 32, "box_contacts: 24 candidate points over one pass of 32 lanes or two passes of 16");
   const int lane = t.thread_rank();
   const V3 tAB = B.c - A.c;
   if (code >= 6) {
@@ -151,10 +151,10 @@ __device__ int box_contacts(const Tile<LPE>& t, float* con, int base, const Obb&
       pu[q] = dot(p, axu); pv[q] = dot(p, axv); pn[q] = dot(p, nref);
     }
   }
-  bool valid = false;
-  float cu = 0, cv = 0, cn = 0;
-  {
-    const int k = lane;
+  // candidate point k of 24 (reference coordinates u, v, n): true when it is a vertex of the clipped incident polygon
+  auto candidate = [&](int k, float& cu, float& cv, float& cn) -> bool {
+    bool valid = false;
+    cu = 0; cv = 0; cn = 0;
     if (k < 4) {
       cu = k == 0 ? pu[0] : (k == 1 ? pu[1] : (k == 2 ? pu[2] : pu[3]));
       cv = k == 0 ? pv[0] : (k == 1 ? pv[1] : (k == 2 ? pv[2] : pv[3]));
@@ -197,19 +197,37 @@ __device__ int box_contacts(const Tile<LPE>& t, float* con, int base, const Obb&
         valid = fabsf(Nn) > 1e-20f;
       }
     }
-  }
-  const float depth = hn - cn;
-  valid = valid && depth > 0;
+    return valid;
+  };
+  // one candidate per lane and pass: a 32-lane tile needs one pass, a 16-lane tile two (candidates 0..15, then 16..23)
+  constexpr int PASSES = (24 + (int)LPE - 1) / (int)LPE;
   const V3 nout = refA ? nref : -nref;                          // always geom1 -> geom2
-  const V3 p = Rf.c + axu * cu + axv * cv + nref * (cn + 0.5f * depth);
+  bool valid[PASSES];
+  float depth[PASSES];
+  V3 p[PASSES];
+#pragma unroll
+  for (int ps = 0; ps < PASSES; ps++) {
+    float cu, cv, cn;
+    const int k = lane + ps * (int)LPE;
+    valid[ps] = k < 24 && candidate(k, cu, cv, cn);
+    depth[ps] = hn - cn;
+    valid[ps] = valid[ps] && depth[ps] > 0;
+    p[ps] = Rf.c + axu * cu + axv * cv + nref * (cn + 0.5f * depth[ps]);
+  }
   if (single) {
     // mjc_Convex semantics (one contact per pair): deepest feature, centroid if it is not a single vertex
-    float dmax = valid ? depth : -1.0f;
+    float dmax = -1.0f;
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ps++) dmax = fmaxf(dmax, valid[ps] ? depth[ps] : -1.0f);
 #pragma unroll
     for (int off = LPE / 2; off > 0; off >>= 1) dmax = fmaxf(dmax, t.shfl_xor(dmax, off));
     if (dmax <= 0) return 0;
-    const bool deep = valid && depth >= dmax - 1e-6f;
-    float sx = deep ? p.x : 0, sy = deep ? p.y : 0, sz = deep ? p.z : 0, cnt = deep ? 1.0f : 0.0f;
+    float sx = 0, sy = 0, sz = 0, cnt = 0;
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ps++) {
+      const bool deep = valid[ps] && depth[ps] >= dmax - 1e-6f;
+      sx += deep ? p[ps].x : 0.0f; sy += deep ? p[ps].y : 0.0f; sz += deep ? p[ps].z : 0.0f; cnt += deep ? 1.0f : 0.0f;
+    }
     tsum2(t, sx, sy);
     tsum2(t, sz, cnt);
     if (lane == 0 && base < NC) {
@@ -218,11 +236,15 @@ __device__ int box_contacts(const Tile<LPE>& t, float* con, int base, const Obb&
     }
     return 1;
   }
-  const unsigned m = t.ballot(valid);
-  const int slot = __popc(m & ((1u << lane) - 1u));
-  const int total = min(__popc(m), 8);
-  if (valid && slot < 8 && base + slot < NC) put_contact(con, base + slot, p, nout, -depth, pair);
-  return total;
+  int total = 0;
+#pragma unroll
+  for (int ps = 0; ps < PASSES; ps++) {
+    const unsigned m = t.ballot(valid[ps]);
+    const int slot = total + __popc(m & ((1u << lane) - 1u));
+    if (valid[ps] && slot < 8 && base + slot < NC) put_contact(con, base + slot, p[ps], nout, -depth[ps], pair);
+    total += __popc(m);
+  }
+  return min(total, 8);
 }
 
 // Stage A for one env.  Writes the contact list and the header of workspace record `w`; returns (on every lane)

@@ -293,13 +293,14 @@ __global__ void __launch_bounds__(128, NCAP == NCL ? SO100_K3M_MINB : SO100_K3H_
 #endif
 constexpr size_t slow_max2(size_t a, size_t b) { return a > b ? a : b; }
 constexpr size_t SLOW_SMEM = slow_max2(slow_max2(sizeof(KinS), sizeof(BoxS)), slow_max2(slow_max2(sizeof(HullS), 2 * sizeof(SolS<NCL>)), sizeof(SolS<NC>)));
-template <unsigned LPE_KIN, unsigned LPE_LIGHT>
+template <unsigned LPE_KIN, unsigned LPE_BOX, unsigned LPE_LIGHT>
 __global__ void __launch_bounds__(32, SO100_SLOW_MINB) phase_slow_lane(float* state, float* work, DevTables T, Queues Q, int stage, int nsub, int trailing) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::thread_block blk = cg::this_thread_block();
   Tile<32> t = cg::tiled_partition<32>(blk);
   Tile<LPE_KIN> tk = cg::tiled_partition<LPE_KIN>(blk);
   Tile<LPE_LIGHT> tl = cg::tiled_partition<LPE_LIGHT>(blk);
+  Tile<LPE_BOX> tb = cg::tiled_partition<LPE_BOX>(blk);
   const int lane = t.thread_rank();
   SO100_TRACE_SCOPE(Q.trace + TR_SLOW);
   const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_LANE_COUNT]);
@@ -324,10 +325,11 @@ __global__ void __launch_bounds__(32, SO100_SLOW_MINB) phase_slow_lane(float* st
       BoxS* B = reinterpret_cast<BoxS*>(smem_raw);
       copy_vec<32, W_FRAMES_N>(t, reinterpret_cast<float*>(&B->f), w + W_FRAMES);
       t.sync();
-      int ncon = 0;
+      int ncon = 0, nsurv = 0;
       bool coupled = false;
-      const int nsurv = collide_box_env(t, B, w, T, &ncon, &coupled);
+      if (tb.meta_group_rank() == 0) nsurv = collide_box_env(tb, B, w, T, &ncon, &coupled);     // on a sub-tile of the regular kernel's width
       t.sync();
+      nsurv = t.shfl(nsurv, 0); ncon = t.shfl(ncon, 0); coupled = t.shfl((int)coupled, 0) != 0;
       if (nsurv > 0) {
         HullS* H = reinterpret_cast<HullS*>(smem_raw);     // its frame block is the one just loaded (both layouts start with it)
         for (int slot = 0; slot < nsurv; slot++) {
