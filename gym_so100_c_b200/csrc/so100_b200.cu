@@ -740,9 +740,11 @@ static int create_device_side(so100_ctx* h, const DevModel& dm, const std::vecto
   if (const char* e = getenv("SO100_K2B_BLOCKS")) h->k2b_blocks = std::max(1, atoi(e));
   if (const char* e = getenv("SO100_K2B_DIV")) h->k2b_div = std::max(1, atoi(e));
   {
-    // env groups: SO100_GROUPS overrides; default one group per 1024 envs, at most 6 (measured on B200 at 16384 envs with the
-    // three solve classes: 5 groups 2.53 ms, 6 2.54, 7 2.54, 8 2.56, 10 2.62 per step; 4096 envs want 4)
-    int ng = std::min(6, num_envs / 1024);
+    // env groups: SO100_GROUPS overrides.  Round 1 (one env per warp in the solve kernel): one group per 1024 envs, at most 6 (16384 envs:
+    // 5 groups 2.53 ms, 6 2.54, 7 2.54, 8 2.56, 10 2.62 per step).
+    // round 2, after the two-envs-per-warp kernels (16384 envs: 1 group 2.58 ms, 2 2.46, 3 2.37, 4 2.38, 6 2.41, 8 2.52; 65536 envs: 2 groups
+    // 5.95 ms, 3 5.98, 4 6.12, 6 6.44; 131072 envs: 2 10.9, 4 11.0, 6 11.6; 4096 envs: 3 or 4): three groups, two for large batches
+    int ng = num_envs >= 49152 ? 2 : std::min(3, num_envs / 1024);
     if (const char* e = getenv("SO100_GROUPS")) ng = atoi(e);
     ng = std::max(1, std::min(ng, 32));
     rc = make_group(h, h->whole, 0, num_envs, 32, false);
