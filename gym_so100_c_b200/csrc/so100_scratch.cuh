@@ -158,7 +158,9 @@ struct __align__(16) KinS {
   FrameBlock f;
   DynBlock d;
   float com[NL][3], Iw[NL][6], U[21][3], Y[21][3], FN[NL][6];
+  float bank_pad[20];              // stride of 16 banks (mod 32) between the two 16-lane tiles of a warp
 };
+static_assert((sizeof(KinS) / 4) % 32 == 16, "KinS stride: half the banks");
 
 // K2a: broad phase + box-like pairs
 constexpr int NPEN = 32;           // penetrating box pairs per env that reach contact generation
@@ -170,6 +172,7 @@ struct __align__(16) BoxS {
   unsigned char q1[NPEN], qcode[NPEN];
   float qsep[NPEN];
 };
+static_assert((sizeof(BoxS) / 4) % 32 == 16, "BoxS stride: half the banks");
 
 // K2b: GJK / EPA for hull pairs
 struct __align__(16) HullS {
@@ -200,7 +203,10 @@ template <int NCAP_> struct __align__(16) SolS {
 #endif
   float J[NCAP_ * 4][JS];
   float T[NCAP_ * 4][JS];          // H_c J_c rows of the current Newton iteration
+  float bank_pad[NCAP_ == NCL ? 8 : 4];   // the two 16-lane tiles of a warp sit in consecutive structs: a stride of 16 banks (mod 32) keeps
+                                          // their lane-contiguous accesses on disjoint banks (ncu counted 0.56 M two-way conflicts per launch)
 };
+static_assert((sizeof(SolS<NCL>) / 4) % 32 == 16, "SolS<NCL> stride: half the banks");
 
 // K4 / reset: task layer
 struct __align__(16) TaskS {

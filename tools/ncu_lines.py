@@ -41,8 +41,23 @@ def main():
     lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, 'gym_so100_c_b200', 'libso100_b200.so')
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     table = line_table(lib, kernel)
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
+    # NCU_PICK="-k regex:phase_solve_light -c 1": pick one result of a multi-kernel report
+    pick = os.environ.get('NCU_PICK', '').split()
+    out = subprocess.run(['ncu', '-i', rep] + pick + ['--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
+    allrows = list(csv.reader(out.splitlines()))
+    # a report with several results prints one block per kernel ("Kernel Name" row, header row, instruction rows): keep the one asked for
+    want = os.environ.get('NCU_KERNEL', kernel.split('ILj')[0].replace('_ZN5so100', '').lstrip('0123456789'))
+    rows, keep = [], False
+    for r in allrows:
+        if r and r[0] == 'Kernel Name':
+            if rows:
+                break
+            keep = want in r[1]
+            if keep:
+                rows.append(r)
+            continue
+        if keep:
+            rows.append(r)
     hdr = rows[1]
     ia, ii, isamp = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('# Samples')
     stall_cols = [(k, h) for k, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
