@@ -34,3 +34,21 @@ def test_static_tables_of_the_gpu_arm():
     # measured DRAM traffic of the dominant kernel within 2x of its algorithmic bytes (no wasted re-reads)
     alg = bench.PHASE_ALG_BYTES["solve_light"] * traffic["envs"]
     assert 0.5 * alg < traffic["solve_light"]["dram_bytes_per_launch"] < 2.0 * alg
+
+
+def test_measured_step_metrics_feed_the_roofline():
+    """The FP32 roofline numerator is MEASURED (ncu thread-instruction counts, profiles/r02_step_metrics.json), not the
+    Appendix-C convention: the file bench.py reads must exist, cover every phase kernel and be self-consistent."""
+    sys.path.insert(0, ROOT)
+    import bench
+    m = bench.step_metrics()
+    assert m is not None and m["envs"] == bench.ENVS_PER_GPU and m["steps"] >= 1
+    kernels = {k.split("<")[0].replace("phase_", "") for k in m["kernels"]}
+    assert {"kin_dyn", "collide_box", "collide_hull", "solve_light", "solve_heavy", "task"} <= kernels
+    per = m["per_env_step"]
+    total = sum(v["flop32"] for v in m["kernels"].values()) / (m["envs"] * m["steps"])
+    assert abs(total - per["flop32"]) < 1e-6 * per["flop32"]
+    assert 1e5 < per["flop32"] < bench.FLOP_CONVENTION_PER_ENV_STEP          # measured work is below the 1 MFLOP convention
+    assert 2e4 < per["warp_inst"] < 2e5 and per["flop64"] < 0.05 * per["flop32"]
+    light = [v for k, v in m["kernels"].items() if "solve_light" in k][0]
+    assert 0.5 * bench.PHASE_ALG_BYTES["solve_light"] * m["envs"] < light["dram_bytes_per_launch"] < 2.0 * bench.PHASE_ALG_BYTES["solve_light"] * m["envs"]
