@@ -75,7 +75,10 @@ struct DeviceGuard {
 #define CUDA_OK(expr)                                                                              \
   do {                                                                                             \
     cudaError_t e_ = (expr);                                                                       \
-    if (e_ != cudaSuccess) return fail(SO100_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    if (e_ != cudaSuccess) {                                                                       \
+      (void)cudaGetLastError();   /* a non-sticky error (e.g. out of memory) must not resurface in the next call's check */ \
+      return fail(SO100_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));             \
+    }                                                                                              \
   } while (0)
 
 // A contiguous range of envs that runs the step pipeline on its own stream.  Kernel durations are set by their slowest

@@ -155,20 +155,35 @@ class SO100GoalVecEnv(_VecBase):
 
     _task = ext.TASK_GOAL
 
-    def __init__(self, num_envs: int, **kw):
+    def __init__(self, num_envs: int, observation: str = "state", observation_width: int = 640, observation_height: int = 480, **kw):
+        """`observation`: "state" (default; the 15-float so100_state vector, the declared deviation that keeps 65536-env
+        rollouts feasible) or "pixels" (the reference's own layout, env.py:208-225, 267-270: the flattened "top" image / 255
+        followed by the six joint angles, drawn by the library's ray-caster)."""
+        if observation not in ("state", "pixels"):
+            raise NotImplementedError(f"observation {observation!r}")
         super().__init__(num_envs, **kw)
         self.max_episode_steps = 300                  # env.py:200
         self.distance_threshold = 0.01                # env.py:252
+        self.observation_kind = observation
+        self.observation_width, self.observation_height = int(observation_width), int(observation_height)
+        obs_dim = 15
+        if observation == "pixels":
+            self.sim.configure_render(self.observation_width, self.observation_height, camera="top")
+            obs_dim = self.observation_height * self.observation_width * 3 + 6
         inf = np.inf
         self.single_observation_space = DictSpace({
-            "observation": Box(low=-inf, high=inf, shape=(15,), dtype=np.float32),
+            "observation": Box(low=-inf, high=inf, shape=(obs_dim,), dtype=np.float32),
             "achieved_goal": Box(low=-inf, high=inf, shape=(3,), dtype=np.float32),   # env.py:228-235
             "desired_goal": Box(low=-inf, high=inf, shape=(3,), dtype=np.float32),
         })
         self.observation_space = DictSpace({k: batch_box(s, self.num_envs) for k, s in self.single_observation_space.items()})
 
     def _obs(self):
-        return {"observation": self.sim.obs, "achieved_goal": self.sim.achieved, "desired_goal": self.sim.desired}
+        observation = self.sim.obs
+        if self.observation_kind == "pixels":         # env.py:267-270: pixels.flatten() / 255 ++ agent_pos
+            pix = self.sim.render().reshape(self.num_envs, -1).to(torch.float32) / 255.0
+            observation = torch.cat([pix, self.sim.obs[:, 9:15]], dim=1)
+        return {"observation": observation, "achieved_goal": self.sim.achieved, "desired_goal": self.sim.desired}
 
     def reset(self, seed=None, options: Optional[dict] = None):
         self.sim.reset(mask=self._mask(options), box_pose=self._box_poses(seed))

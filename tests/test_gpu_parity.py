@@ -828,3 +828,41 @@ def test_pixel_observation_matches_numpy_raycaster(model_blob, model_rec):
             assert abs(cols.mean() - col) < 1.5 and abs(rows.mean() - row) < 1.5, (i, cols.mean(), col, rows.mean(), row)
     assert seen_cube >= 3
     env.close()
+
+
+def test_goal_env_pixel_observation_layout(model_blob):
+    """SO100GoalEnv's own observation layout (env.py:208-225, 267-270): flattened "top" image / 255 followed by the six joint
+    angles; achieved / desired goals unchanged."""
+    import torch
+    from gym_so100_c_b200.vec_env import SO100GoalVecEnv
+    n, W, H = 3, 32, 24
+    env = SO100GoalVecEnv(n, observation="pixels", observation_width=W, observation_height=H, seed=1)
+    obs, _ = env.reset()
+    assert obs["observation"].shape == (n, W * H * 3 + 6) and obs["observation"].dtype == torch.float32
+    assert env.single_observation_space["observation"].shape == (W * H * 3 + 6,)
+    obs, rew, term, trunc, info = env.step(torch.zeros((n, 6)))
+    pix = env.sim.render().reshape(n, -1).float() / 255.0
+    assert torch.equal(obs["observation"][:, :-6], pix) and torch.equal(obs["observation"][:, -6:], env.sim.obs[:, 9:15])
+    assert 0.0 <= float(obs["observation"][:, :-6].min()) and float(obs["observation"][:, :-6].max()) <= 1.0
+    assert obs["achieved_goal"].shape == (n, 3) and set(torch.unique(rew).tolist()) <= {0.0, -1.0}
+    env.close()
+
+
+def test_failed_create_leaves_the_library_usable(model_blob):
+    """so100_create that fails half-way (device allocation of an absurd batch) must release everything it took, including the
+    live-model registration: afterwards a handle with a DIFFERENT model can be created (round 1 leaked the count and refused)."""
+    import ctypes as C
+    from gym_so100_c_b200 import ext, model
+    from gym_so100_c_b200.engine import BatchedSim
+    lib = ext.load()
+    h = C.c_void_p()
+    rc = lib.so100_create(model_blob, len(model_blob), 2**31 - 64, 0, 0, C.c_uint64(0), C.c_int64(0), C.byref(h))
+    assert rc == -2 and b"cudaMalloc" in lib.so100_last_error()
+    m = model.unpack(model_blob).copy()
+    m["timestep"] = 0.001
+    other = BatchedSim(8, model_blob=model.pack(m))        # would fail with "one model per process" if the failed create still counted
+    other.reset()
+    other.close()
+    again = BatchedSim(8, model_blob=model_blob)
+    again.reset()
+    again.close()
