@@ -441,6 +441,7 @@ static int configure_kernels(int device) {
   CUDA_OK(cudaFuncSetAttribute(phase_collide_hull<LPE_K2B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<HullS>(LPE_K2B)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_light<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L)));
   CUDA_OK(cudaFuncSetAttribute(phase_slow_lane<LPE_K1, LPE_K2A, LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLOW_SMEM));
+  CUDA_OK(cudaFuncSetAttribute(phase_hull_solve<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * HULL_SOLVE_SMEM)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_light_queue<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NC>>(LPE_K3H)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_heavy<LPE_K3H, NCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3H)));
@@ -539,6 +540,18 @@ static void launch_solve_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const
     mark(h, st, CLS_SOLVE, false);
     return;
   }
+  if (h->timing && h->dag == 3 && !hull_done) {
+    mark(h, st, CLS_HULL, true);
+    launch_p(phase_hull_solve<LPE_K3L>, k2b_grid(h, n), BLOCK, 4 * HULL_SOLVE_SMEM, st, h->prio_high, state, h->work + (size_t)G.off * WORK_WORDS, T, Q, O);
+    mark(h, st, CLS_HULL, false);
+    mark(h, st, CLS_HEAVY, true);
+    medium(st, 0); heavy(st);
+    mark(h, st, CLS_HEAVY, false);
+    mark(h, st, CLS_SOLVE, true);
+    light_a(st);
+    mark(h, st, CLS_SOLVE, false);
+    return;
+  }
   if (h->timing || hull_done) {
     // timing mode (one stream, so that every event pair brackets its kernels alone) and so100_forward (K2b already ran)
     if (!hull_done) launch_hull(h, G, st);
@@ -566,6 +579,23 @@ static void launch_solve_stage(so100_ctx* h, EnvGroup& G, cudaStream_t st, const
     light_a(st);
     cudaStreamWaitEvent(st, G.join, 0);
     cudaStreamWaitEvent(st, G.join2, 0);
+    return;
+  }
+  if (h->dag == 3) {
+    // K2b fused with the solves of the envs it completes, beside the light grid of the other envs and the medium queue a; the
+    // (rare) heavy class after it
+    cudaEventRecord(G.fork, st);
+    cudaStreamWaitEvent(G.side, G.fork, 0);
+    cudaStreamWaitEvent(G.hull, G.fork, 0);
+    medium(G.side, 0);
+    cudaEventRecord(G.join, G.side);
+    launch_p(phase_hull_solve<LPE_K3L>, k2b_grid(h, n), BLOCK, 4 * HULL_SOLVE_SMEM, G.hull, h->prio_high, state, h->work + (size_t)G.off * WORK_WORDS,
+             T, Q, O);
+    heavy(G.hull);
+    cudaEventRecord(G.join3, G.hull);
+    light_a(st);
+    cudaStreamWaitEvent(st, G.join, 0);
+    cudaStreamWaitEvent(st, G.join3, 0);
     return;
   }
   if (h->dag == 2) {
@@ -872,7 +902,7 @@ int so100_launches_per_step(so100_handle h) {
   // nsub x (K1, K2a, K2b, K3l, K3m, K3h [+ K3l-b, K3m-b with the a / b work classes]) + trailing (K1, K2a, K2b) + K4
   // with the slow lane (default): nsub x (K1, K2a, K2b, K3l, slow lane) + trailing (K1, K2a, K2b) + K4
   const bool slow = h->slowlane_enabled && h->grid_class == 0 && h->nsub >= 1 && h->nsub <= 11;
-  const int per_group = slow ? h->nsub * 5 + 3 + 1 : h->nsub * (h->dag != 0 ? 8 : 6) + 3 + 1;
+  const int per_group = slow ? h->nsub * 5 + 3 + 1 : h->nsub * ((h->dag == 1 || h->dag == 2) ? 8 : 6) + 3 + 1;
   return per_group * (int)std::max<size_t>(h->groups.size(), 1);
 }
 

@@ -226,6 +226,82 @@ __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TP
   }
 }
 
+// K2b + solve, fused (schedule 3): the tile that completes an env's last hull pair goes straight on to solve that env -- the light
+// class on a 16-lane sub-tile with an inactive sibling (the same code and tile width as the regular light grid), an arm-cube
+// contact with the dense 8-contact code -- instead of queueing it for a kernel behind a grid-wide boundary.  For the envs with
+// hull pairs (the ones with the long solves) the stage then costs the slowest env's OWN GJK/EPA + solve, not the slowest
+// GJK/EPA item of the group plus the slowest solve of the group.  Envs with more than NCL contacts still go to the heavy queue.
+// After the hull-pair queue the tiles drain light queue b / medium queue b (filled only when the first stage of a step reuses
+// the previous step's contact lists).
+constexpr size_t hs_max2(size_t a, size_t b) { return a > b ? a : b; }
+constexpr size_t HULL_SOLVE_SMEM = hs_max2(sizeof(HullS), 2 * sizeof(SolS<NCL>));
+template <unsigned LPE_LIGHT>
+__device__ __forceinline__ void hull_solve_env(const Tile<32>& t, const Tile<LPE_LIGHT>& tl, unsigned char* smem, float* state, const float* work,
+                                               int env, int ncon, bool coupled, const DevTables& T, const Queues& Q, const SolveOut& O) {
+  float* rec = state + (size_t)env * STATE_WORDS;
+  const float* w = work + (size_t)env * WORK_WORDS;
+  if (ncon > NCL) {
+    if (t.thread_rank() == 0) Q.heavy[atomicAdd(&Q.ctl[Q_HEAVY_COUNT], 1)] = env;
+  } else if (coupled) {
+    solve_env<true>(t, reinterpret_cast<SolS<NCL>*>(smem), rec, w, env, ncon, T, O);
+  } else if constexpr (LPE_LIGHT < 32) {
+    const int half = tl.meta_group_rank() & 1;
+    solve_env<false>(tl, reinterpret_cast<SolS<NCL>*>(smem) + half, rec, w, env, ncon, T, O, half == 0);
+  } else {
+    solve_env<false>(t, reinterpret_cast<SolS<NCL>*>(smem), rec, w, env, ncon, T, O);
+  }
+  t.sync();
+}
+#ifndef SO100_K2BS_MINB
+#define SO100_K2BS_MINB 3
+#endif
+template <unsigned LPE_LIGHT>
+__global__ void __launch_bounds__(128, SO100_K2BS_MINB) phase_hull_solve(float* state, float* work, DevTables T, Queues Q, SolveOut O) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::thread_block blk = cg::this_thread_block();
+  Tile<32> t = cg::tiled_partition<32>(blk);
+  Tile<LPE_LIGHT> tl = cg::tiled_partition<LPE_LIGHT>(blk);
+  unsigned char* smem = smem_raw + (size_t)t.meta_group_rank() * HULL_SOLVE_SMEM;
+  HullS* S = reinterpret_cast<HullS*>(smem);
+  const int lane = t.thread_rank();
+  SO100_TRACE_SCOPE(Q.trace + TR_HULL);
+  const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_HULL_COUNT]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) Q.note(1, count);
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&Q.ctl[Q_HULL_NEXT], 1);
+    i = t.shfl(i, 0);
+    if (i >= count) break;
+    const int item = Q.hull[i], env = item / NHP;
+    float* w = work + (size_t)env * WORK_WORDS;
+    copy_vec<32, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
+    t.sync();
+    bool coupled = false;
+    const int ncon = collide_hull_item(t, S, w, item % NHP, T, &coupled);
+    t.sync();
+    if (ncon >= 0) hull_solve_env<LPE_LIGHT>(t, tl, smem, state, work, env, ncon, coupled, T, Q, O);
+  }
+  // the queues the reuse path of K2a fills for envs with hull pairs
+  const int nlb = *reinterpret_cast<volatile int*>(&Q.ctl[Q_LB_COUNT]);
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&Q.ctl[Q_LB_NEXT], 1);
+    i = t.shfl(i, 0);
+    if (i >= nlb) break;
+    const int env = Q.light_b[i];
+    hull_solve_env<LPE_LIGHT>(t, tl, smem, state, work, env, __float_as_int(work[(size_t)env * WORK_WORDS + W_HDR]), false, T, Q, O);
+  }
+  const int nmb = *reinterpret_cast<volatile int*>(&Q.ctl[Q_MEDB_COUNT]);
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&Q.ctl[Q_MEDB_NEXT], 1);
+    i = t.shfl(i, 0);
+    if (i >= nmb) break;
+    const int env = Q.medium_b[i];
+    hull_solve_env<LPE_LIGHT>(t, tl, smem, state, work, env, __float_as_int(work[(size_t)env * WORK_WORDS + W_HDR]), true, T, Q, O);
+  }
+}
+
 // K3l-b: the light-class envs whose contact list K2b completed (light queue b), same solver code and tile width as the regular
 // grid above.  Persistent warps; the tiles of a warp pull their items independently but enter the solver together (its loop
 // votes warp-wide), a tile that found the queue empty as inactive.

@@ -248,10 +248,12 @@ def test_groups_and_graph_replay_are_bit_invariant(model_blob, monkeypatch):
     g = torch.Generator(device="cuda").manual_seed(5)
     acts = torch.rand((6, n, 6), device="cuda", generator=g) * 2 - 1
     results = []
-    #          groups graph reuse slowlane budgets (newton, gjk, epa)
-    configs = (("4", "1", "1", "1", None), ("1", "0", "0", "0", None), ("8", "0", "1", "1", None), ("4", "1", "0", "0", None),
-               ("6", "1", "1", "1", ("1", "2", "1")), ("1", "0", "1", "1", ("2", "4", "2")))
-    for groups, graph, reuse, slow, budgets in configs:
+    #          groups graph reuse slowlane budgets (newton, gjk, epa)  schedule (SO100_DAG)
+    configs = (("4", "1", "1", "1", None, "0"), ("1", "0", "0", "0", None, "0"), ("8", "0", "1", "1", None, "0"), ("4", "1", "0", "0", None, "0"),
+               ("6", "1", "1", "1", ("1", "2", "1"), "0"), ("1", "0", "1", "1", ("2", "4", "2"), "0"),
+               ("3", "1", "1", "0", None, "3"), ("2", "0", "0", "0", None, "3"), ("3", "1", "1", "0", None, "1"))
+    for groups, graph, reuse, slow, budgets, dag in configs:
+        monkeypatch.setenv("SO100_DAG", dag)
         monkeypatch.setenv("SO100_GROUPS", groups)
         monkeypatch.setenv("SO100_GRAPH", graph)
         monkeypatch.setenv("SO100_REUSE", reuse)
@@ -266,7 +268,7 @@ def test_groups_and_graph_replay_are_bit_invariant(model_blob, monkeypatch):
         for k in range(6):
             obs, r, term, trunc, succ = sim.step(acts[k], autoreset=True)
             rew.append(r.clone())
-        assert sim.launches_per_step() == (54 if slow == "1" else 64) * int(groups)
+        assert sim.launches_per_step() == (54 if slow == "1" else (84 if dag == "1" else 64)) * int(groups)
         d = sim.diagnostics()
         results.append([t.cpu().numpy() for t in sim.get_state()] + [torch.stack(rew).cpu().numpy(), obs.cpu().numpy(),
                                                                      np.array([d["solver_runs"], d["newton_iters"], d["contacts_seen"]])])
