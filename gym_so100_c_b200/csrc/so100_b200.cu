@@ -191,7 +191,7 @@ struct so100_ctx {
     const size_t N = (size_t)n;
     return Queues{G.ctl, base + N + (size_t)G.off * NHP, base + G.off, base + (1 + NHP) * N + G.off, base + (2 + NHP) * N + G.off,
                   base + (3 + NHP) * N + G.off, G.order + (size_t)G.parity * n, G.order + (size_t)(1 - G.parity) * n, qstat,
-                  (1024 * 1024) / std::max(G.n, 1), G.index < 8 ? (G.index * 12 + G.stage) * 10 : -1000000, dag != 0 ? 1 : 0,
+                  (1024 * 1024) / std::max(G.n, 1), (G.index < 8 || G.index == 32) ? ((G.index & 7) * 12 + G.stage) * 10 : -1000000, dag != 0 ? 1 : 0,
                   base + (4 + NHP) * N + G.off, base + (5 + NHP) * N + G.off, slow_on ? 1 : 0, budget_newton, budget_gjk, budget_epa};
   }
 };
