@@ -322,6 +322,9 @@ def run_gpu(args):
         env4 = SO100GoalVecEnv(n4, device=dev, seed=0x50100)
         roll = HerRollout(env4, horizon=320, n_sampled_goal=4)      # ring of 320 steps x 65536 envs (3.9 GB): holds whole 300-step episodes
         roll.reset()
+        # de-synchronise the episodes (every env would otherwise be truncated and reset at the same step 300, and the timed window
+        # right after it would see 65536 cubes landing at once): start each env at a random point of its 300-step episode
+        env4.sim.set_aux(step_count=torch.randint(0, 300, (n4,), dtype=torch.int32))
         acts4 = torch.rand((32 + 10, n4, 6), device=dev, generator=gen) * 2 - 1
         for s in range(310):                                        # every env finishes at least one episode: the ring has finished episodes to sample
             roll.step(acts4[s % 32])

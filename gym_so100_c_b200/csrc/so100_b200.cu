@@ -1407,7 +1407,8 @@ int so100_her_begin(const so100_her_ring* ring, int32_t pos, const float* obs, c
   HerRing R;
   if (int rc = her_ring(ring, R)) return rc;
   if (pos < 0 || pos >= R.capacity || !obs || !achieved || !desired || !action) return fail(SO100_ERR_ARG, "so100_her_begin: bad argument");
-  her_begin_kernel<<<(R.num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(R, pos, obs, achieved, desired, action);
+  her_begin_kernel<<<(R.num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(R, pos);
+  her_begin_copy_kernel<<<(unsigned)(((long long)R.num_envs * 27 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(R, pos, obs, achieved, desired, action);
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
@@ -1418,7 +1419,9 @@ int so100_her_commit(const so100_her_ring* ring, int32_t pos, const float* obs, 
   if (int rc = her_ring(ring, R)) return rc;
   if (pos < 0 || pos >= R.capacity || !obs || !achieved || !final_obs || !reward || !terminated || !truncated)
     return fail(SO100_ERR_ARG, "so100_her_commit: bad argument");
-  her_commit_kernel<<<(R.num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(R, pos, obs, achieved, final_obs, reward, terminated, truncated);
+  her_commit_copy_kernel<<<(unsigned)(((long long)R.num_envs * 18 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(R, pos, obs, achieved, final_obs,
+                                                                                                                  terminated, truncated);
+  her_commit_kernel<<<(R.num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(R, pos, reward, terminated, truncated);
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
@@ -1431,9 +1434,10 @@ int so100_her_sample(const so100_her_ring* ring, int64_t batch, int32_t n_sample
   if (batch < 0 || n_sampled_goal < 0 || !obs || !action || !next_obs || !achieved || !next_achieved || !desired || !reward || !done || !index)
     return fail(SO100_ERR_ARG, "so100_her_sample: bad argument");
   if (batch == 0) return SO100_OK;
-  her_sample_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(R, batch, n_sampled_goal, threshold, (uint32_t)seed,
-                                                                                       (uint32_t)(seed >> 32), call, obs, action, next_obs,
-                                                                                       achieved, next_achieved, desired, reward, done, index);
+  her_pick_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(R, batch, n_sampled_goal, threshold, (uint32_t)seed,
+                                                                                     (uint32_t)(seed >> 32), call, reward, done, index);
+  her_gather_kernel<<<(unsigned)((batch * 45 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(R, batch, index, obs, action, next_obs, achieved,
+                                                                                            next_achieved, desired);
   CUDA_OK(cudaGetLastError());
   return SO100_OK;
 }
