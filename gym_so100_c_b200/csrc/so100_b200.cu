@@ -152,6 +152,7 @@ struct so100_ctx {
   // stagger = 1 starts every odd group only after its even neighbour has finished its first position stage, so that the
   // two are about a third of a substep apart for the rest of the step; 2 chains all groups that way.
   // slow lane (so100_scratch.cuh: Queues): on by default for the small grid class; budgets of the regular kernels
+  bool fuse_k12 = true;       // SO100_FUSE_K12=0: K1 and K2a as two kernels
   bool slowlane_enabled = false, slow_on = false;   // SO100_SLOWLANE=1 enables it.  Measured (B200, 16384 envs): 3.6-4.9 ms per step against
                                                     // 2.5 without: one warp taking an env through kinematics, box collision, its hull pairs one
                                                     // after the other and the solve needs 250-450 us per stage, longer than the regular
@@ -189,7 +190,7 @@ struct so100_ctx {
   Queues queues(const EnvGroup& G) const {
     int* base = qmem + CTL_WORDS;
     const size_t N = (size_t)n;
-    return Queues{G.ctl, base + N + (size_t)G.off * NHP, base + G.off, base + (1 + NHP) * N + G.off, base + (2 + NHP) * N + G.off,
+    return Queues{G.ctl + (G.stage & 1) * Q_PARITY, G.ctl + ((G.stage + 1) & 1) * Q_PARITY, G.ctl + Q_LANE_BASE, base + N + (size_t)G.off * NHP, base + G.off, base + (1 + NHP) * N + G.off, base + (2 + NHP) * N + G.off,
                   base + (3 + NHP) * N + G.off, G.order + (size_t)G.parity * n, G.order + (size_t)(1 - G.parity) * n, qstat,
                   (1024 * 1024) / std::max(G.n, 1), (G.index < 8 || G.index == 32) ? ((G.index & 7) * 12 + G.stage) * 10 : -1000000, dag != 0 ? 1 : 0,
                   base + (4 + NHP) * N + G.off, base + (5 + NHP) * N + G.off, slow_on ? 1 : 0, budget_newton, budget_gjk, budget_epa};
@@ -438,6 +439,7 @@ static int configure_kernels(int device) {
   if (done) return SO100_OK;
   CUDA_OK(cudaFuncSetAttribute(phase_kin_dyn<LPE_K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<KinS>(LPE_K1)));
   CUDA_OK(cudaFuncSetAttribute(phase_collide_box<LPE_K2A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<BoxS>(LPE_K2A)));
+  CUDA_OK(cudaFuncSetAttribute(phase_kin_box<LPE_K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((BLOCK / LPE_K1) * KINBOX_SMEM)));
   CUDA_OK(cudaFuncSetAttribute(phase_collide_hull<LPE_K2B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<HullS>(LPE_K2B)));
   CUDA_OK(cudaFuncSetAttribute(phase_solve_light<LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<SolS<NCL>>(LPE_K3L, TPB_K3L)));
   CUDA_OK(cudaFuncSetAttribute(phase_slow_lane<LPE_K1, LPE_K2A, LPE_K3L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLOW_SMEM));
@@ -487,6 +489,13 @@ static void launch_kin_box(so100_ctx* h, EnvGroup& G, cudaStream_t st, const flo
   const Queues Q = h->queues(G);
   float* state = h->state + (size_t)G.off * STATE_WORDS;
   float* work = h->work + (size_t)G.off * WORK_WORDS;
+  if (h->fuse_k12 && LPE_K1 == LPE_K2A) {
+    mark(h, st, CLS_KIN, true);
+    launch_p(phase_kin_box<LPE_K1>, grid_of(n, LPE_K1), BLOCK, (BLOCK / LPE_K1) * KINBOX_SMEM, st, h->prio_mid, state, work,
+             action ? action + (size_t)G.off * 6 : nullptr, n, with_dyn, T, Q, G.stage, reuse);
+    mark(h, st, CLS_KIN, false);
+    return;
+  }
   mark(h, st, CLS_KIN, true);
   launch_p(phase_kin_dyn<LPE_K1>, grid_of(n, LPE_K1), BLOCK, smem_of<KinS>(LPE_K1), st, h->prio_mid, state, work, action ? action + (size_t)G.off * 6 : nullptr, n, with_dyn, Q, G.stage);
   mark(h, st, CLS_KIN, false); mark(h, st, CLS_BOX, true);
@@ -708,13 +717,16 @@ static void free_group(EnvGroup& G) {
 // Runs `body(group, stream)` for every env group: on the groups' own streams, forked from and joined back into `st`,
 // or (one group / timing mode) directly on `st`.
 template <class F> static void for_each_group(so100_ctx* h, cudaStream_t st, bool allow_groups, F body) {
-  if (!allow_groups || h->timing || h->groups.size() < 2) { body(h->whole, st); return; }
+  // both copies of a group's stage words start a pipeline call at zero (afterwards every stage re-arms the next one's copy)
+  auto arm = [](EnvGroup& G, cudaStream_t s_) { cudaMemsetAsync(G.ctl, 0, 2 * Q_PARITY * sizeof(int), s_); };
+  if (!allow_groups || h->timing || h->groups.size() < 2) { arm(h->whole, st); body(h->whole, st); return; }
   cudaEventRecord(h->ev_start, st);
   if (h->group_times) cudaEventRecordWithFlags(h->t_start, st, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
   for (size_t gi = 0; gi < h->groups.size(); gi++) {
     EnvGroup& G = h->groups[gi];
     cudaStreamWaitEvent(G.st, h->ev_start, 0);
     if (gi > 0 && (h->stagger == 2 || (h->stagger == 1 && (gi & 1)))) cudaStreamWaitEvent(G.st, h->groups[gi - 1].staged, 0);
+    arm(G, G.st);
     body(G, G.st);
     if (h->group_times) cudaEventRecordWithFlags(G.t_done, G.st, h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
     cudaEventRecord(G.done, G.st);
@@ -753,6 +765,10 @@ static int create_device_side(so100_ctx* h, const DevModel& dm, const std::vecto
   if (const char* e = getenv("SO100_STAGGER")) h->stagger = atoi(e);
   if (const char* e = getenv("SO100_DAG")) h->dag = atoi(e);
   if (const char* e = getenv("SO100_SLOWLANE")) h->slowlane_enabled = atoi(e) != 0;
+  // K1 + K2a as one kernel saves a kernel boundary per stage where the step is latency-bound (4096 envs +2 %, 16384 +1 %) and costs
+  // K1 its occupancy (80 instead of 40 registers) where it is throughput-bound (131072 envs -5 %)
+  h->fuse_k12 = h->n < 49152;
+  if (const char* e = getenv("SO100_FUSE_K12")) h->fuse_k12 = atoi(e) != 0;
   if (const char* e = getenv("SO100_BUDGET_NEWTON")) h->budget_newton = std::max(1, atoi(e));
   if (const char* e = getenv("SO100_BUDGET_GJK")) h->budget_gjk = std::max(1, atoi(e));
   if (const char* e = getenv("SO100_BUDGET_EPA")) h->budget_epa = std::max(1, atoi(e));
@@ -900,9 +916,11 @@ int so100_num_envs(so100_handle h) { return h ? h->n : SO100_ERR_ARG; }
 int so100_launches_per_step(so100_handle h) {
   if (!h) return SO100_ERR_ARG;
   // nsub x (K1, K2a, K2b, K3l, K3m, K3h [+ K3l-b, K3m-b with the a / b work classes]) + trailing (K1, K2a, K2b) + K4
-  // with the slow lane (default): nsub x (K1, K2a, K2b, K3l, slow lane) + trailing (K1, K2a, K2b) + K4
+  // per stage: K1 + K2a (one kernel when fused), K2b, then K3l, K3m, K3h (with the slow lane: K3l and the lane kernel; schedules 1 and
+  // 2: five solve kernels); trailing position stage; K4
   const bool slow = h->slowlane_enabled && h->grid_class == 0 && h->nsub >= 1 && h->nsub <= 11;
-  const int per_group = slow ? h->nsub * 5 + 3 + 1 : h->nsub * ((h->dag == 1 || h->dag == 2) ? 8 : 6) + 3 + 1;
+  const int front = (h->fuse_k12 && LPE_K1 == LPE_K2A) ? 2 : 3;
+  const int per_group = h->nsub * (front + (slow ? 2 : ((h->dag == 1 || h->dag == 2) ? 5 : 3))) + front + 1;
   return per_group * (int)std::max<size_t>(h->groups.size(), 1);
 }
 
@@ -1262,6 +1280,7 @@ int so100_forward(so100_handle h, float* qacc, int32_t* ncon, int32_t* con_geom,
   // solve classes in forward mode (nothing is integrated)
   h->slow_on = false;        // mj_forward solves every env in the regular kernels (no budgets, medium / heavy queue kernels)
   h->whole.stage = 0;
+  CUDA_OK(cudaMemsetAsync(h->whole.ctl, 0, 2 * Q_PARITY * sizeof(int), st));
   launch_kin_box(h, h->whole, st, nullptr, 1);
   launch_hull(h, h->whole, st);
   const int threads = h->n * 32;

@@ -57,19 +57,24 @@ __device__ __forceinline__ void kin_dyn_env(const Tile<LPE>& t, KinS* S, float* 
   copy_vec<LPE, W_FRAMES_N>(t, w + W_FRAMES, reinterpret_cast<const float*>(&S->f));
 }
 
-// K1: regular grid over a group's envs; also re-arms the queues (`stage` = 0 for the first stage of a step, which also re-arms
-// the slow lane; every stage notes where the slow-lane queue stands: the entries a stage adds belong to that stage's slow-lane kernel)
+// first kernel of a stage: re-arm the NEXT stage's copy of the stage words; slow-lane words (`stage` = 0 for the first stage of a
+// step, which also re-arms the slow lane; every stage notes where the slow-lane queue stands: the entries a stage adds belong to
+// that stage's slow-lane kernel)
+__device__ __forceinline__ void rearm_queues(const Queues& Q, int stage) {
+  if (blockIdx.x != 0) return;
+  if (threadIdx.x < Q_WORDS) Q.ctl_next[threadIdx.x] = 0;
+  if (threadIdx.x == Q_WORDS) {
+    if (stage == 0) Q.lanectl[Q_LANE_COUNT] = 0;
+    if (stage >= 0 && stage < 12) Q.lanectl[Q_LANE_CURSOR + stage] = stage == 0 ? 0 : Q.lanectl[Q_LANE_COUNT];
+  }
+}
+
+// K1: regular grid over a group's envs
 template <unsigned LPE>
 __global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, const float* action, int n, int with_dyn, Queues Q, int stage) {
   SO100_TILE_PROLOGUE(LPE, 128, KinS);
   SO100_TRACE_SCOPE(Q.trace + TR_KIN);
-  if (blockIdx.x == 0) {
-    if (threadIdx.x < Q_WORDS) Q.ctl[threadIdx.x] = 0;
-    if (threadIdx.x == Q_WORDS) {
-      if (stage == 0) Q.ctl[Q_LANE_COUNT] = 0;
-      if (stage >= 0 && stage < 12) Q.ctl[Q_LANE_CURSOR + stage] = stage == 0 ? 0 : Q.ctl[Q_LANE_COUNT];
-    }
-  }
+  rearm_queues(Q, stage);
   const int env = blockIdx.x * EPB + t.meta_group_rank();
   if (env >= n) return;
   if (Q.slowlane) {
@@ -83,6 +88,23 @@ __global__ void __launch_bounds__(128) phase_kin_dyn(float* state, float* work, 
 // `reuse`: the workspace already holds the complete contact lists of exactly this state (the trailing collision stage of
 // the previous so100_step), except for envs whose header says HDR_STALE (reset since): everyone else only re-enters the
 // heavy queue, which K1 has just re-armed
+// K2a for one env whose frames are in S->f
+template <unsigned LPE>
+__device__ __forceinline__ void collide_box_route(const Tile<LPE>& t, BoxS* S, float* w, int env, const DevTables& T, const Queues& Q) {
+  const int lane = t.thread_rank();
+  int ncon;
+  bool coupled;
+  const int nsurv = collide_box_env(t, S, w, T, &ncon, &coupled);
+  if (nsurv > 0) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&Q.ctl[Q_HULL_COUNT], nsurv);
+    base = t.shfl(base, 0);
+    if (lane < nsurv) Q.hull[base + lane] = env * NHP + lane;
+  } else if (lane == 0) {
+    Q.route(env, ncon, coupled, false);
+  }
+}
+
 template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_box(float* work, int n, DevTables T, Queues Q, int reuse) {
   SO100_TILE_PROLOGUE(LPE, 128, BoxS);
   SO100_TRACE_SCOPE(Q.trace + TR_BOX);
@@ -99,17 +121,56 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_box
   }
   copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
   t.sync();
-  int ncon;
-  bool coupled;
-  const int nsurv = collide_box_env(t, S, w, T, &ncon, &coupled);
-  if (nsurv > 0) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&Q.ctl[Q_HULL_COUNT], nsurv);
-    base = t.shfl(base, 0);
-    if (lane < nsurv) Q.hull[base + lane] = env * NHP + lane;
-  } else if (lane == 0) {
-    Q.route(env, ncon, coupled, false);
+  collide_box_route(t, S, w, env, T, Q);
+}
+
+// K1 + K2a in one kernel (both run two envs per warp): the frames go from the kinematics scratch to the collision scratch through
+// registers instead of through the workspace and a kernel boundary.  The queue words K2a appends to were re-armed by the previous
+// stage (rearm_queues), so no block has to wait for block 0.
+constexpr size_t KINBOX_SMEM = sizeof(KinS) > sizeof(BoxS) ? sizeof(KinS) : sizeof(BoxS);
+template <unsigned LPE>
+__global__ void __launch_bounds__(128) phase_kin_box(float* state, float* work, const float* action, int n, int with_dyn, DevTables T, Queues Q,
+                                                     int stage, int reuse) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int EPB = 128 / LPE;
+  cg::thread_block blk = cg::this_thread_block();
+  Tile<LPE> t = cg::tiled_partition<LPE>(blk);
+  unsigned char* smem = smem_raw + (size_t)t.meta_group_rank() * KINBOX_SMEM;
+  const int lane = t.thread_rank();
+  SO100_TRACE_SCOPE(Q.trace + TR_KIN);
+  rearm_queues(Q, stage);
+  const int env = blockIdx.x * EPB + t.meta_group_rank();
+  if (env >= n) return;
+  if (Q.slowlane) {
+    if (stage == 0) { if (lane == 0) Q.lane[env] = 0; }
+    else if (Q.lane[env] != 0) return;
   }
+  float* w = work + (size_t)env * WORK_WORDS;
+  KinS* K = reinterpret_cast<KinS*>(smem);
+  kin_dyn_env(t, K, state + (size_t)env * STATE_WORDS, w, action, env, with_dyn);
+  if (reuse) {
+    const int4 hdr = *reinterpret_cast<const int4*>(w + W_HDR);
+    if (hdr.w == 0) {
+      if (lane == 0) Q.route(env, hdr.x, (hdr.z & HDR_COUPLED) != 0, hdr.y > 0);
+      return;
+    }
+  }
+  t.sync();
+  BoxS* B = reinterpret_cast<BoxS*>(smem);
+  {
+    // the two layouts overlap in the scratch: every lane holds its part of the frame block in registers before anyone stores
+    constexpr int NV4 = W_FRAMES_N / 4, R = (NV4 + LPE - 1) / LPE;
+    const float4* src = reinterpret_cast<const float4*>(&K->f);
+    float4* dst = reinterpret_cast<float4*>(&B->f);
+    float4 v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) if (lane + r * (int)LPE < NV4) v[r] = src[lane + r * LPE];
+    t.sync();
+#pragma unroll
+    for (int r = 0; r < R; r++) if (lane + r * (int)LPE < NV4) dst[lane + r * LPE] = v[r];
+  }
+  t.sync();
+  collide_box_route(t, B, w, env, T, Q);
 }
 
 // K2b: persistent tiles drain the hull-pair queue
@@ -379,12 +440,12 @@ __global__ void __launch_bounds__(32, SO100_SLOW_MINB) phase_slow_lane(float* st
   Tile<LPE_BOX> tb = cg::tiled_partition<LPE_BOX>(blk);
   const int lane = t.thread_rank();
   SO100_TRACE_SCOPE(Q.trace + TR_SLOW);
-  const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_LANE_COUNT]);
+  const int count = *reinterpret_cast<volatile int*>(&Q.lanectl[Q_LANE_COUNT]);
   if (blockIdx.x == 0 && threadIdx.x == 0) Q.note(0, count >> 2);      // a quarter of the envs suspended so far this step
   const SolveOut O{nullptr, nullptr, 0};
   for (;;) {
     int i = 0;
-    if (lane == 0) i = atomicAdd(&Q.ctl[Q_LANE_CURSOR + stage], 1);
+    if (lane == 0) i = atomicAdd(&Q.lanectl[Q_LANE_CURSOR + stage], 1);
     i = t.shfl(i, 0);
     if (i >= count) break;
     const int env = Q.slow[i];

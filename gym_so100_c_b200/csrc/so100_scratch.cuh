@@ -50,10 +50,15 @@ static_assert(NHP <= 16, "hull pair list is 4 words");
 
 // queue control words (device ints)
 enum { Q_HULL_COUNT = 0, Q_HULL_NEXT = 1, Q_HEAVY_COUNT = 2, Q_HEAVY_NEXT = 3, Q_SLOW = 4, Q_FAST = 5, Q_MEDA_COUNT = 6, Q_MEDA_NEXT = 7,
-       Q_MEDB_COUNT = 8, Q_MEDB_NEXT = 9, Q_LB_COUNT = 10, Q_LB_NEXT = 11, Q_WORDS = 12,     // words 0..11 are re-armed by every stage's K1
-       Q_LANE_COUNT = 12,        // slow-lane queue length: grows over the stages of a step, re-armed by the first stage only
-       Q_LANE_CURSOR = 16,       // [12] per stage: the next slow-lane queue entry of that stage's slow-lane kernel
-       Q_STRIDE = 32 };
+       Q_MEDB_COUNT = 8, Q_MEDB_NEXT = 9, Q_LB_COUNT = 10, Q_LB_NEXT = 11, Q_WORDS = 12,
+       // The stage words above exist twice per group (Q_PARITY words apart): stage s works on copy s & 1 and its first kernel re-arms
+       // the other copy for stage s + 1 (nobody touches that copy during stage s), so the re-arming needs no kernel boundary of its
+       // own and K1 / K2a can be one kernel.  A pipeline call starts with a memset of both copies.
+       Q_PARITY = 16,
+       Q_LANE_BASE = 32,         // slow-lane words, outside the two stage copies (Queues::lanectl)
+       Q_LANE_COUNT = 0,         // slow-lane queue length: grows over the stages of a step, re-armed by the first stage only
+       Q_LANE_CURSOR = 4,        // [12] per stage: the next slow-lane queue entry of that stage's slow-lane kernel
+       Q_STRIDE = 64 };
 
 // Work classes of a substep.  The collision stage ends in two steps: the box stage (K2a) completes every env without a hull
 // pair, the GJK/EPA queue kernel (K2b) the other ~14 %.  Everything that only needs K2a starts right after it and runs BESIDE
@@ -89,7 +94,9 @@ struct TraceScope {
 enum { TR_KIN = 0, TR_BOX = 1, TR_HULL = 2, TR_LIGHT_A = 3, TR_LIGHT_B = 4, TR_MED_A = 5, TR_MED_B = 6, TR_HEAVY = 7, TR_TASK = 8, TR_SLOW = 9 };
 
 struct Queues {
-  int* ctl;      // [Q_WORDS]
+  int* ctl;      // [Q_WORDS] this stage's copy of the stage words
+  int* ctl_next; // the other copy: re-armed by this stage's first kernel for the next stage
+  int* lanectl;  // slow-lane words
   int* hull;     // [N * NHP] hull pairs for GJK/EPA this substep, one item = env * NHP + slot
   int* heavy;    // [N] envs with more than NCL contacts this substep (solved after K2b)
   int* medium_a; // [N] envs with at most NCL contacts, one of which couples the arm and the cube (dense Hessian); complete after K2a
@@ -118,7 +125,7 @@ struct Queues {
   int budget_newton, budget_gjk, budget_epa;
   __device__ __forceinline__ bool suspended(int env) const { return slowlane && lane[env] != 0; }
   __device__ __forceinline__ void suspend(int env) const {
-    if (atomicExch(&lane[env], 1) == 0) slow[atomicAdd(&ctl[Q_LANE_COUNT], 1)] = env;
+    if (atomicExch(&lane[env], 1) == 0) slow[atomicAdd(&lanectl[Q_LANE_COUNT], 1)] = env;
   }
   __device__ __forceinline__ void note(int which, int count) const { atomicMax(&stat[which], (count * scale) >> 10); }
   // work class of an env whose collision stage is complete (`after_hull`: completed by K2b, or had hull pairs when the

@@ -249,10 +249,12 @@ def test_groups_and_graph_replay_are_bit_invariant(model_blob, monkeypatch):
     acts = torch.rand((6, n, 6), device="cuda", generator=g) * 2 - 1
     results = []
     #          groups graph reuse slowlane budgets (newton, gjk, epa)  schedule (SO100_DAG)
-    configs = (("4", "1", "1", "1", None, "0"), ("1", "0", "0", "0", None, "0"), ("8", "0", "1", "1", None, "0"), ("4", "1", "0", "0", None, "0"),
-               ("6", "1", "1", "1", ("1", "2", "1"), "0"), ("1", "0", "1", "1", ("2", "4", "2"), "0"),
-               ("3", "1", "1", "0", None, "3"), ("2", "0", "0", "0", None, "3"), ("3", "1", "1", "0", None, "1"))
-    for groups, graph, reuse, slow, budgets, dag in configs:
+    #                                                                                           K1 + K2a fused (SO100_FUSE_K12)
+    configs = (("4", "1", "1", "1", None, "0", "1"), ("1", "0", "0", "0", None, "0", "0"), ("8", "0", "1", "1", None, "0", "1"),
+               ("4", "1", "0", "0", None, "0", "1"), ("6", "1", "1", "1", ("1", "2", "1"), "0", "1"), ("1", "0", "1", "1", ("2", "4", "2"), "0", "0"),
+               ("3", "1", "1", "0", None, "3", "1"), ("2", "0", "0", "0", None, "3", "1"), ("3", "1", "1", "0", None, "1", "0"))
+    for groups, graph, reuse, slow, budgets, dag, fuse in configs:
+        monkeypatch.setenv("SO100_FUSE_K12", fuse)
         monkeypatch.setenv("SO100_DAG", dag)
         monkeypatch.setenv("SO100_GROUPS", groups)
         monkeypatch.setenv("SO100_GRAPH", graph)
@@ -268,7 +270,9 @@ def test_groups_and_graph_replay_are_bit_invariant(model_blob, monkeypatch):
         for k in range(6):
             obs, r, term, trunc, succ = sim.step(acts[k], autoreset=True)
             rew.append(r.clone())
-        assert sim.launches_per_step() == (54 if slow == "1" else (84 if dag == "1" else 64)) * int(groups)
+        front = 2 if fuse == "1" else 3                                            # K1 + K2a as one kernel or two
+        per_stage = front + (2 if slow == "1" else (5 if dag == "1" else 3))
+        assert sim.launches_per_step() == (10 * per_stage + front + 1) * int(groups)
         d = sim.diagnostics()
         results.append([t.cpu().numpy() for t in sim.get_state()] + [torch.stack(rew).cpu().numpy(), obs.cpu().numpy(),
                                                                      np.array([d["solver_runs"], d["newton_iters"], d["contacts_seen"]])])
