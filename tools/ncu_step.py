@@ -7,6 +7,7 @@ import sys
 
 os.environ.setdefault("SO100_GROUPS", "1")
 os.environ.setdefault("SO100_GRAPH", "0")
+os.environ.setdefault("SO100_FUSE_K12", "0")     # K1 and K2a as separate kernels: per-kernel attribution, 64 launches per step
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
