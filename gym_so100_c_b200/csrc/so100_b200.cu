@@ -1313,6 +1313,11 @@ int so100_hull_stats(int32_t* out /* host [65536][4] */) {
   CUDA_OK(cudaMemcpyToSymbol(g_hull_stat_n, &zero, sizeof(int)));
   return n;
 }
+int so100_hull_phases(int32_t* out /* host [65536][6] */) {
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpyFromSymbol(out, g_hull_phase, sizeof(int) * 6 * 65536));
+  return 0;
+}
 #endif
 
 int so100_measure_fp32_peak(int device, float* tflops) {

@@ -177,8 +177,14 @@ struct EpaScratch {
   unsigned char freed[EPA_MAXF];
 #ifdef SO100_HULL_CLOCK
   int dbg[2];
+  int ph[6];     // cycles: closest face, support, visibility, horizon, new faces, (spare)
 #endif
 };
+#ifdef SO100_HULL_CLOCK
+#define HULL_PH(k) { const long long c_ = clock64(); if (lane == 0) E->ph[k] += (int)(c_ - phc_); phc_ = c_; }
+#else
+#define HULL_PH(k)
+#endif
 
 __device__ __forceinline__ void epa_make_face(EpaScratch* E, int slot, int i, int j, int k) {
   const V3 a = ld3(E->vw[i]), b = ld3(E->vw[j]), c = ld3(E->vw[k]);
@@ -198,6 +204,7 @@ __device__ __forceinline__ void epa_make_face(EpaScratch* E, int slot, int i, in
 #ifdef SO100_HULL_CLOCK
 // development build: per GJK/EPA item (ns, GJK iterations, EPA iterations, hull vertices), ring buffer of 65536 items
 __device__ int g_hull_stat[65536][4];
+__device__ int g_hull_phase[65536][6];
 __device__ int g_hull_stat_n;
 #endif
 
@@ -230,6 +237,7 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
   }
 #ifdef SO100_HULL_CLOCK
   E->dbg[0] = gjk_its_; E->dbg[1] = 0;
+  if (lane < 6) E->ph[lane] = 0;
 #endif
   if (!hit) return false;
   // ---- EPA
@@ -258,6 +266,7 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
     if (it >= max_epa) { *over_budget = true; t.sync(); return false; }
 #ifdef SO100_HULL_CLOCK
     if (lane == 0) E->dbg[1] = it + 1;
+    long long phc_ = clock64();
 #endif
     // closest face (ties -> lowest slot)
     float bd = 3.0e38f; int bf = 0x7fffffff;
@@ -267,7 +276,9 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
     if (bf == 0x7fffffff) break;
     best = bf;
     const V3 nb = ld3(E->fn[best]);
+    HULL_PH(0)
     const MV w = msupport(t, A, B, nb, vert);
+    HULL_PH(1)
     if (dot(w.w, nb) - E->fdp[best] < 1e-6f || nface + 2 > EPA_MAXF) break;
     // visibility
     int myvis = 0;
@@ -277,6 +288,7 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
       myvis += v;
     }
     t.sync();
+    HULL_PH(2)
     if (!E->vis[best]) break;      // round-off: the expanding face does not see the new point
     // freed slots (compaction of visible faces) and horizon edges
     int nfree = 0, nh = 0;
@@ -303,6 +315,7 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
       nh += __popc(m);
     }
     t.sync();
+    HULL_PH(3)
     if (nh < 3 || nh > EPA_MAXF || nface + (nh - nfree) > EPA_MAXF) break;
     if (lane == 0) { st3(E->vw[nv], w.w); st3(E->va[nv], w.a); }
     for (int f = lane; f < nface; f += LPE) if (E->vis[f]) E->fv[f][3] = 0;
@@ -314,6 +327,7 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
     nface += max(nh - nfree, 0);
     nv++;
     t.sync();
+    HULL_PH(4)
   }
   const V3 a0 = ld3(E->vw[E->fv[best][0]]), a1 = ld3(E->vw[E->fv[best][1]]), a2 = ld3(E->vw[E->fv[best][2]]);
   float lam[3];
@@ -327,7 +341,7 @@ __device__ bool gjk_epa(const Tile<LPE>& t, const Shape& A, const Shape& B, V3 c
   return depth > 0;
 }
 
-static_assert(sizeof(EpaScratch) <= sizeof(float) * 900, "EPA scratch does not fit its shared-memory slot");
+static_assert(sizeof(EpaScratch) <= sizeof(HullS::epa), "EPA scratch does not fit its shared-memory slot");
 
 // vertices of a shape within `tol` of its support plane in world direction d: count, centroid (world), radius and
 // the world vector from the centroid to the farthest member (the edge direction when count == 2)
@@ -356,23 +370,26 @@ __device__ int support_set(const Tile<LPE>& t, const Shape& s, V3 d, float tol, 
   }
   const float ic = 1.0f / cnt;
   const V3 c = mk(sx * ic, sy * ic, sz * ic);
-  float r2 = -1.0f;
-  int bi = 0x7fffffff;
+  float r2 = 0.0f;
   V3 fl = mk(0, 0, 0);
-  for (int i = t.thread_rank(); i < n; i += LPE) {
-    const V3 v = vertex(i);
-    if (dot(v, dl) >= best - tol) {
-      const V3 e = v - c;
-      const float q = dot(e, e);
-      if (q > r2) { r2 = q; bi = i; fl = e; }
+  if (cnt > 1.5f) {          // a single member is its own centroid: radius 0, no third sweep
+    r2 = -1.0f;
+    int bi = 0x7fffffff;
+    for (int i = t.thread_rank(); i < n; i += LPE) {
+      const V3 v = vertex(i);
+      if (dot(v, dl) >= best - tol) {
+        const V3 e = v - c;
+        const float q = dot(e, e);
+        if (q > r2) { r2 = q; bi = i; fl = e; }
+      }
     }
-  }
 #pragma unroll
-  for (int off = LPE / 2; off > 0; off >>= 1) {
-    const float oq = t.shfl_xor(r2, off);
-    const int oi = t.shfl_xor(bi, off);
-    const V3 of = mk(t.shfl_xor(fl.x, off), t.shfl_xor(fl.y, off), t.shfl_xor(fl.z, off));
-    if (oq > r2 || (oq == r2 && oi < bi)) { r2 = oq; bi = oi; fl = of; }
+    for (int off = LPE / 2; off > 0; off >>= 1) {
+      const float oq = t.shfl_xor(r2, off);
+      const int oi = t.shfl_xor(bi, off);
+      const V3 of = mk(t.shfl_xor(fl.x, off), t.shfl_xor(fl.y, off), t.shfl_xor(fl.z, off));
+      if (oq > r2 || (oq == r2 && oi < bi)) { r2 = oq; bi = oi; fl = of; }
+    }
   }
   radius = sqrtf(fmaxf(r2, 0.0f));
   centroid = s.base + mulmv(s.mat, c);
@@ -411,12 +428,13 @@ __device__ V3 deepest_feature_point(const Tile<LPE>& t, const Shape& A, const Sh
   V3 cA, cB, fA, fB;
   float rA, rB;
   const int nA = support_set(t, A, n, 1e-6f, vert, cA, rA, fA);
+  if (nA == 1) return cA - n * (0.5f * depth);          // a single deepest vertex of A decides; B's feature is not needed
   const int nB = support_set(t, B, -n, 1e-6f, vert, cB, rB, fB);
   if (nA == 2 && nB == 2) {
     const V3 x = cross(fA, fB);
     if (dot(x, x) > 1e-6f * dot(fA, fA) * dot(fB, fB)) return pos;   // crossing edges: the EPA witness is unique
   }
-  if (nA == 1 || (nB != 1 && rA <= rB)) return cA - n * (0.5f * depth);
+  if (nB != 1 && rA <= rB) return cA - n * (0.5f * depth);
   return cB + n * (0.5f * depth);
 }
 
@@ -456,6 +474,7 @@ template <unsigned LPE> __device__ int collide_hull_item(const Tile<LPE>& t, Hul
     const EpaScratch* E_ = reinterpret_cast<const EpaScratch*>(S->epa);
     g_hull_stat[k_][0] = (int)(hc1_ - hc0_); g_hull_stat[k_][1] = (int)(hc2_ - hc1_);
     g_hull_stat[k_][2] = E_->dbg[0] | (E_->dbg[1] << 8) | ((int)hit_ << 16); g_hull_stat[k_][3] = A.vnum + B.vnum;
+    for (int q_ = 0; q_ < 6; q_++) g_hull_phase[k_][q_] = hit_ ? E_->ph[q_] : 0;
   }
 #else
   bool over = false;
@@ -467,16 +486,24 @@ template <unsigned LPE> __device__ int collide_hull_item(const Tile<LPE>& t, Hul
   if (over) return -2;
 #endif
   int* hdr = reinterpret_cast<int*>(w + W_HDR);
-  int last = 0;
-  if (lane == 0) {
-    put_contact(w + W_HSTAGE, slot, pos, n, -depth, pid);
+  const int nbox = hdr[0], nsurv = min(hdr[1], NHP);     // written by K2a (the previous kernel)
+  if (nsurv > 1) {
+    // several pairs, several tiles: staged results are published with a fence, the tile that takes the counter to zero merges
+    int last = 0;
+    if (lane == 0) {
+      put_contact(w + W_HSTAGE, slot, pos, n, -depth, pid);
+      __threadfence();
+      last = atomicSub(&hdr[3], 1) == 1;
+    }
+    last = t.shfl(last, 0);
+    if (!last) return -1;
     __threadfence();
-    last = atomicSub(&hdr[3], 1) == 1;
+  } else if (lane == 0) {
+    // the env's only pair (the common case): nobody to synchronise with
+    put_contact(w + W_HSTAGE, slot, pos, n, -depth, pid);
+    hdr[3] = 0;
   }
-  last = t.shfl(last, 0);
-  if (!last) return -1;
-  __threadfence();
-  const int nbox = hdr[0], nsurv = min(hdr[1], NHP);
+  t.sync();
   float4 q0 = make_float4(0, 0, 0, 0), q1 = make_float4(0, 0, 0, __int_as_float(-1));
   if (lane < nsurv) {
     q0 = __ldcg(reinterpret_cast<const float4*>(w + W_HSTAGE + lane * CON_WORDS));

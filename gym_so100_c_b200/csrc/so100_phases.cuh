@@ -174,7 +174,10 @@ __global__ void __launch_bounds__(128) phase_kin_box(float* state, float* work, 
 }
 
 // K2b: persistent tiles drain the hull-pair queue
-template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_hull(float* work, DevTables T, Queues Q) {
+#ifndef SO100_K2B_MINB
+#define SO100_K2B_MINB 5
+#endif
+template <unsigned LPE> __global__ void __launch_bounds__(128, SO100_K2B_MINB) phase_collide_hull(float* work, DevTables T, Queues Q) {
   SO100_TILE_PROLOGUE(LPE, 128, HullS);
   SO100_TRACE_SCOPE(Q.trace + TR_HULL);
 #ifdef SO100_DEV_SKIP_HULL
@@ -182,20 +185,22 @@ template <unsigned LPE> __global__ void __launch_bounds__(128) phase_collide_hul
 #endif
   const int count = *reinterpret_cast<volatile int*>(&Q.ctl[Q_HULL_COUNT]);
   if (blockIdx.x == 0 && threadIdx.x == 0) Q.note(1, count);
+  // every tile's first item is its own index (no 4096 atomics on one word before anyone starts); the rest is handed out dynamically
+  const int ntiles = gridDim.x * (128 / LPE);
+  int i = blockIdx.x * (128 / LPE) + t.meta_group_rank();
+  const int max_gjk = Q.slowlane ? Q.budget_gjk : 48, max_epa = Q.slowlane ? Q.budget_epa : EPA_MAXV - 4;
   for (;;) {
-    int i = 0;
-    if (lane == 0) i = atomicAdd(&Q.ctl[Q_HULL_NEXT], 1);
-    i = t.shfl(i, 0);
     if (i >= count) break;
     const int item = Q.hull[i], env = item / NHP;
     float* w = work + (size_t)env * WORK_WORDS;
     copy_vec<LPE, W_FRAMES_N>(t, reinterpret_cast<float*>(&S->f), w + W_FRAMES);
+    if (lane == 0) i = ntiles + atomicAdd(&Q.ctl[Q_HULL_NEXT], 1);     // next item: in flight during this one
     t.sync();
     bool coupled = false;
-    const int ncon = Q.slowlane ? collide_hull_item(t, S, w, item % NHP, T, &coupled, Q.budget_gjk, Q.budget_epa)
-                                : collide_hull_item(t, S, w, item % NHP, T, &coupled);
+    const int ncon = collide_hull_item(t, S, w, item % NHP, T, &coupled, max_gjk, max_epa);     // one call site: the item code is 60 KB
     if (lane == 0 && ncon >= 0) Q.route(env, ncon, coupled, true);
     if (lane == 0 && ncon == -2) Q.suspend(env);        // over budget: the slow lane redoes this env's collision stage
+    i = t.shfl(i, 0);
     t.sync();
   }
 }

@@ -184,7 +184,11 @@ static_assert((sizeof(BoxS) / 4) % 32 == 16, "BoxS stride: half the banks");
 // K2b: GJK / EPA for hull pairs
 struct __align__(16) HullS {
   FrameBlock f;
+#ifdef SO100_HULL_CLOCK
+  float epa[908];      // development build: + per-phase cycle counters
+#else
   float epa[900];
+#endif
 };
 
 // K3: constraint rows + Newton solve, NCAP contacts

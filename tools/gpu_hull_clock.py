@@ -23,6 +23,8 @@ buf = np.zeros((65536, 4), dtype=np.int32)
 lib.so100_hull_stats(buf.ctypes.data_as(C.c_void_p))
 for _ in range(3):
     sim.step(torch.rand((n, 6), device="cuda", generator=g) * 2 - 1)
+ph = np.zeros((65536, 6), dtype=np.int32)
+lib.so100_hull_phases(ph.ctypes.data_as(C.c_void_p))
 cnt = lib.so100_hull_stats(buf.ctypes.data_as(C.c_void_p))
 a = buf[:min(cnt, 65536)]
 gjk_ns, post_ns = a[:, 0], a[:, 1]
@@ -37,3 +39,10 @@ print("hits: gjk+epa ns mean %.0f p90 %.0f p99 %.0f max %d; gjk its mean %.1f; e
 for e in sorted(set(ei[h].tolist())):
     m = h & (ei == e)
     print(f"  epa its {e:2d}: n {m.sum():5d}  ns mean {gjk_ns[m].mean():8.0f}  verts mean {a[m, 3].mean():5.0f}")
+
+ph = ph[:len(a)]
+for lo, hi in ((1, 4), (5, 8), (9, 30)):
+    m = h & (ei >= lo) & (ei <= hi)
+    if m.sum():
+        per = ph[m].sum(0) / ei[m].sum()
+        print(f"  epa its {lo}-{hi}: cycles per iteration: closest {per[0]:.0f} support {per[1]:.0f} visibility {per[2]:.0f} horizon {per[3]:.0f} new faces {per[4]:.0f}  (verts mean {a[m, 3].mean():.0f})")

@@ -24,9 +24,19 @@ for s in range(warm):
 lib = ext.load()
 buf = np.zeros((960, 2), dtype=np.uint64)
 KINDS = ["kin", "box", "hull", "lightA", "lightB", "medA", "medB", "heavy", "task", "slow"]
+flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda") if os.environ.get("FLUSH") == "1" else None
 for rep in range(2):
     lib.so100_trace_read(None)
+    if flush is not None:           # bench.py's timing: the step starts with a cold L2
+        flush.fill_(float(rep))
+        if os.environ.get("FLUSH_SYNC", "1") == "1":
+            torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     sim.step(acts[rep])
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"event-timed step: {e0.elapsed_time(e1) * 1e3:.1f} us")
     lib.so100_trace_read(buf.ctypes.data_as(C.c_void_p))
     a = buf.astype(np.float64)
     valid = a[:, 1] > 0
