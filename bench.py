@@ -250,7 +250,7 @@ def run_gpu(args):
     d0 = sim.diagnostics()
     parallel.barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get("SO100_BENCH_NO_SAMPLER") != "1":
         sampler.start()
     t_wall = time.perf_counter()
     ms = timed_steps(sim, acts, W, K, flush, torch)
@@ -453,6 +453,7 @@ def run_gpu(args):
                              "solver_cap_hits": window["solver_cap_hits"], "contact_overflows": window["contact_overflow"],
                              "episodes_finished": window["episodes"]},
             "rank_ms_per_step": rank_ms,
+            "step_ms": {"min": float(np.min(ms)), "median": float(np.median(ms)), "p90": float(np.percentile(ms, 90)), "max": float(np.max(ms))},
             "roofline": roof,
             "cpu_baseline": {"value": cpu_value, "unit": "env-steps/s", "cores": cores, "kind": cpu_kind,
                              "sample": f"{cpu_n} envs x {cpu_steps} steps of the same workload after 40 settle steps, " + CPU_SAMPLE},

@@ -1320,6 +1320,15 @@ int so100_hull_phases(int32_t* out /* host [65536][6] */) {
 }
 #endif
 
+#ifdef SO100_SOLVE_TRACE
+// development build: per-iteration solver trace of envs 0..63 from the last so100_forward
+int so100_solve_trace(float* out /* host [64][104][8] */) {
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpyFromSymbol(out, g_solve_trace, sizeof(float) * 64 * 104 * 8));
+  return 0;
+}
+#endif
+
 int so100_measure_fp32_peak(int device, float* tflops) {
   if (!tflops) return fail(SO100_ERR_ARG, "so100_measure_fp32_peak: null output");
   int ndev = 0;

@@ -228,7 +228,11 @@ __device__ int solve_env(const Tile<LPE>& t, ES* S, float* rec, const float* w, 
   if (lane == 0) S->ncon = ncon;
   t.sync();
   make_contact_rows(t, S, T);
+#ifdef SO100_SOLVE_TRACE
+  const int iters = solve<DENSE>(t, S, T, (O.forward || !active) ? nullptr : reinterpret_cast<uint32_t*>(rec + S_DIAG), active, max_it, O.forward ? env : -1);
+#else
   const int iters = solve<DENSE>(t, S, T, (O.forward || !active) ? nullptr : reinterpret_cast<uint32_t*>(rec + S_DIAG), active, max_it);
+#endif
   if (!active || iters < 0) return iters;
   if (O.forward) {
     t.sync();

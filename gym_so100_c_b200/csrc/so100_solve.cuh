@@ -516,8 +516,13 @@ template <unsigned LPE, class ES> __device__ __forceinline__ float dense_newton_
 // Returns the number of Newton iterations.
 // max_it < NEWTON_MAXIT: iteration budget of the regular light kernel; a solve that uses it up without converging returns -1,
 // counts nothing in `diag` and leaves an unfinished iterate behind (the env goes to the slow lane, which solves it again in full).
+#ifdef SO100_SOLVE_TRACE
+// development build: per Newton iteration of env < 64 (so100_forward on a small batch): cost, scaled gradient, its tolerance, phi'(0),
+// step length, line-search evaluations, final phi', relative predicted decrease
+__device__ float g_solve_trace[64][104][8];
+#endif
 template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LPE>& t, ES* S, const DevTables& T, uint32_t* diag, bool active = true,
-                                                                   int max_it = NEWTON_MAXIT) {
+                                                                   int max_it = NEWTON_MAXIT, int dbg_env = -1) {
   using Regs = SolveRegs<LPE, ES::NCAP>;
   const int lane = t.thread_rank();
   const int ncon = S->ncon;
@@ -587,6 +592,12 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
     // tolerance is 2e-6 relative to their magnitude (|qfrc_smooth| + |J^T f|), scaled like MuJoCo's.
     float gg = g * g, ss = r.qfs * r.qfs + jtf * jtf;
     tsum2(t, gg, ss);
+#ifdef SO100_SOLVE_TRACE
+    if (lane == 0 && dbg_env >= 0 && dbg_env < 64 && it < 104) {
+      float* q_ = g_solve_trace[dbg_env][it];
+      q_[0] = cost; q_[1] = sqrtf(gg) * c_m.inv_scale; q_[2] = SO100_GTOL * (1.0f + sqrtf(ss));
+    }
+#endif
     if (sqrtf(gg) * c_m.inv_scale < SO100_GTOL * (1.0f + sqrtf(ss))) { converged = true; done = true; return; }
     float pd;
     SOLVE_CLK(1);
@@ -666,8 +677,10 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
     const float d10 = fabsf(gp);
     const bool descent = gp < 0;                 // no descent left at float32 resolution otherwise
     float alpha = 1.0f, d1 = 0, d2 = 1, lo = 0, hi = -1;
+    [[maybe_unused]] int ls_n_ = 0;
 #pragma unroll 1
     for (int ls = 0; descent && ls < LS_MAXIT; ls++) {
+      ls_n_ = ls + 1;
       if (ls > 0) {
         float na = alpha - __fdividef(d1, d2);     // approximate division: a safeguarded iterate, not a result
         if (hi >= 0 && (na <= lo || na >= hi)) na = 0.5f * (lo + hi);
@@ -701,6 +714,12 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
       if (d1 < 0) lo = alpha; else hi = alpha;
       if (hi >= 0 && hi - lo <= 2e-7f * hi) break;     // bracket at float32 resolution: nothing left to search
     }
+#ifdef SO100_SOLVE_TRACE
+    if (lane == 0 && dbg_env >= 0 && dbg_env < 64 && it < 104) {
+      float* q_ = g_solve_trace[dbg_env][it];
+      q_[3] = gp; q_[4] = alpha; q_[5] = (float)ls_n_; q_[6] = d1; q_[7] = 0.5f * alpha * d10 / (1.0f + fabsf(cost));
+    }
+#endif
     if (!descent) { converged = true; done = true; return; }
     if (lane < NV) {
       const double na = fma((double)alpha, (double)pd, S->ad[lane]);
@@ -730,10 +749,11 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
         // MuJoCo's "improvement < tolerance" test on the ACTUAL decrease: two consecutive iterations that did not lower the
         // cost by one part in 10^7 (float32 resolution) mean the iterate sits at the float32 optimum; without this the rare
         // solve whose predicted decrease stays above the tolerance (round-off in the cancelling terms) runs to the iteration cap
-        if (it > 0) {
-          if (cost > cost_prev - 1e-7f * fabsf(cost_prev)) { if (++stall >= 2) last = true; } else stall = 0;
-        }
-        cost_prev = cost;
+        // cost_prev is the LOWEST cost seen: at the float32 optimum of a stiff problem the iterate can alternate between two points
+        // whose costs differ by a few 1e-6 relative (every second iteration "improves" on the one before, each with a ~25-evaluation
+        // line search that ends at bracket resolution), which a test against the previous iteration alone never catches
+        if (it > 0 && !(cost < cost_prev - 1e-7f * fabsf(cost_prev))) { if (++stall >= 2) last = true; }
+        else { stall = 0; cost_prev = cost; }
         if (last || it >= max_it) done = true;
         else newton_step();
       }

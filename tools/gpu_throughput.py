@@ -27,6 +27,8 @@ def main():
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for s in range(steps):
             flush.fill_(float(s))
+            if os.environ.get("PREWARM") == "1":     # experiment: how much of the flushed step's extra time is the cold state / workspace
+                sim.debug_read(0); sim.debug_read(1)
             ev[s][0].record()
             sim.step(acts[20 + s])
             ev[s][1].record()
