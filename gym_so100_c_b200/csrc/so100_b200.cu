@@ -489,7 +489,7 @@ static void launch_kin_box(so100_ctx* h, EnvGroup& G, cudaStream_t st, const flo
   const Queues Q = h->queues(G);
   float* state = h->state + (size_t)G.off * STATE_WORDS;
   float* work = h->work + (size_t)G.off * WORK_WORDS;
-  if (h->fuse_k12 && LPE_K1 == LPE_K2A) {
+  if (h->fuse_k12 && LPE_K1 == LPE_K2A && !h->timing) {       // timing mode keeps K1 / K2a apart: one duration per phase
     mark(h, st, CLS_KIN, true);
     launch_p(phase_kin_box<LPE_K1>, grid_of(n, LPE_K1), BLOCK, (BLOCK / LPE_K1) * KINBOX_SMEM, st, h->prio_mid, state, work,
              action ? action + (size_t)G.off * 6 : nullptr, n, with_dyn, T, Q, G.stage, reuse);
