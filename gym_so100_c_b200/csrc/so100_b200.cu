@@ -153,6 +153,7 @@ struct so100_ctx {
   // two are about a third of a substep apart for the rest of the step; 2 chains all groups that way.
   // slow lane (so100_scratch.cuh: Queues): on by default for the small grid class; budgets of the regular kernels
   bool fuse_k12 = true;       // SO100_FUSE_K12=0: K1 and K2a as two kernels
+  bool pair_far = true;       // SO100_PAIR_FAR=0: the light solve kernel pairs neighbours of the longest-first order in a warp
   bool slowlane_enabled = false, slow_on = false;   // SO100_SLOWLANE=1 enables it.  Measured (B200, 16384 envs): 3.6-4.9 ms per step against
                                                     // 2.5 without: one warp taking an env through kinematics, box collision, its hull pairs one
                                                     // after the other and the solve needs 250-450 us per stage, longer than the regular
@@ -193,7 +194,7 @@ struct so100_ctx {
     return Queues{G.ctl + (G.stage & 1) * Q_PARITY, G.ctl + ((G.stage + 1) & 1) * Q_PARITY, G.ctl + Q_LANE_BASE, base + N + (size_t)G.off * NHP, base + G.off, base + (1 + NHP) * N + G.off, base + (2 + NHP) * N + G.off,
                   base + (3 + NHP) * N + G.off, G.order + (size_t)G.parity * n, G.order + (size_t)(1 - G.parity) * n, qstat,
                   (1024 * 1024) / std::max(G.n, 1), (G.index < 8 || G.index == 32) ? ((G.index & 7) * 12 + G.stage) * 10 : -1000000, dag != 0 ? 1 : 0,
-                  base + (4 + NHP) * N + G.off, base + (5 + NHP) * N + G.off, slow_on ? 1 : 0, budget_newton, budget_gjk, budget_epa};
+                  base + (4 + NHP) * N + G.off, base + (5 + NHP) * N + G.off, slow_on ? 1 : 0, budget_newton, budget_gjk, budget_epa, pair_far ? 1 : 0};
   }
 };
 
@@ -769,6 +770,8 @@ static int create_device_side(so100_ctx* h, const DevModel& dm, const std::vecto
   // K1 its occupancy (80 instead of 40 registers) where it is throughput-bound (131072 envs -5 %)
   h->fuse_k12 = h->n < 49152;
   if (const char* e = getenv("SO100_FUSE_K12")) h->fuse_k12 = atoi(e) != 0;
+  h->pair_far = h->n < 49152;
+  if (const char* e = getenv("SO100_PAIR_FAR")) h->pair_far = atoi(e) != 0;
   if (const char* e = getenv("SO100_BUDGET_NEWTON")) h->budget_newton = std::max(1, atoi(e));
   if (const char* e = getenv("SO100_BUDGET_GJK")) h->budget_gjk = std::max(1, atoi(e));
   if (const char* e = getenv("SO100_BUDGET_EPA")) h->budget_epa = std::max(1, atoi(e));

@@ -251,8 +251,16 @@ template <unsigned LPE>
 __global__ void __launch_bounds__(SO100_TPB_K3L, SO100_WARPS_K3L * 32 / SO100_TPB_K3L) phase_solve_light(float* state, const float* work, int n, DevTables T, Queues Q, SolveOut O) {
   SO100_TILE_PROLOGUE(LPE, SO100_TPB_K3L, SolS<NCL>);
   SO100_TRACE_SCOPE(Q.trace + TR_LIGHT_A);
-  const int slot = blockIdx.x * EPB + t.meta_group_rank();
-  const bool live = slot < n;
+  int slot = blockIdx.x * EPB + t.meta_group_rank();
+  bool live = slot < n;
+  if (LPE == 16 && Q.pair_far) {
+    // the two tiles of warp W take slots W and n - 1 - W: paired stragglers run their data-dependent branches (line-search trip counts,
+    // cone zones) one after the other, 7.8 us per Newton iteration instead of ~6 for a straggler whose sibling is done after one
+    const int W = slot >> 1;                  // EPB is even: bit 0 of the slot is the tile's position in its warp
+    const bool second = (slot & 1) != 0;
+    slot = second ? n - 1 - W : W;
+    live = second ? slot > W : 2 * W <= n - 1;      // an odd n's middle env belongs to the first tile
+  }
   if (LPE == 32 && !live) return;            // one tile per warp: nobody to vote with
   const int env = Q.order_in[live ? slot : n - 1];
   const float* w = work + (size_t)env * WORK_WORDS;
@@ -423,7 +431,28 @@ __global__ void __launch_bounds__(128, NCAP == NCL ? SO100_K3M_MINB : SO100_K3H_
     if (i >= count) break;
     const int env = queue[i];
     const float* w = work + (size_t)env * WORK_WORDS;
+#ifdef SO100_SOLVE_CLOCK
+    unsigned long long t0_, t1_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0_));
+    if (lane < 4) S->clk2[lane] = 0;
+    const int iters_ = solve_env<true>(t, S, state + (size_t)env * STATE_WORDS, w, env, __float_as_int(w[W_HDR]), T, O);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1_));
+    if (lane == 0) {       // same record as the light kernel writes; bit 11: dense kernel
+      float* rec_ = state + (size_t)env * STATE_WORDS;
+      rec_[57] = __int_as_float((int)(t1_ - t0_));
+      rec_[58] = __int_as_float(iters_);
+      rec_[59] = __int_as_float(min(__float_as_int(w[W_HDR]), 255) | ((S->coupled ? 1 : 0) << 8) | (1 << 11) | (S->clk2[3] << 12));
+#if SO100_SOLVE_CLOCK == 2
+      // split of the dense direction: Hessian + factorisation total, then assembly / arm block + W / Schur complement + solves
+      rec_[60] = __int_as_float(S->clk[2]);
+      for (int k_ = 0; k_ < 3; k_++) rec_[61 + k_] = __int_as_float(S->clk2[k_]);
+#else
+      for (int k_ = 0; k_ < 4; k_++) rec_[60 + k_] = __int_as_float(S->clk[k_]);
+#endif
+    }
+#else
     solve_env<true>(t, S, state + (size_t)env * STATE_WORDS, w, env, __float_as_int(w[W_HDR]), T, O);
+#endif
     t.sync();
   }
 }

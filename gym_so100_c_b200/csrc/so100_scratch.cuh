@@ -123,6 +123,8 @@ struct Queues {
   int* lane;     // [N] 1: the env is suspended (owned by the slow lane) for the rest of this step
   int slowlane;  // 0: classic schedule (medium / heavy queue kernels, no budgets)
   int budget_newton, budget_gjk, budget_epa;
+  int pair_far;  // light solve kernel, two envs per warp: the warp's second tile takes its env from the far end of the longest-first order, so
+                 // a likely straggler shares its warp with a likely one-iteration solve instead of with another straggler
   __device__ __forceinline__ bool suspended(int env) const { return slowlane && lane[env] != 0; }
   __device__ __forceinline__ void suspend(int env) const {
     if (atomicExch(&lane[env], 1) == 0) slow[atomicAdd(&lanectl[Q_LANE_COUNT], 1)] = env;
@@ -217,7 +219,9 @@ template <int NCAP_> struct __align__(16) SolS {
   float bank_pad[NCAP_ == NCL ? 8 : 4];   // the two 16-lane tiles of a warp sit in consecutive structs: a stride of 16 banks (mod 32) keeps
                                           // their lane-contiguous accesses on disjoint banks (ncu counted 0.56 M two-way conflicts per launch)
 };
+#ifndef SO100_SOLVE_CLOCK      // the development build adds eight counters to the struct
 static_assert((sizeof(SolS<NCL>) / 4) % 32 == 16, "SolS<NCL> stride: half the banks");
+#endif
 
 // K4 / reset: task layer
 struct __align__(16) TaskS {

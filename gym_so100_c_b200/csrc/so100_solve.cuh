@@ -407,30 +407,11 @@ template <class ES> __device__ __forceinline__ float hess_contact(const ES* S, i
 // light kernel's hot loop carries neither this code nor its registers.
 template <unsigned LPE, class ES> __device__ __forceinline__ float dense_newton_dir(const Tile<LPE>& t, ES* S, float g) {
   const int lane = t.thread_rank();
-  const int ncon = S->ncon;
   float pd;
 #ifdef SO100_SOLVE_CLOCK
   long long dc_[5]; dc_[0] = clock64();
 #endif
-    // ---- dense 12x12 Hessian, packed lower triangle in shared memory
-    for (int e = lane; e < 78; e += LPE) {
-      int i, j;
-      untri(e, i, j);
-      float h = 0;
-      if (i < NL) h = S->d.Mfull[i][j];
-      else if (i == j) h = (i < 9 ? c_m.cube_mass : c_m.cube_I[i - 9]);
-      if (i == j) h += S->hdiag[i];
-      // entry (i, j) only sees contacts that touch both its blocks: bit 0 arm, bit 1 cube
-      const int need = (i < NL ? 1 : 2) | (j < NL ? 1 : 2);
-      float h2 = 0;
-      for (int c = 0; c < ncon; c++) {
-        if (S->czone[c] == 0 || (S->ckind[c] & need) != need) continue;
-        h += S->J[c * 4 + 0][i] * S->T[c * 4 + 0][j] + S->J[c * 4 + 1][i] * S->T[c * 4 + 1][j];
-        h2 += S->J[c * 4 + 2][i] * S->T[c * 4 + 2][j] + S->J[c * 4 + 3][i] * S->T[c * 4 + 3][j];
-      }
-      S->H[e] = h + h2;
-    }
-    t.sync();
+    // the dense 12x12 Hessian (packed lower triangle) is in S->H: assembled by the caller
     // Block elimination H = [[A, B^T], [B, C]] (A arm 6x6, C cube 6x6, B their coupling): factor A in registers,
     // W = L_A^-1 B^T with one column per lane, the Schur complement S = C - W^T W with one entry per lane, factor S in
     // registers.  Two 6-column register factorisations and two barriers instead of a 12-column chain of dependent
@@ -567,10 +548,65 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
     t.sync();
   };
   set_a(qas_d);
+  // ---- Hessian entries of this lane (packed lower triangle: 78 dense, 42 block-diagonal), fixed for the whole solve: indices, the
+  // blocks a contact has to touch to contribute, and the mass-matrix term.  (Recomputing them in every Newton iteration, with the
+  // contact loop inside the entry loop, made the assembly 3.0 k of the dense iteration's 14 k cycles.)
+  constexpr int HR = LPE == 16 ? 3 : (DENSE ? 3 : 2);
+  int hidx[HR];
+  float hbase[HR];
+#pragma unroll
+  for (int k = 0; k < HR; k++) {
+    const int e = lane + k * (int)LPE;
+    int gi, gj, need, valid;
+    float b = 0.0f;
+    if (coupled) {
+      valid = e < 78;
+      untri(valid ? e : 0, gi, gj);
+      if (gi < NL) b = S->d.Mfull[gi][gj];
+      else if (gi == gj) b = gi < 9 ? c_m.cube_mass : c_m.cube_I[gi - 9];
+      need = (gi < NL ? 1 : 2) | (gj < NL ? 1 : 2);
+    } else {
+      valid = e < 42;
+      const int ee = valid ? e : 0, blk = ee >= 21 ? 1 : 0, rr = ee - 21 * blk;
+      const int i = tri_row6(rr), j = rr - tri(i, 0);
+      if (blk == 0) b = S->d.Mfull[i][j];
+      else if (i == j) b = i < 3 ? c_m.cube_mass : c_m.cube_I[i - 3];
+      gi = i + NL * blk; gj = j + NL * blk;
+      need = 1 << blk;
+    }
+    hidx[k] = gi | (gj << 4) | (need << 8) | (valid << 10) | ((gi == gj ? 1 : 0) << 11);
+    hbase[k] = b;
+  }
+  // S->H = M + diag(friction / limit curvature) + sum_c J_c^T (H_c J_c); entry e of lane `lane` is e = lane + k LPE
+  auto assemble_hessian = [&]() {
+    float h[HR];
+#pragma unroll
+    for (int k = 0; k < HR; k++) h[k] = hbase[k] + (((hidx[k] >> 11) & 1) ? S->hdiag[hidx[k] & 15] : 0.0f);
+    for (int c = 0; c < ncon; c++) {
+      if (S->czone[c] == 0) continue;
+      const int kind = S->ckind[c];
+      const float* Jc = &S->J[c * 4][0];
+      const float* Tc = &S->T[c * 4][0];
+#pragma unroll
+      for (int k = 0; k < HR; k++) {
+        const int need = (hidx[k] >> 8) & 3;
+        if (((hidx[k] >> 10) & 1) && (kind & need) == need) {
+          const int gi = hidx[k] & 15, gj = (hidx[k] >> 4) & 15;
+          const float a01 = fmaf(Jc[gi], Tc[gj], Jc[JS + gi] * Tc[JS + gj]);
+          const float a23 = fmaf(Jc[2 * JS + gi], Tc[2 * JS + gj], Jc[3 * JS + gi] * Tc[3 * JS + gj]);
+          h[k] += a01 + a23;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < HR; k++) if ((hidx[k] >> 10) & 1) S->H[lane + k * (int)LPE] = h[k];
+    t.sync();
+  };
   int stage = 0, it = 0;
   bool done = !active, last = false, converged = false;
   float Ma = 0, dof_force = 0, cost = 0, cost_qas = 0, cost_prev = 3.0e38f;
   int stall = 0;
+  float pred_rel = 1.0f;      // predicted decrease of the last Newton step relative to the cost
   // one Newton iteration from the iterate / forces of the last evaluation; sets `done` when the solve is over
   SOLVE_CLK_DECL;
   auto newton_step = [&]() {
@@ -602,24 +638,9 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
     float pd;
     SOLVE_CLK(1);
     cone_hess_rows(t, S);
+    assemble_hessian();
     if (!coupled) {
       // ---- block-diagonal Hessian: entries 0..20 arm block, 21..41 cube block
-      for (int e = lane; e < 42; e += LPE) {
-        const int blk = e >= 21 ? 1 : 0, rr = e - 21 * blk;
-        const int i = tri_row6(rr), j = rr - tri(i, 0);
-        float h;
-        if (blk == 0) h = S->d.Mfull[i][j];
-        else h = (i == j) ? (i < 3 ? c_m.cube_mass : c_m.cube_I[i - 3]) : 0.0f;
-        const int gi = i + NL * blk, gj = j + NL * blk;
-        if (i == j) h += S->hdiag[gi];
-        for (int c = 0; c < ncon; c++) {
-          const int zone = S->czone[c];
-          if (zone == 0 || !(S->ckind[c] & (1 << blk))) continue;
-          h += hess_contact(S, c, gi, gj);
-        }
-        S->H[e] = h;
-      }
-      t.sync();
       // both blocks factored + solved in registers: lanes 0..5 (and 12..) the arm block, lanes 6..11 the cube block, so
       // that dof lane d already holds its own component of the direction
       const int hb = (lane >= NL && lane < NV) ? 1 : 0;
@@ -732,7 +753,8 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
     SOLVE_CLK(3);
     // predicted decrease 1/2 alpha |phi'(0)| below float32 resolution of the cost: stop after refreshing the forces
     // (MuJoCo's "improvement < tolerance" test, made relative because the arithmetic is float32)
-    if (0.5f * alpha * d10 < SO100_ITOL * (1.0f + fabsf(cost))) last = true;
+    pred_rel = 0.5f * alpha * d10 / (1.0f + fabsf(cost));
+    if (pred_rel < SO100_ITOL) last = true;
   };
   // Every trip = one evaluation, then (stage 2) one Newton iteration.  With two envs per warp (LPE = 16) both tiles
   // vote at the top of every trip, so they run the trip in lock step and re-converge there; without the vote, tiles
@@ -754,7 +776,10 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
         // cost_prev is the LOWEST cost seen: at the float32 optimum of a stiff problem the iterate can alternate between two points
         // whose costs differ by a few 1e-6 relative (every second iteration "improves" on the one before, each with a ~25-evaluation
         // line search that ends at bracket resolution), which a test against the previous iteration alone never catches
-        if (it > 0 && !(cost < cost_prev - 1e-7f * fabsf(cost_prev))) { if (++stall >= 2) last = true; }
+        // An iteration only counts as stalled when its step did not promise a visible decrease either (predicted < 1e-7 of the cost):
+        // a cost of a few hundred resolves 3e-5, and a solve that still gains 5e-5 per iteration on stiff contacts is making progress
+        // its float32 cost cannot show (cube in the bin: force error 6e-3 instead of 2e-4 when such iterations were counted).
+        if (it > 0 && !(cost < cost_prev - 1e-7f * fabsf(cost_prev))) { if (pred_rel < 1e-7f && ++stall >= 2) last = true; }
         else { stall = 0; cost_prev = cost; }
         if (last || it >= max_it) done = true;
         else newton_step();

@@ -28,6 +28,8 @@ a = np.concatenate(rows)
 ok = a[:, 1] < 1000
 ncon = a[:, 2] & 255
 ls = a[:, 2] >> 12
+ok = ok & (((a[:, 2] >> 11) & 1) == 0)     # the light kernel's solves; the dense ones are split out at the end
+ok_all = a[:, 1] < 1000
 for it in sorted(set(a[ok, 1].tolist())):
     m = ok & (a[:, 1] == it)
     if m.sum():
@@ -40,3 +42,14 @@ if m.sum():
           " ls iterations per Newton iteration %.2f (max %.1f)" % ((ls[m] / a[m, 1]).mean(), (ls[m] / a[m, 1]).max()))
 m = ok & (a[:, 1] == 1)
 print("single-iteration solves: cycles", np.round(a[m, 3:7].mean(axis=0)).astype(int).tolist(), " ls its %.2f" % ls[m].mean())
+dense = (a[:, 2] >> 11) & 1
+for name, sel in (("light kernel (block-diagonal Hessian, two envs per warp)", dense == 0), ("queue kernels (dense Hessian, one env per warp)", dense != 0)):
+    m = ok_all & sel & (a[:, 1] >= 6)
+    if m.sum():
+        per_it = a[m, 3:7] / a[m, 1:2]
+        print(f"{name}: n {m.sum()}  cycles/iteration [eval, gradient, Hessian+factor, line search] {np.round(per_it.mean(axis=0)).astype(int).tolist()}  "
+              f"ns/iteration {(a[m, 0] / a[m, 1]).mean():.0f}  ls/iteration {(ls[m] / a[m, 1]).mean():.2f}  ncon {ncon[m].mean():.1f}  its mean {a[m, 1].mean():.1f} max {a[m, 1].max()}")
+if os.environ.get("DENSE_SPLIT") == "1":      # a -DSO100_SOLVE_CLOCK=2 build
+    m = ok_all & (dense != 0) & (a[:, 1] >= 6)
+    per_it = a[m, 3:7] / a[m, 1:2]
+    print("dense direction, cycles per iteration [H_c J_c rows + direction total, assembly, arm block + W, Schur + solves]", np.round(per_it.mean(axis=0)).astype(int).tolist())
