@@ -770,7 +770,7 @@ static int create_device_side(so100_ctx* h, const DevModel& dm, const std::vecto
   // K1 its occupancy (80 instead of 40 registers) where it is throughput-bound (131072 envs -5 %)
   h->fuse_k12 = h->n < 49152;
   if (const char* e = getenv("SO100_FUSE_K12")) h->fuse_k12 = atoi(e) != 0;
-  h->pair_far = h->n < 49152;
+  h->pair_far = false;      // measured: no gain at 16384 envs (the dense queue kernel ends the stage), -2 % at 131072
   if (const char* e = getenv("SO100_PAIR_FAR")) h->pair_far = atoi(e) != 0;
   if (const char* e = getenv("SO100_BUDGET_NEWTON")) h->budget_newton = std::max(1, atoi(e));
   if (const char* e = getenv("SO100_BUDGET_GJK")) h->budget_gjk = std::max(1, atoi(e));
