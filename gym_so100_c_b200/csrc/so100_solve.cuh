@@ -373,28 +373,44 @@ __device__ __forceinline__ float eval_cost(const Tile<LPE>& t, ES* S, SolveRegs<
 // T = H_c J_c for every active contact row (lane per (row, dof)): the Hessian J^T H J then costs 4 multiply-adds per
 // (entry, contact) instead of a 4x4 quadratic form per (entry, contact)
 template <unsigned LPE, class ES> __device__ __forceinline__ void cone_hess_rows(const Tile<LPE>& t, ES* S) {
-  // uncoupled: a contact touches the arm block or the cube block, 6 dofs (8 slots per row); coupled: all 12 (16 slots)
-  const int sh = S->coupled ? 4 : 3, W = S->coupled ? NV : NL;
-  const int n = (S->ncon * 4) << sh;
-  for (int it = t.thread_rank(); it < n; it += LPE) {
-    const int row = it >> sh, c = row >> 2, k = row & 3, slot = it & ((1 << sh) - 1);
-    if (slot >= W) continue;
-    const int d = slot + ((W == NL && !(S->ckind[c] & 1)) ? NL : 0);
-    const int zone = S->czone[c];
-    const float* Hc = S->cH[c];
-    float v = 0;
-    if (zone == 1) {
-      v = Hc[tri(k, k)] * S->J[row][d];          // bottom zone: H_c = diag(D)
-    } else if (zone == 2) {
+  // T_c = H_c J_c (4 rows per contact).  One lane per dof column: it loads the four J entries of its column once and writes the four T
+  // entries; groups of W lanes take contacts g, g + G, ...  (Item-per-lane indexing with the zone / kind look-ups inside cost 1.6 k cycles
+  // of a Newton iteration; this is one shared-memory round trip per contact.)
+  // uncoupled: a contact touches the arm block or the cube block, 6 dofs; coupled: all 12
+  const int lane = t.thread_rank();
+  const bool cpl = S->coupled != 0;
+  const int W = cpl ? NV : NL;
+  const int g = cpl ? (lane >= NV ? (lane >= 2 * NV ? 2 : 1) : 0) : (lane * 43) >> 8;      // lane / W for lane < 32
+  const int G = cpl ? (int)LPE / NV : (int)LPE / NL;
+  const int dl = lane - g * W;
+  const int ncon = S->ncon;
+  if (g < G) {
+    for (int c = g; c < ncon; c += G) {
+      const int zone = S->czone[c];
+      if (zone == 0) continue;                     // the assembly skips the contact
+      const int d = dl + ((!cpl && !(S->ckind[c] & 1)) ? NL : 0);
+      const float* Hc = S->cH[c];
+      const float j0 = S->J[c * 4 + 0][d], j1 = S->J[c * 4 + 1][d], j2 = S->J[c * 4 + 2][d], j3 = S->J[c * 4 + 3][d];
+      float v[4];
+      if (zone == 1) {                             // bottom zone: H_c = diag(D)
+        v[0] = Hc[tri(0, 0)] * j0; v[1] = Hc[tri(1, 1)] * j1; v[2] = Hc[tri(2, 2)] * j2; v[3] = Hc[tri(3, 3)] * j3;
+      } else {
 #pragma unroll
-      for (int l = 0; l < 4; l++) v = fmaf(Hc[l >= k ? tri(l, k) : tri(k, l)], S->J[c * 4 + l][d], v);
+        for (int k = 0; k < 4; k++) {
+          float a = 0;
+          a = fmaf(Hc[tri(k > 0 ? k : 0, 0)], j0, a);
+          a = fmaf(Hc[1 >= k ? tri(1, k) : tri(k, 1)], j1, a);
+          a = fmaf(Hc[2 >= k ? tri(2, k) : tri(k, 2)], j2, a);
+          a = fmaf(Hc[3 >= k ? tri(3, k) : tri(k, 3)], j3, a);
+          v[k] = a;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) S->T[c * 4 + k][d] = v[k];
     }
-    S->T[row][d] = v;
   }
   t.sync();
 }
-
-// contribution of contact c to Hessian entry (i, j)
 template <class ES> __device__ __forceinline__ float hess_contact(const ES* S, int c, int i, int j) {
   float h = 0;
 #pragma unroll
@@ -553,35 +569,34 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
   // contact loop inside the entry loop, made the assembly 3.0 k of the dense iteration's 14 k cycles.)
   constexpr int HR = LPE == 16 ? 3 : (DENSE ? 3 : 2);
   int hidx[HR];
-  float hbase[HR];
 #pragma unroll
   for (int k = 0; k < HR; k++) {
     const int e = lane + k * (int)LPE;
     int gi, gj, need, valid;
-    float b = 0.0f;
     if (coupled) {
       valid = e < 78;
       untri(valid ? e : 0, gi, gj);
-      if (gi < NL) b = S->d.Mfull[gi][gj];
-      else if (gi == gj) b = gi < 9 ? c_m.cube_mass : c_m.cube_I[gi - 9];
       need = (gi < NL ? 1 : 2) | (gj < NL ? 1 : 2);
     } else {
       valid = e < 42;
       const int ee = valid ? e : 0, blk = ee >= 21 ? 1 : 0, rr = ee - 21 * blk;
       const int i = tri_row6(rr), j = rr - tri(i, 0);
-      if (blk == 0) b = S->d.Mfull[i][j];
-      else if (i == j) b = i < 3 ? c_m.cube_mass : c_m.cube_I[i - 3];
       gi = i + NL * blk; gj = j + NL * blk;
       need = 1 << blk;
     }
     hidx[k] = gi | (gj << 4) | (need << 8) | (valid << 10) | ((gi == gj ? 1 : 0) << 11);
-    hbase[k] = b;
   }
   // S->H = M + diag(friction / limit curvature) + sum_c J_c^T (H_c J_c); entry e of lane `lane` is e = lane + k LPE
   auto assemble_hessian = [&]() {
     float h[HR];
 #pragma unroll
-    for (int k = 0; k < HR; k++) h[k] = hbase[k] + (((hidx[k] >> 11) & 1) ? S->hdiag[hidx[k] & 15] : 0.0f);
+    for (int k = 0; k < HR; k++) {
+      const int gi = hidx[k] & 15, gj = (hidx[k] >> 4) & 15;
+      float b = 0.0f;                                 // mass matrix: arm block dense, cube block diagonal, no coupling
+      if (gi < NL) b = S->d.Mfull[gi][gj];
+      else if ((hidx[k] >> 11) & 1) b = gi < 9 ? c_m.cube_mass : c_m.cube_I[gi - 9];
+      h[k] = b + (((hidx[k] >> 11) & 1) ? S->hdiag[gi] : 0.0f);
+    }
     for (int c = 0; c < ncon; c++) {
       if (S->czone[c] == 0) continue;
       const int kind = S->ckind[c];
