@@ -411,12 +411,6 @@ template <unsigned LPE, class ES> __device__ __forceinline__ void cone_hess_rows
   }
   t.sync();
 }
-template <class ES> __device__ __forceinline__ float hess_contact(const ES* S, int c, int i, int j) {
-  float h = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) h = fmaf(S->J[c * 4 + k][i], S->T[c * 4 + k][j], h);
-  return h;
-}
 
 // Newton direction -H^-1 g for a Hessian that couples the arm and the cube (a contact between them): dense 12x12.
 // Only the heavy solve kernel is compiled with it (solve<DENSE = true>): envs with an arm-cube contact are routed there, so the
