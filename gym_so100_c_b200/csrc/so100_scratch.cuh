@@ -238,6 +238,14 @@ template <unsigned LPE> __device__ __forceinline__ float tsum(const Tile<LPE>& t
   for (int off = LPE / 2; off > 0; off >>= 1) v += t.shfl_xor(v, off);
   return v;
 }
+template <unsigned LPE> __device__ __forceinline__ void tsum3(const Tile<LPE>& t, float& a, float& b, float& c) {
+#pragma unroll
+  for (int off = LPE / 2; off > 0; off >>= 1) {
+    a += t.shfl_xor(a, off);
+    b += t.shfl_xor(b, off);
+    c += t.shfl_xor(c, off);
+  }
+}
 template <unsigned LPE> __device__ __forceinline__ void tsum2(const Tile<LPE>& t, float& a, float& b) {
 #pragma unroll
   for (int off = LPE / 2; off > 0; off >>= 1) {

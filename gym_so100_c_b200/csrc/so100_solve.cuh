@@ -672,8 +672,7 @@ template <bool DENSE, unsigned LPE, class ES> __device__ int solve(const Tile<LP
     float Mp = 0;
     if (lane < NV) Mp = mul_M(S, S->vec, lane);
     float pMp = pd * Mp, pg = pd * (Ma - r.qfs), gp = pd * g;    // gp: phi'(0) = g . p
-    tsum2(t, pMp, pg);
-    gp = tsum(t, gp);
+    tsum3(t, pMp, pg, gp);       // one pass of shuffle rounds for the three sums
     const int nrow = ncon * 4;
 #pragma unroll
     for (int s = 0; s < Regs::RPL; s++) {
