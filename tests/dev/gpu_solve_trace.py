@@ -16,7 +16,8 @@ from gym_so100_c_b200.engine import BatchedSim  # noqa: E402
 src = os.path.join(ROOT, "gpurun_out", "caphits.npz")
 d = np.load(src if os.path.exists(src) else os.path.join(ROOT, "tests", "dev", "_scen", "caphits.npz"))
 lo = int(sys.argv[1]) if len(sys.argv) > 1 else 30
-sel = np.nonzero(d["iters"] >= lo)[0]
+hi = int(os.environ.get("HI", "1000"))
+sel = np.nonzero((d["iters"] >= lo) & (d["iters"] <= hi))[0]
 sel = sel[np.argsort(-d["iters"][sel])][:64]
 k = len(sel)
 pad = lambda a: np.concatenate([a[sel], np.repeat(a[sel][:1], 64 - k, 0)]).astype(np.float32)
