@@ -336,3 +336,28 @@ def test_box_manifold_matches_independent_clipping():
         multi += len(pos) >= 4
     print(f"box manifold check: {checked} face-face manifolds, {multi} with >= 4 points")
     assert checked >= 150 and multi >= 80
+
+
+def test_oracle_converges_quickly_on_the_float32_two_cycle_states(model_blob):
+    """The ten states of tests/golden/solver_two_cycle_states.npz made the float32 solver alternate between two points until the iteration
+    cap (tests/test_gpu_parity.py checks that it no longer does).  In fp64 they are ordinary solves: a few iterations at MuJoCo's
+    tolerances, and the tight checker tolerance reaches the same accelerations."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "solver_two_cycle_states.npz"))
+    k = d["qpos"].shape[0]
+    args = [d[n].astype(np.float64) for n in ("qpos", "qvel", "ctrl", "warm")]
+    qacc = {}
+    try:
+        for mode in (1, 0):
+            O.lib().so100o_set_solver_mode(mode)
+            orc = O.Oracle(model_blob, k)
+            orc.set_state(*args)
+            orc.forward()
+            its = np.array([orc.solver(i)["iters"] for i in range(k)])
+            qacc[mode] = np.array([orc.dyn(i)["qacc"] for i in range(k)])
+            if mode == 1:
+                assert its.max() <= 15, its
+            orc.close()
+    finally:
+        O.lib().so100o_set_solver_mode(0)
+    assert np.abs(qacc[0] - qacc[1]).max() / (1 + np.abs(qacc[0]).max()) < 1e-5
