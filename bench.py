@@ -208,6 +208,13 @@ def run_reference(args):
     return 0
 
 
+def settle_steps(sim, n, steps, gen, torch, dev):
+    """Untimed steps with FRESH U(-1,1) actions every step (a short cycle of repeated action sets settles into a calmer population:
+    1.29 instead of 1.37 Newton iterations per solve, 7 % faster steps at 131072 envs)."""
+    for _ in range(steps):
+        sim.step(torch.rand((n, 6), device=dev, generator=gen) * 2 - 1, autoreset=True)
+
+
 def timed_steps(sim, acts, first, count, flush, torch):
     """`count` steps from acts[first:], each bracketed by CUDA events on the launching stream, L2 flushed (untimed) before each."""
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(count)]
@@ -240,10 +247,7 @@ def run_gpu(args):
     acts = torch.rand((K + W, nl, 6), device=dev, generator=gen) * 2 - 1       # inputs resident in HBM
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
     # settle to the steady state of the workload first (always, independent of --warmup), then W warm-up steps
-    settle_acts = torch.rand((64, nl, 6), device=dev, generator=gen) * 2 - 1
-    for s in range(args.settle):
-        sim.step(settle_acts[s % 64], autoreset=True)
-    del settle_acts
+    settle_steps(sim, nl, args.settle, gen, torch, dev)
     for s in range(W):
         sim.step(acts[s], autoreset=True)
     torch.cuda.synchronize()
@@ -300,18 +304,21 @@ def run_gpu(args):
         lo5, _hi5 = parallel.shard_range(n5 * world, rank, world)
         sim5 = BatchedSim(n5, device=dev, task=0, seed=0x50100, env_offset=lo5)
         sim5.reset()
-        acts5 = torch.rand((32 + 10, n5, 6), device=dev, generator=gen) * 2 - 1      # 32 sets cycled while settling, 10 fresh ones timed
-        for s in range(args.settle):
-            sim5.step(acts5[s % 32], autoreset=True)
+        settle_steps(sim5, n5, args.settle, gen, torch, dev)
+        acts5 = torch.rand((10, n5, 6), device=dev, generator=gen) * 2 - 1
         torch.cuda.synchronize()
+        d50 = sim5.diagnostics()
         parallel.barrier()
-        ms5 = timed_steps(sim5, acts5, 32, 10, flush, torch)
+        ms5 = timed_steps(sim5, acts5, 0, 10, flush, torch)
+        d51 = sim5.diagnostics()
+        w5 = parallel.all_reduce_stats({k: d51[k] - d50[k] for k in d51}, device=dev)
         tot5 = parallel.max_over_ranks(float(sum(ms5)), device=dev)
         rank5 = parallel.gather_floats(float(sum(ms5)) / 10, device=dev)
         sim5.close()
         extra["config5_1M_envs_over_8_gpus_shard"] = {
             "envs_per_gpu": n5, "envs_total": n5 * world, "steps": 10, "settle_steps": args.settle, "ms_per_step": tot5 / 10,
-            "value": n5 * world * 10 / (tot5 * 1e-3), "unit": "env-steps/s", "rank_ms_per_step": rank5, "l2": "flushed between timed steps"}
+            "value": n5 * world * 10 / (tot5 * 1e-3), "unit": "env-steps/s", "rank_ms_per_step": rank5, "l2": "flushed between timed steps",
+            "contacts_per_solve": w5["contacts_seen"] / max(w5["solver_runs"], 1), "newton_iters_per_solve": w5["newton_iters"] / max(w5["solver_runs"], 1)}
     if world == 1 and not args.no_extra:
         # ---- BASELINE config 4: 65536 GoalEnv envs (dict observation pieces) driving a device-resident SAC+HER rollout: every
         # step the transition goes into the HER replay ring and a batch of 65536 x n_sampled_goal = 4 relabelled goals gets its
@@ -325,14 +332,14 @@ def run_gpu(args):
         # de-synchronise the episodes (every env would otherwise be truncated and reset at the same step 300, and the timed window
         # right after it would see 65536 cubes landing at once): start each env at a random point of its 300-step episode
         env4.sim.set_aux(step_count=torch.randint(0, 300, (n4,), dtype=torch.int32))
-        acts4 = torch.rand((32 + 10, n4, 6), device=dev, generator=gen) * 2 - 1
         for s in range(310):                                        # every env finishes at least one episode: the ring has finished episodes to sample
-            roll.step(acts4[s % 32])
+            roll.step(torch.rand((n4, 6), device=dev, generator=gen) * 2 - 1)       # fresh actions every step (see settle_steps)
+        acts4 = torch.rand((10, n4, 6), device=dev, generator=gen) * 2 - 1
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for s in range(10):
-            roll.step(acts4[32 + s])
+            roll.step(acts4[s])
             batch = roll.sample(5 * n4)             # n4 real + 4 x n4 "future"-relabelled transitions (n_sampled_goal = 4), rewards recomputed
         e1.record()
         torch.cuda.synchronize()
