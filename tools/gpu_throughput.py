@@ -20,7 +20,9 @@ def main():
     if len(sys.argv) > 3 and sys.argv[3] == "mix":
         return mix(sim, n, steps, acts)
     for s in range(int(os.environ.get("WARM", "150"))):       # settle: the bench workload's steady state needs ~150 steps
-        sim.step(acts[s % 20])
+        # fresh actions every step, like bench.py (CYCLE=1: the old cycle of 20 action sets, a calmer population: numbers quoted as
+        # "back to back" in DESIGN.md section 5 before item 17c's correction were taken that way)
+        sim.step(acts[s % 20] if os.environ.get("CYCLE") == "1" else torch.rand((n, 6), device="cuda", generator=g) * 2 - 1)
     torch.cuda.synchronize()
     if os.environ.get("FLUSH") == "1":       # bench.py's timing: L2 flushed before every step, each step bracketed by its own event pair
         flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
