@@ -335,6 +335,7 @@ def run_gpu(args):
         for s in range(310):                                        # every env finishes at least one episode: the ring has finished episodes to sample
             roll.step(torch.rand((n4, 6), device=dev, generator=gen) * 2 - 1)       # fresh actions every step (see settle_steps)
         acts4 = torch.rand((10, n4, 6), device=dev, generator=gen) * 2 - 1
+        roll.sample(5 * n4)                          # untimed: the first call allocates the batch tensors (0.3 - 10 ms, once)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
